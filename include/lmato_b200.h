@@ -1,0 +1,145 @@
+/* lmato_b200.h -- C ABI of the B200-native batched lunar-ascent trajectory optimiser.
+ *
+ * Drop-in boundary for ONE hot path of the reference: the GEKKO/IPOPT solve
+ *     m.solve(disp=True)                      /root/reference/Launch_Optimiser.py:177
+ * together with the model declaration that feeds it (LO:19-176) and the `.value`
+ * read-back that follows it (LO:178-202).  The reference has no FFI of its own (the
+ * boundary there is a Python object API over a process boundary to the `apm`
+ * executable); INTEGRATION.md shows the ctypes binding a maintainer of the reference
+ * would add.  Everything here is plain C: pointers, sizes, ints.  No exceptions cross
+ * this boundary; every function returns an lmato_status_t and lmato_last_error() gives
+ * the text of the last failure on the calling thread.
+ *
+ * Threading: a handle is bound to one CUDA device and must be used from one host thread
+ * at a time.  Distinct handles are independent.  Ownership: the caller owns every
+ * input/output buffer; the library owns only the workspace inside the handle.
+ */
+#ifndef LMATO_B200_H
+#define LMATO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lmato_handle lmato_handle;
+
+typedef enum {
+  LMATO_OK = 0,
+  LMATO_ERR_INVALID = 1,     /* bad argument */
+  LMATO_ERR_CUDA = 2,        /* CUDA runtime failure (text in lmato_last_error) */
+  LMATO_ERR_NO_DEVICE = 3,   /* no usable CUDA device: there is NO CPU fallback */
+  LMATO_ERR_UNSUPPORTED = 4  /* model / NODES combination not implemented */
+} lmato_status_t;
+
+/* Model variants.  ELLIPTICAL = Launch_Optimiser.py as shipped (LO:83-173);
+ * CIRCULAR = the "original IB-document" model (reference PDF p.26-28). */
+typedef enum { LMATO_MODEL_ELLIPTICAL = 0, LMATO_MODEL_CIRCULAR = 1 } lmato_model_t;
+
+/* Per-problem parameter rows of the `params` array, shape [LMATO_NPARAM][B], row-major
+ * (struct of arrays: row p, problem b at params[p*B + b]).  Names and defaults are the
+ * reference's literals. */
+enum {
+  LMATO_P_G = 0,                 /* LO:50  6.674e-11 */
+  LMATO_P_M = 1,                 /* LO:51  7.346e22  */
+  LMATO_P_R0 = 2,                /* LO:52  1738100   */
+  LMATO_P_FT = 3,                /* LO:61  15346     */
+  LMATO_P_M0 = 4,                /* LO:62  4821      */
+  LMATO_P_M_DOT = 5,             /* LO:63/65  5.053  */
+  LMATO_P_FUEL_MASS = 6,         /* LO:64  2376      */
+  LMATO_P_ANGLE_DOUBLEDOT_MAX = 7,  /* LO:66  5e-4   */
+  LMATO_P_R_PERIAPSIS = 8,       /* LO:70  17703     */
+  LMATO_P_R_APOAPSIS = 9,        /* LO:71  88615     */
+  LMATO_P_FINAL_TIME = 10,       /* LO:38  470       */
+  LMATO_P_MASS_SCALAR = 11,      /* LO:108 = fuel_mass (2576 in the PDF original) */
+  LMATO_P_ANGLE_UB = 12,         /* LO:94  pi/3      */
+  LMATO_P_U_BOUND = 13,          /* LO:96  1         */
+  LMATO_NPARAM = 14
+};
+
+/* Rows of the output trajectory, shape [LMATO_NVAR][nt][B]; GEKKO declaration order
+ * (LO:83-96).  Scaled units, exactly as the reference's `.value` lists (LO:188-202);
+ * node 0 holds the pinned initial values (all zero). */
+enum {
+  LMATO_V_Y = 0, LMATO_V_YDOT = 1, LMATO_V_YDOUBLEDOT = 2,
+  LMATO_V_X = 3, LMATO_V_XDOT = 4, LMATO_V_XDOUBLEDOT = 5,
+  LMATO_V_ANGLE = 6, LMATO_V_ANGLEDOT = 7, LMATO_V_MASS = 8,
+  LMATO_V_ANGLEDOUBLEDOT = 9,
+  LMATO_NVAR = 10
+};
+
+/* Per-problem solve status (not an error of the call). */
+enum {
+  LMATO_ST_CONVERGED = 0,        /* scaled KKT error <= tol */
+  LMATO_ST_MAX_ITER = 1,         /* MAX_ITER reached (LO:28) */
+  LMATO_ST_LINESEARCH_FAIL = 2,  /* filter line search could not make progress */
+  LMATO_ST_INERTIA_FAIL = 3,     /* KKT inertia could not be corrected */
+  LMATO_ST_NUMERICAL = 4         /* NaN/Inf encountered */
+};
+
+typedef struct {
+  double tol;        /* scaled KKT tolerance (IPOPT `tol`); default 1e-8 */
+  double mu_init;    /* initial barrier parameter; default 0.1 */
+  double obj_scale;  /* objective = obj_scale * tf; default 10 */
+  double tf_guess;   /* initial scaled final time; default 0.9 */
+  double delta_c;    /* dual regularisation of the terminal equality row; default 1e-8 */
+  int32_t max_iter;  /* LO:28 MAX_ITER; default 20000 (the reference's value) */
+  int32_t max_ls;    /* max backtracking steps per iteration; default 40 */
+} lmato_options;
+
+/* Fill `o` with the defaults above. */
+void lmato_default_options(lmato_options* o);
+
+/* Create a solver for one device and one mesh.
+ *   device  CUDA ordinal
+ *   nt      number of mesh nodes (LO:20, 200)
+ *   time    host pointer to nt normalised times in [0,1], strictly increasing, time[0]=0
+ *           (LO:21); NULL = linspace(0,1,nt)
+ *   nodes   collocation NODES (LO:25); 2 is implemented on the device
+ *   model   lmato_model_t
+ * Replaces: GEKKO() + m.time + m.options.* (LO:19-33). */
+lmato_status_t lmato_create(lmato_handle** out, int32_t device, int32_t nt, const double* time,
+                            int32_t nodes, int32_t model);
+lmato_status_t lmato_destroy(lmato_handle* h);
+lmato_status_t lmato_set_options(lmato_handle* h, const lmato_options* o);
+
+/* Solve B independent ascent problems.  All pointers are DEVICE pointers on the handle's
+ * device; `stream` is a cudaStream_t (NULL = default stream).  Asynchronous with respect
+ * to the host: results are valid after the stream is synchronised.
+ *   params        [LMATO_NPARAM][B]
+ *   out_traj      [LMATO_NVAR][nt][B] or NULL
+ *   out_tf        [B]   scaled final time in (0,1)  (tf.value[0], LO:178)
+ *   out_final_mass[B]   kg:  M0 - fuel_mass * mass(nt-1)
+ *   out_status    [B]   LMATO_ST_*
+ *   out_iters     [B]   IPM iterations used
+ *   out_kkt       [B]   final scaled KKT error, or NULL
+ * Replaces: m.solve() (LO:177) and the read-back LO:178-202. */
+lmato_status_t lmato_solve_batch(lmato_handle* h, const double* params, int64_t B,
+                                 double* out_traj, double* out_tf, double* out_final_mass,
+                                 int32_t* out_status, int32_t* out_iters, double* out_kkt,
+                                 void* stream);
+
+/* Same with HOST buffers: copies params to the device, solves, copies results back and
+ * synchronises.  This is the end-to-end call the Python API makes for host tensors. */
+lmato_status_t lmato_solve_batch_host(lmato_handle* h, const double* params, int64_t B,
+                                      double* out_traj, double* out_tf, double* out_final_mass,
+                                      int32_t* out_status, int32_t* out_iters, double* out_kkt);
+
+/* Introspection (for benchmarks and tests). */
+lmato_status_t lmato_workspace_bytes(lmato_handle* h, int64_t B, int64_t* bytes);
+lmato_status_t lmato_kernel_launches(lmato_handle* h, int64_t* n);  /* launches so far */
+/* Device time of the last lmato_solve_batch IPM kernel in milliseconds (CUDA events on
+ * the launching stream); synchronises that stream. */
+lmato_status_t lmato_last_kernel_ms(lmato_handle* h, double* ms);
+/* Measured FP64 FMA peak of the handle's device in GFLOP/s (dependent-chain-free DFMA
+ * micro-benchmark; used as the roofline denominator, MEASURED_PEAKS.json has no FP64). */
+lmato_status_t lmato_measure_fp64_peak(lmato_handle* h, double* gflops);
+
+const char* lmato_last_error(void);
+const char* lmato_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LMATO_B200_H */

@@ -1,0 +1,422 @@
+"""Python API: ``optimise()`` / ``optimise_batch()``.
+
+Drop-in for the model that ``Launch_Optimiser.py`` declares and solves (LO:19-202 of
+/root/reference/Launch_Optimiser.py): the same physical parameters, mesh and options go
+in; the same ``tf``, per-node state lists, control and final mass come out, in the same
+scaled units the reference's ``.value`` lists use.
+
+    reference                                   here
+    ---------                                   ----
+    G_py, M_py, R0_py            (LO:50-52)     AscentParams.G, .M, .R0
+    Ft, M0, M_dot, fuel_mass     (LO:61-65)     AscentParams.Ft, .M0, .M_dot, .fuel_mass
+    angle_doubledot_max          (LO:66)        AscentParams.angle_doubledot_max
+    r_periapsis, r_apoapsis      (LO:70-71)     AscentParams.r_periapsis, .r_apoapsis
+    final_time                   (LO:38)        AscentParams.final_time
+    nt, m.time, m.options.NODES  (LO:20-25)     Mesh.nt, .time, .nodes
+    m.options.MAX_ITER/OTOL/RTOL (LO:28-32)     SolverOptions.max_iter, .otol, .rtol
+    m.solve()                    (LO:177)       optimise() / optimise_batch()
+    tf.value[0]                  (LO:178)       solution.tf
+    y.value, x.value, ...        (LO:188-202)   solution.states["y"], ...  ([B, nt])
+    failure -> Exception         (LO:177)       optimise(): raises; optimise_batch(): status[b]
+
+Host code is Python; all numerical work happens in hand-written sm_100a CUDA kernels
+behind the C ABI of ``include/lmato_b200.h`` (ctypes).  PyTorch provides device memory,
+streams and ``torch.distributed`` only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+import math
+from typing import Callable, Dict, Optional, Sequence, Union
+
+import torch
+
+from . import _cabi
+
+Scalar = Union[float, int, torch.Tensor]
+
+G_ISP = 9.807   # reference PDF p.6:  M_dot = Ft / (Isp * 9.807)
+
+
+@dataclasses.dataclass
+class AscentParams:
+    """Physical parameters, reference names and defaults.  Every field may be a python
+    float (shared by the whole batch) or a float64 tensor of shape ``[B]``."""
+
+    G: Scalar = 6.674e-11                 # LO:50
+    M: Scalar = 7.346e22                  # LO:51
+    R0: Scalar = 1738100.0                # LO:52
+    Ft: Scalar = 15346.0                  # LO:61
+    M0: Scalar = 4821.0                   # LO:62
+    M_dot: Scalar = 5.053                 # LO:63 (the literal used in mflow, LO:65)
+    fuel_mass: Scalar = 2376.0            # LO:64
+    angle_doubledot_max: Scalar = 5e-4    # LO:66
+    r_periapsis: Scalar = 17703.0         # LO:70
+    r_apoapsis: Scalar = 88615.0          # LO:71
+    final_time: Scalar = 470.0            # LO:38
+    model: str = "elliptical"             # "elliptical" | "circular" (reference PDF p.26-28)
+    Isp: Optional[Scalar] = None          # if given, M_dot = Ft/(Isp*9.807) (PDF p.6)
+    mass_scalar: Optional[Scalar] = None  # LO:108 (= fuel_mass); 2576 in the PDF original
+    angle_ub: Scalar = math.pi / 3        # LO:94
+    u_bound: Scalar = 1.0                 # LO:96
+    dcost: float = 1e-5                   # LO:99 (accepted; see DESIGN.md "DCOST")
+
+    @staticmethod
+    def circular() -> "AscentParams":
+        """The 'original IB-document' model (reference PDF p.26 src 32-46, p.27 src 66-67)."""
+        return AscentParams(r_periapsis=53108.4, r_apoapsis=53108.4, model="circular",
+                            mass_scalar=2576.0)
+
+    def batch_size(self) -> Optional[int]:
+        B = None
+        for f in dataclasses.fields(self):
+            v = getattr(self, f.name)
+            if isinstance(v, torch.Tensor) and v.dim() > 0:
+                if v.dim() != 1:
+                    raise ValueError(f"AscentParams.{f.name}: expected shape [B], got {tuple(v.shape)}")
+                if B is not None and v.shape[0] != B:
+                    raise ValueError(f"AscentParams.{f.name}: batch {v.shape[0]} != {B}")
+                B = v.shape[0]
+        return B
+
+    def rows(self, B: Optional[int] = None, device: Union[str, torch.device] = "cpu") -> torch.Tensor:
+        """Pack into the C ABI's ``[LMATO_NPARAM][B]`` struct-of-arrays block (float64)."""
+        Bt = self.batch_size()
+        if B is None:
+            B = 1 if Bt is None else Bt
+        elif Bt is not None and Bt != B:
+            raise ValueError(f"batch size mismatch: tensors have {Bt}, requested {B}")
+        vals = {}
+        for name in _cabi.PARAM_ROWS:
+            vals[name] = getattr(self, name)
+        if self.Isp is not None:
+            vals["M_dot"] = _t(self.Ft, device) / (_t(self.Isp, device) * G_ISP)
+        if self.mass_scalar is None:
+            vals["mass_scalar"] = self.fuel_mass
+        out = torch.empty((_cabi.NPARAM, B), dtype=torch.float64, device=device)
+        for i, name in enumerate(_cabi.PARAM_ROWS):
+            out[i] = _t(vals[name], device)
+        return out
+
+
+def _t(v: Scalar, device) -> torch.Tensor:
+    if isinstance(v, torch.Tensor):
+        return v.to(device=device, dtype=torch.float64)
+    return torch.tensor(float(v), dtype=torch.float64, device=device)
+
+
+@dataclasses.dataclass
+class Mesh:
+    """LO:20-25: ``nt`` nodes on normalised time, GEKKO ``NODES`` per step."""
+    nt: int = 200
+    time: Optional[Sequence[float]] = None    # explicit m.time (overrides nt)
+    nodes: int = 2
+
+    def grid(self) -> torch.Tensor:
+        if self.time is not None:
+            t = torch.as_tensor(self.time, dtype=torch.float64).flatten().cpu()
+            return t
+        return torch.linspace(0.0, 1.0, self.nt, dtype=torch.float64)   # LO:21
+
+
+@dataclasses.dataclass
+class SolverOptions:
+    """LO:26-33 plus solver-native knobs."""
+    max_iter: int = 20000          # LO:28
+    otol: float = 1e-3             # LO:31 (recorded; the device IPM converges to `tol`)
+    rtol: float = 1e-3             # LO:32
+    tol: float = 1e-8              # scaled KKT error at which a problem counts as converged
+    mu_init: float = 0.1
+    obj_scale: float = 10.0
+    tf_guess: float = 0.9
+    delta_c: float = 1e-8
+    max_ls: int = 40
+
+
+@dataclasses.dataclass
+class AscentBatchSolution:
+    tf: torch.Tensor                 # [B] scaled final time (tf.value[0], LO:178)
+    tf_seconds: torch.Tensor         # [B] tf * final_time (LO:194)
+    states: Dict[str, torch.Tensor]  # name -> [B, nt], reference `.value` lists, scaled units
+    control: Optional[torch.Tensor]  # [B, nt] angledoubledot (node 0 = 0)
+    final_mass: torch.Tensor         # [B] kg
+    status: torch.Tensor             # [B] int32, 0 = converged
+    iterations: torch.Tensor         # [B] int32
+    kkt_error: torch.Tensor          # [B]
+    time: torch.Tensor               # [nt] normalised mesh (m.time)
+
+    @property
+    def converged(self) -> torch.Tensor:
+        return self.status == 0
+
+    def __len__(self) -> int:
+        return int(self.tf.shape[0])
+
+
+@dataclasses.dataclass
+class AscentSolution:
+    tf: float
+    tf_seconds: float
+    states: Dict[str, torch.Tensor]  # name -> [nt]
+    control: torch.Tensor            # [nt]
+    final_mass: float
+    status: int
+    iterations: int
+    kkt_error: float
+    time: torch.Tensor
+
+
+class AscentSolver:
+    """Owns one C-ABI handle: one device, one mesh, one model."""
+
+    def __init__(self, mesh: Optional[Mesh] = None, options: Optional[SolverOptions] = None,
+                 device: Union[int, str, torch.device, None] = None, model: str = "elliptical"):
+        self.mesh = mesh or Mesh()
+        self.options = options or SolverOptions()
+        L = _cabi.lib()
+        if not torch.cuda.is_available():
+            raise _cabi.LmatoError("no CUDA device: the solver has no CPU fallback")
+        if device is None:
+            device = torch.cuda.current_device()
+        dev = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
+        self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
+        self.time = self.mesh.grid()
+        self.nt = int(self.time.shape[0])
+        model_id = {"elliptical": 0, "circular": 1}.get(model)
+        if model_id is None:
+            raise ValueError(f"unknown model {model!r}")
+        self._h = C.c_void_p()
+        tbuf = (C.c_double * self.nt)(*self.time.tolist())
+        _cabi.check(L.lmato_create(C.byref(self._h), self.device.index, self.nt,
+                                   C.cast(tbuf, C.c_void_p), int(self.mesh.nodes), model_id), "lmato_create")
+        self.set_options(self.options)
+
+    def set_options(self, o: SolverOptions) -> None:
+        co = _cabi.LmatoOptions(tol=o.tol, mu_init=o.mu_init, obj_scale=o.obj_scale, tf_guess=o.tf_guess,
+                                delta_c=o.delta_c, max_iter=int(o.max_iter), max_ls=int(o.max_ls))
+        _cabi.check(_cabi.lib().lmato_set_options(self._h, C.byref(co)), "lmato_set_options")
+        self.options = o
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _cabi.lib().lmato_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- raw entry points ---------------------------------------------------------------
+    def solve_rows(self, rows: torch.Tensor, trajectories: bool = True) -> Dict[str, torch.Tensor]:
+        """``rows``: ``[NPARAM, B]`` float64.  CUDA tensor -> device entry point, results stay on
+        the device (asynchronous on the current stream).  CPU tensor -> host entry point
+        (H2D + solve + D2H, synchronous), results in pinned host memory."""
+        L = _cabi.lib()
+        if rows.dtype != torch.float64 or rows.dim() != 2 or rows.shape[0] != _cabi.NPARAM:
+            raise ValueError("rows must be float64 [NPARAM, B]")
+        rows = rows.contiguous()
+        B = int(rows.shape[1])
+        on_dev = rows.is_cuda
+        if on_dev and rows.device != self.device:
+            raise ValueError(f"rows live on {rows.device}, solver on {self.device}")
+        kw = dict(device=self.device) if on_dev else dict(pin_memory=True)
+        out = {
+            "traj": torch.empty((_cabi.NVAR, self.nt, B), dtype=torch.float64, **kw) if trajectories else None,
+            "tf": torch.empty(B, dtype=torch.float64, **kw),
+            "final_mass": torch.empty(B, dtype=torch.float64, **kw),
+            "status": torch.empty(B, dtype=torch.int32, **kw),
+            "iterations": torch.empty(B, dtype=torch.int32, **kw),
+            "kkt": torch.empty(B, dtype=torch.float64, **kw),
+        }
+        if B == 0:
+            return out
+        ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p()
+        if on_dev:
+            with torch.cuda.device(self.device):
+                stream = torch.cuda.current_stream(self.device).cuda_stream
+                _cabi.check(L.lmato_solve_batch(self._h, ptr(rows), B, ptr(out["traj"]), ptr(out["tf"]),
+                                                ptr(out["final_mass"]), ptr(out["status"]),
+                                                ptr(out["iterations"]), ptr(out["kkt"]),
+                                                C.c_void_p(stream)), "lmato_solve_batch")
+        else:
+            _cabi.check(L.lmato_solve_batch_host(self._h, ptr(rows), B, ptr(out["traj"]), ptr(out["tf"]),
+                                                 ptr(out["final_mass"]), ptr(out["status"]),
+                                                 ptr(out["iterations"]), ptr(out["kkt"])),
+                        "lmato_solve_batch_host")
+        return out
+
+    def last_kernel_ms(self) -> float:
+        ms = C.c_double()
+        _cabi.check(_cabi.lib().lmato_last_kernel_ms(self._h, C.byref(ms)), "lmato_last_kernel_ms")
+        return ms.value
+
+    def kernel_launches(self) -> int:
+        n = C.c_int64()
+        _cabi.check(_cabi.lib().lmato_kernel_launches(self._h, C.byref(n)), "lmato_kernel_launches")
+        return n.value
+
+    def workspace_bytes(self, B: int) -> int:
+        n = C.c_int64()
+        _cabi.check(_cabi.lib().lmato_workspace_bytes(self._h, B, C.byref(n)), "lmato_workspace_bytes")
+        return n.value
+
+    def measure_fp64_peak(self) -> float:
+        g = C.c_double()
+        _cabi.check(_cabi.lib().lmato_measure_fp64_peak(self._h, C.byref(g)), "lmato_measure_fp64_peak")
+        return g.value
+
+    # -- packaged result ----------------------------------------------------------------
+    def solve(self, params: AscentParams, B: Optional[int] = None, trajectories: bool = True,
+              on_device: bool = False) -> AscentBatchSolution:
+        rows = params.rows(B, device=self.device if on_device else "cpu")
+        if not on_device:
+            rows = rows.pin_memory()
+        raw = self.solve_rows(rows, trajectories)
+        return package_solution(raw, rows, self.time)
+
+
+def package_solution(raw: Dict[str, torch.Tensor], rows: torch.Tensor, time: torch.Tensor) -> AscentBatchSolution:
+    traj = raw["traj"]
+    states: Dict[str, torch.Tensor] = {}
+    control = None
+    if traj is not None:
+        for i, name in enumerate(_cabi.VAR_ROWS):
+            states[name] = traj[i].transpose(0, 1)      # [B, nt] view
+        control = states.pop("angledoubledot")
+    T = rows[_cabi.PARAM_ROWS.index("final_time")]
+    return AscentBatchSolution(tf=raw["tf"], tf_seconds=raw["tf"] * T.to(raw["tf"].device), states=states,
+                               control=control, final_mass=raw["final_mass"], status=raw["status"],
+                               iterations=raw["iterations"], kkt_error=raw["kkt"], time=time)
+
+
+# ---------------------------------------------------------------------------------------
+# index-partitioned multi-GPU solve: problem i -> rank floor(i*G/B); ONE allgather at the end
+# ---------------------------------------------------------------------------------------
+def shard_bounds(B: int, world: int, rank: int):
+    """Contiguous index ranges, sizes differ by at most one."""
+    lo = (B * rank) // world
+    hi = (B * (rank + 1)) // world
+    return lo, hi
+
+
+def sharded_solve(rows: torch.Tensor, solve_fn: Callable[[torch.Tensor], Dict[str, torch.Tensor]],
+                  group=None, gather: bool = True) -> Dict[str, torch.Tensor]:
+    """Every rank holds the full ``rows`` block; rank r solves its contiguous shard with
+    ``solve_fn`` and a single ``all_gather`` (NCCL over NVLink on GPUs, gloo in the CPU tests)
+    reassembles the per-problem results on every rank.  No per-iteration collectives: the
+    problems are independent."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    B = int(rows.shape[1])
+    lo, hi = shard_bounds(B, world, rank)
+    local = solve_fn(rows[:, lo:hi].contiguous())
+    if not gather:
+        return local
+    per = (B + world - 1) // world
+    keys = [k for k, v in local.items() if v is not None]
+    # pack every result into one float64 buffer [per, width] so that one collective suffices
+    cols = []
+    for k in keys:
+        v = local[k]
+        if k == "traj":
+            v = v.permute(2, 0, 1).reshape(hi - lo, -1)
+        else:
+            v = v.reshape(hi - lo, 1)
+        cols.append(v.to(torch.float64))
+    packed = torch.cat(cols, dim=1)
+    width = packed.shape[1]
+    send = torch.zeros((per, width), dtype=torch.float64, device=packed.device)
+    send[: hi - lo] = packed
+    recv = torch.empty((world * per, width), dtype=torch.float64, device=packed.device)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    pieces = []
+    for r in range(world):
+        l, h = shard_bounds(B, world, r)
+        pieces.append(recv[r * per: r * per + (h - l)])
+    full = torch.cat(pieces, dim=0)
+    out: Dict[str, torch.Tensor] = {k: None for k in local}
+    c = 0
+    for k in keys:
+        v = local[k]
+        if k == "traj":
+            w = v.shape[0] * v.shape[1]
+            out[k] = full[:, c: c + w].reshape(B, v.shape[0], v.shape[1]).permute(1, 2, 0).contiguous()
+        else:
+            w = 1
+            out[k] = full[:, c].to(v.dtype)
+        c += w
+    return out
+
+
+# ---------------------------------------------------------------------------------------
+# public functions
+# ---------------------------------------------------------------------------------------
+_solver_cache: Dict[tuple, AscentSolver] = {}
+
+
+def _get_solver(mesh: Mesh, options: SolverOptions, device, model: str) -> AscentSolver:
+    if device is None:
+        device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+    dev = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
+    key = (dev.index or 0, tuple(mesh.grid().tolist()), mesh.nodes, model)
+    s = _solver_cache.get(key)
+    if s is None:
+        s = AscentSolver(mesh, options, dev, model)
+        _solver_cache[key] = s
+    else:
+        s.set_options(options)
+    return s
+
+
+def optimise_batch(params: AscentParams, mesh: Optional[Mesh] = None,
+                   options: Optional[SolverOptions] = None, device=None, batch: Optional[int] = None,
+                   trajectories: bool = True, group=None) -> AscentBatchSolution:
+    """Solve a batch of ascent problems (one per entry of the ``[B]`` parameter tensors).
+
+    Results follow the placement of the inputs: CPU parameter tensors (or plain floats) give
+    pinned CPU result tensors (host->device and device->host copies are part of the call);
+    CUDA parameter tensors give CUDA results without any host transfer.
+
+    ``group``: a ``torch.distributed`` process group (or ``True`` for the default group).  Every
+    rank passes the same full batch; rank r solves the contiguous index shard
+    ``[B*r/G, B*(r+1)/G)`` on its own GPU and one allgather returns the full result everywhere.
+    """
+    mesh = mesh or Mesh()
+    options = options or SolverOptions()
+    on_dev = any(isinstance(getattr(params, f.name), torch.Tensor) and getattr(params, f.name).is_cuda
+                 for f in dataclasses.fields(params))
+    solver = _get_solver(mesh, options, device, params.model)
+    rows = params.rows(batch, device=solver.device if on_dev else "cpu")
+    if group is not None:
+        import torch.distributed as dist
+        g = None if group is True else group
+        dev_rows = rows.to(solver.device)
+        raw = sharded_solve(dev_rows, lambda r: solver.solve_rows(r, trajectories), g)
+        if not on_dev:
+            raw = {k: (v.cpu() if v is not None else None) for k, v in raw.items()}
+        return package_solution(raw, rows, solver.time)
+    if not on_dev:
+        rows = rows.pin_memory()
+    raw = solver.solve_rows(rows, trajectories)
+    return package_solution(raw, rows, solver.time)
+
+
+def optimise(params: Optional[AscentParams] = None, mesh: Optional[Mesh] = None,
+             options: Optional[SolverOptions] = None, device=None) -> AscentSolution:
+    """Solve one ascent problem; the single-instance twin of the reference script.
+    Raises ``LmatoError`` if the solver does not converge (the reference raises a bare
+    ``Exception`` from ``m.solve``, LO:177)."""
+    params = params or AscentParams()
+    sol = optimise_batch(params, mesh, options, device, batch=1)
+    st = int(sol.status[0])
+    if st != 0:
+        raise _cabi.LmatoError(f"@error: Solution Not Found (status {st}: {_cabi.STATUS_NAMES.get(st, '?')}, "
+                               f"kkt error {float(sol.kkt_error[0]):.3e} after {int(sol.iterations[0])} iterations)")
+    return AscentSolution(tf=float(sol.tf[0]), tf_seconds=float(sol.tf_seconds[0]),
+                          states={k: v[0].clone() for k, v in sol.states.items()},
+                          control=sol.control[0].clone(), final_mass=float(sol.final_mass[0]), status=st,
+                          iterations=int(sol.iterations[0]), kkt_error=float(sol.kkt_error[0]), time=sol.time)

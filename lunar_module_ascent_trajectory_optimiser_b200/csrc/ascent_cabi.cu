@@ -1,0 +1,410 @@
+// C ABI + kernels of the batched ascent solver (sm_100a).  See include/lmato_b200.h.
+//
+// Kernel mapping: ONE PROBLEM PER THREAD, persistent warps.  A warp claims 32 consecutive
+// problems from a device-side counter, solves them to convergence without returning to the
+// host (barrier updates, fraction-to-boundary, filter line search and convergence masks all
+// live in registers/local memory of the owning thread), writes the results and claims the
+// next 32.  The stage data of a problem is far too large for registers (90 doubles x nt), so
+// it streams through a struct-of-arrays workspace in HBM indexed [field][stage][slot]; the 32
+// lanes of a warp own 32 consecutive slots, so every access is a fully coalesced 256-byte
+// transaction.  Tensor cores are not used: the stage blocks are 7x7 FP64 and the recursion
+// over stages is sequential (see DESIGN.md for the roofline argument).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+#include <new>
+#include <vector>
+
+#include "../../include/lmato_b200.h"
+#include "ascent_ipm.cuh"
+
+using namespace lmato;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+void set_err(const char* fmt, const char* a = "", const char* b = "") {
+  snprintf(g_err, sizeof(g_err), fmt, a, b);
+}
+
+#define CUDA_TRY(expr)                                                        \
+  do {                                                                        \
+    cudaError_t e__ = (expr);                                                 \
+    if (e__ != cudaSuccess) {                                                 \
+      set_err("CUDA error: %s at %s", cudaGetErrorString(e__), #expr);        \
+      return LMATO_ERR_CUDA;                                                  \
+    }                                                                         \
+  } while (0)
+
+constexpr int kBlock = 64;          // threads per CTA (2 warps)
+constexpr int kBlocksPerSM = 4;     // 256 threads/SM at <=255 registers
+
+struct KArgs {
+  const double* params;  // [NPARAM][B]
+  long B;
+  double* traj;          // [NVAR][nt][B] or null
+  double* tf;
+  double* fmass;
+  int* status;
+  int* iters;
+  double* kkt;
+  double* ws;            // [N_FIELDS][N+1][slots]
+  long slots;
+  int N;
+  const double* h;
+  const double* tau;
+  int* counter;
+  Options O;
+};
+
+__device__ __forceinline__ Params derive_params(const double* __restrict__ p, long B, long b) {
+  // LO:50-75, 107-109
+  Params P;
+  const double G = p[LMATO_P_G * B + b], Mm = p[LMATO_P_M * B + b];
+  const double R0 = p[LMATO_P_R0 * B + b];
+  const double fuel = p[LMATO_P_FUEL_MASS * B + b];
+  const double rp = p[LMATO_P_R_PERIAPSIS * B + b], ra = p[LMATO_P_R_APOAPSIS * B + b];
+  P.GM = G * Mm;
+  P.R0 = R0;
+  P.Ft = p[LMATO_P_FT * B + b];
+  P.M0 = p[LMATO_P_M0 * B + b];
+  P.S = rp;
+  P.ms = p[LMATO_P_MASS_SCALAR * B + b];
+  P.mflow = p[LMATO_P_M_DOT * B + b] / fuel;
+  P.asc = p[LMATO_P_ANGLE_DOUBLEDOT_MAX * B + b] / 3.0;
+  P.T = p[LMATO_P_FINAL_TIME * B + b];
+  P.a_ub = p[LMATO_P_ANGLE_UB * B + b];
+  P.u_ub = p[LMATO_P_U_BOUND * B + b];
+  const double vt = sqrt(P.GM / (R0 + 0.5 * (rp + ra)));
+  P.vt2 = (vt / P.S) * (vt / P.S);
+  P.rt = (R0 + P.S) / P.S;
+  P.R0S = R0 / P.S;
+  P.tf_ub = fmin(1.0, 1.0 / (P.mflow * P.T));
+  P.fuel = fuel;
+  return P;
+}
+
+__global__ void __launch_bounds__(kBlock, kBlocksPerSM) ascent_ipm_kernel(KArgs a) {
+  const long slot = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const Mesh M{a.N, a.h, a.tau};
+  const Ws W{a.ws, a.slots, a.N + 1, slot};
+  const int nt = a.N + 1;
+  while (true) {
+    int chunk = 0;
+    if (lane == 0) chunk = atomicAdd(a.counter, 1);
+    chunk = __shfl_sync(0xffffffffu, chunk, 0);
+    const long b = (long)chunk * 32 + lane;
+    if ((long)chunk * 32 >= a.B) break;
+    if (b < a.B) {
+      const Params P = derive_params(a.params, a.B, b);
+      SolveOut out;
+      ipm_solve(P, M, a.O, W, false, out);
+      a.tf[b] = out.tf;
+      a.fmass[b] = P.M0 - P.fuel * (P.mflow * P.T * out.tf);   // mass(nt-1) = mflow*T*tf (LO:123)
+      a.status[b] = out.status;
+      a.iters[b] = out.iters;
+      if (a.kkt) a.kkt[b] = out.kkt;
+      if (a.traj) {
+        double* __restrict__ t = a.traj;
+        const long B = a.B;
+#pragma unroll
+        for (int v = 0; v < LMATO_NVAR; ++v) t[((long)v * nt) * B + b] = 0.0;   // node 0 pinned
+        for (int k = 1; k <= a.N; ++k) {
+          double z[6];
+#pragma unroll
+          for (int i = 0; i < 6; ++i) z[i] = W.it(out.cur, F_Z + i, k);
+          const double u = W.it(out.cur, F_U, k);
+          const double m = P.mflow * P.T * a.tau[k] * out.tf;
+          Accel1 f;
+          accel_first(P, z[0], z[2], z[4], m, f);
+          t[((long)LMATO_V_Y * nt + k) * B + b] = z[0];
+          t[((long)LMATO_V_YDOT * nt + k) * B + b] = z[1];
+          t[((long)LMATO_V_YDOUBLEDOT * nt + k) * B + b] = f.ay;
+          t[((long)LMATO_V_X * nt + k) * B + b] = z[2];
+          t[((long)LMATO_V_XDOT * nt + k) * B + b] = z[3];
+          t[((long)LMATO_V_XDOUBLEDOT * nt + k) * B + b] = f.ax;
+          t[((long)LMATO_V_ANGLE * nt + k) * B + b] = z[4];
+          t[((long)LMATO_V_ANGLEDOT * nt + k) * B + b] = z[5];
+          t[((long)LMATO_V_MASS * nt + k) * B + b] = m;
+          t[((long)LMATO_V_ANGLEDOUBLEDOT * nt + k) * B + b] = u;
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// FP64 FMA peak: 8 independent chains per thread, no memory traffic.
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
+         a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[(long)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+}  // namespace
+
+struct lmato_handle {
+  int device = 0;
+  int nt = 0;
+  int nodes = 2;
+  int model = 0;
+  int sm_count = 0;
+  double* d_h = nullptr;
+  double* d_tau = nullptr;
+  double* d_ws = nullptr;
+  size_t ws_bytes = 0;
+  long ws_slots = 0;
+  int* d_counter = nullptr;
+  // staging for the host-buffer entry point
+  double* d_params = nullptr; size_t params_bytes = 0;
+  double* d_out = nullptr; size_t out_bytes = 0;
+  lmato_options opt;
+  int64_t launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaStream_t last_stream = nullptr;
+  bool timed = false;
+};
+
+extern "C" {
+
+const char* lmato_last_error(void) { return g_err; }
+const char* lmato_version(void) { return "lmato_b200 0.1 (sm_100a)"; }
+
+void lmato_default_options(lmato_options* o) {
+  if (!o) return;
+  o->tol = 1e-8;
+  o->mu_init = 0.1;
+  o->obj_scale = 10.0;
+  o->tf_guess = 0.9;
+  o->delta_c = 1e-8;
+  o->max_iter = 20000;   // LO:28
+  o->max_ls = 40;
+}
+
+lmato_status_t lmato_create(lmato_handle** out, int32_t device, int32_t nt, const double* time,
+                            int32_t nodes, int32_t model) {
+  if (!out) { set_err("lmato_create: out is NULL"); return LMATO_ERR_INVALID; }
+  *out = nullptr;
+  if (nt < 2) { set_err("lmato_create: nt must be >= 2"); return LMATO_ERR_INVALID; }
+  if (nodes != 2) {
+    set_err("lmato_create: NODES=%s not implemented on the device (only 2 = backward Euler, LO:25)",
+            nodes == 3 ? "3" : "n");
+    return LMATO_ERR_UNSUPPORTED;
+  }
+  if (model != LMATO_MODEL_ELLIPTICAL) {
+    set_err("lmato_create: only the elliptical model (Launch_Optimiser.py) is implemented on the device");
+    return LMATO_ERR_UNSUPPORTED;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    set_err("lmato_create: no CUDA device available (%s); there is no CPU fallback",
+            e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    return LMATO_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= ndev) { set_err("lmato_create: bad device ordinal"); return LMATO_ERR_INVALID; }
+  std::vector<double> h(nt), tau(nt);
+  for (int k = 0; k < nt; ++k) tau[k] = time ? time[k] : (double)k / (double)(nt - 1);   // LO:21
+  if (tau[0] != 0.0) { set_err("lmato_create: time[0] must be 0"); return LMATO_ERR_INVALID; }
+  h[0] = 0.0;
+  for (int k = 1; k < nt; ++k) {
+    h[k] = tau[k] - tau[k - 1];
+    if (!(h[k] > 0.0)) { set_err("lmato_create: time must be strictly increasing"); return LMATO_ERR_INVALID; }
+  }
+  lmato_handle* H = new (std::nothrow) lmato_handle();
+  if (!H) { set_err("lmato_create: out of host memory"); return LMATO_ERR_INVALID; }
+  H->device = device; H->nt = nt; H->nodes = nodes; H->model = model;
+  lmato_default_options(&H->opt);
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  H->sm_count = prop.multiProcessorCount;
+  CUDA_TRY(cudaMalloc(&H->d_h, sizeof(double) * nt));
+  CUDA_TRY(cudaMalloc(&H->d_tau, sizeof(double) * nt));
+  CUDA_TRY(cudaMemcpy(H->d_h, h.data(), sizeof(double) * nt, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(H->d_tau, tau.data(), sizeof(double) * nt, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMalloc(&H->d_counter, sizeof(int)));
+  CUDA_TRY(cudaEventCreate(&H->ev0));
+  CUDA_TRY(cudaEventCreate(&H->ev1));
+  *out = H;
+  return LMATO_OK;
+}
+
+lmato_status_t lmato_destroy(lmato_handle* h) {
+  if (!h) return LMATO_OK;
+  cudaSetDevice(h->device);
+  cudaFree(h->d_h); cudaFree(h->d_tau); cudaFree(h->d_ws); cudaFree(h->d_counter);
+  cudaFree(h->d_params); cudaFree(h->d_out);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  delete h;
+  return LMATO_OK;
+}
+
+lmato_status_t lmato_set_options(lmato_handle* h, const lmato_options* o) {
+  if (!h || !o) { set_err("lmato_set_options: NULL argument"); return LMATO_ERR_INVALID; }
+  if (!(o->tol > 0) || !(o->mu_init > 0) || !(o->obj_scale > 0) || !(o->delta_c > 0) ||
+      !(o->tf_guess > 0 && o->tf_guess < 1) || o->max_iter < 0 || o->max_ls < 1) {
+    set_err("lmato_set_options: option out of range");
+    return LMATO_ERR_INVALID;
+  }
+  h->opt = *o;
+  return LMATO_OK;
+}
+
+static long slots_for(const lmato_handle* h, int64_t B) {
+  const long cap = (long)h->sm_count * kBlocksPerSM * kBlock;   // resident threads
+  long need = ((B + 31) / 32) * 32;
+  long s = need < cap ? need : cap;
+  return ((s + kBlock - 1) / kBlock) * kBlock;
+}
+
+lmato_status_t lmato_workspace_bytes(lmato_handle* h, int64_t B, int64_t* bytes) {
+  if (!h || !bytes || B < 0) { set_err("lmato_workspace_bytes: bad argument"); return LMATO_ERR_INVALID; }
+  *bytes = (int64_t)sizeof(double) * N_FIELDS * h->nt * slots_for(h, B);
+  return LMATO_OK;
+}
+
+lmato_status_t lmato_kernel_launches(lmato_handle* h, int64_t* n) {
+  if (!h || !n) { set_err("lmato_kernel_launches: bad argument"); return LMATO_ERR_INVALID; }
+  *n = h->launches;
+  return LMATO_OK;
+}
+
+lmato_status_t lmato_solve_batch(lmato_handle* h, const double* params, int64_t B,
+                                 double* out_traj, double* out_tf, double* out_final_mass,
+                                 int32_t* out_status, int32_t* out_iters, double* out_kkt,
+                                 void* stream) {
+  if (!h) { set_err("lmato_solve_batch: NULL handle"); return LMATO_ERR_INVALID; }
+  if (B < 0) { set_err("lmato_solve_batch: negative batch"); return LMATO_ERR_INVALID; }
+  if (B == 0) return LMATO_OK;
+  if (!params || !out_tf || !out_final_mass || !out_status || !out_iters) {
+    set_err("lmato_solve_batch: NULL buffer");
+    return LMATO_ERR_INVALID;
+  }
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const long slots = slots_for(h, B);
+  const size_t need = sizeof(double) * (size_t)N_FIELDS * (size_t)h->nt * (size_t)slots;
+  if (need > h->ws_bytes) {
+    if (h->d_ws) { CUDA_TRY(cudaStreamSynchronize(st)); CUDA_TRY(cudaFree(h->d_ws)); h->d_ws = nullptr; h->ws_bytes = 0; }
+    CUDA_TRY(cudaMalloc(&h->d_ws, need));
+    h->ws_bytes = need;
+  }
+  h->ws_slots = slots;
+  CUDA_TRY(cudaMemsetAsync(h->d_counter, 0, sizeof(int), st));
+  KArgs a;
+  a.params = params; a.B = B; a.traj = out_traj; a.tf = out_tf; a.fmass = out_final_mass;
+  a.status = out_status; a.iters = out_iters; a.kkt = out_kkt;
+  a.ws = h->d_ws; a.slots = slots; a.N = h->nt - 1; a.h = h->d_h; a.tau = h->d_tau;
+  a.counter = h->d_counter;
+  a.O.tol = h->opt.tol; a.O.mu_init = h->opt.mu_init; a.O.obj_scale = h->opt.obj_scale;
+  a.O.kappa_eps = 10.0; a.O.kappa_mu = 0.2; a.O.theta_mu = 1.5; a.O.tau_min = 0.99;
+  a.O.delta_c = h->opt.delta_c; a.O.tf_guess = h->opt.tf_guess;
+  a.O.max_iter = h->opt.max_iter; a.O.max_ls = h->opt.max_ls;
+  const int grid = (int)(slots / kBlock);
+  CUDA_TRY(cudaEventRecord(h->ev0, st));
+  ascent_ipm_kernel<<<grid, kBlock, 0, st>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaEventRecord(h->ev1, st));
+  h->last_stream = st; h->timed = true;
+  h->launches += 1;
+  return LMATO_OK;
+}
+
+lmato_status_t lmato_last_kernel_ms(lmato_handle* h, double* ms) {
+  if (!h || !ms) { set_err("lmato_last_kernel_ms: bad argument"); return LMATO_ERR_INVALID; }
+  if (!h->timed) { set_err("lmato_last_kernel_ms: no solve has been launched"); return LMATO_ERR_INVALID; }
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaEventSynchronize(h->ev1));
+  float f = 0.f;
+  CUDA_TRY(cudaEventElapsedTime(&f, h->ev0, h->ev1));
+  *ms = (double)f;
+  return LMATO_OK;
+}
+
+lmato_status_t lmato_solve_batch_host(lmato_handle* h, const double* params, int64_t B,
+                                      double* out_traj, double* out_tf, double* out_final_mass,
+                                      int32_t* out_status, int32_t* out_iters, double* out_kkt) {
+  if (!h) { set_err("lmato_solve_batch_host: NULL handle"); return LMATO_ERR_INVALID; }
+  if (B < 0) { set_err("lmato_solve_batch_host: negative batch"); return LMATO_ERR_INVALID; }
+  if (B == 0) return LMATO_OK;
+  if (!params || !out_tf || !out_final_mass || !out_status || !out_iters) {
+    set_err("lmato_solve_batch_host: NULL buffer");
+    return LMATO_ERR_INVALID;
+  }
+  CUDA_TRY(cudaSetDevice(h->device));
+  const size_t pbytes = sizeof(double) * LMATO_NPARAM * (size_t)B;
+  if (pbytes > h->params_bytes) {
+    if (h->d_params) CUDA_TRY(cudaFree(h->d_params));
+    h->d_params = nullptr; h->params_bytes = 0;
+    CUDA_TRY(cudaMalloc(&h->d_params, pbytes));
+    h->params_bytes = pbytes;
+  }
+  const size_t traj_n = out_traj ? (size_t)LMATO_NVAR * h->nt * (size_t)B : 0;
+  // layout of d_out: traj | tf | fmass | kkt | status | iters
+  const size_t obytes = sizeof(double) * (traj_n + 3 * (size_t)B) + sizeof(int32_t) * 2 * (size_t)B;
+  if (obytes > h->out_bytes) {
+    if (h->d_out) CUDA_TRY(cudaFree(h->d_out));
+    h->d_out = nullptr; h->out_bytes = 0;
+    CUDA_TRY(cudaMalloc(&h->d_out, obytes));
+    h->out_bytes = obytes;
+  }
+  double* d_traj = out_traj ? h->d_out : nullptr;
+  double* d_tf = h->d_out + traj_n;
+  double* d_fm = d_tf + B;
+  double* d_kkt = d_fm + B;
+  int32_t* d_st = (int32_t*)(d_kkt + B);
+  int32_t* d_it = d_st + B;
+  cudaStream_t st = nullptr;
+  CUDA_TRY(cudaMemcpyAsync(h->d_params, params, pbytes, cudaMemcpyHostToDevice, st));
+  lmato_status_t rc = lmato_solve_batch(h, h->d_params, B, d_traj, d_tf, d_fm, d_st, d_it, d_kkt, st);
+  if (rc != LMATO_OK) return rc;
+  if (out_traj) CUDA_TRY(cudaMemcpyAsync(out_traj, d_traj, sizeof(double) * traj_n, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(out_tf, d_tf, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(out_final_mass, d_fm, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
+  if (out_kkt) CUDA_TRY(cudaMemcpyAsync(out_kkt, d_kkt, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(out_status, d_st, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(out_iters, d_it, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return LMATO_OK;
+}
+
+lmato_status_t lmato_measure_fp64_peak(lmato_handle* h, double* gflops) {
+  if (!h || !gflops) { set_err("lmato_measure_fp64_peak: bad argument"); return LMATO_ERR_INVALID; }
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int blocks = h->sm_count * 8, threads = 256, iters = 20000;
+  double* d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, sizeof(double) * (size_t)blocks * threads));
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    CUDA_TRY(cudaEventRecord(e0, 0));
+    dfma_peak_kernel<<<blocks, threads>>>(d, iters);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(e1, 0));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    const double fl = 2.0 * 8.0 * (double)iters * (double)blocks * threads;
+    const double g = fl / (ms * 1e-3) * 1e-9;
+    if (rep > 0 && g > best) best = g;
+  }
+  h->launches += 5;
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+  *gflops = best;
+  return LMATO_OK;
+}
+
+}  // extern "C"

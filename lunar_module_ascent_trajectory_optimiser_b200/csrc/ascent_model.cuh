@@ -1,0 +1,154 @@
+// Ascent dynamics, hand-derived first and second derivatives (FP64).
+//
+// Reference equations (LO:n = /root/reference/Launch_Optimiser.py line n):
+//   differential rows  LO:114-123, algebraic accelerations LO:127-136,
+//   terminal rows LO:161, 169, 173.  The circular variant (PDF p.27 src 76-96) uses the
+//   same acceleration expressions with the pitch angle as the manipulated variable.
+//
+// Formulation used on the device (equivalent NLP, see DESIGN.md "Transcription"):
+//   * ydoubledot / xdoubledot are substituted into the velocity rows (they are explicit
+//     functions of y, x, angle, mass);
+//   * mass obeys mass' = mflow*T*tf with mass(0)=0 (LO:123, LO:151), hence
+//     mass_k = mflow*T*tf*tau_k exactly under any collocation scheme that is exact for
+//     constants -- it is eliminated and re-materialised on output;
+//   * tf (one global FV, LO:39) is carried as a stage state so that the KKT system is
+//     block tridiagonal with no dense border.
+//
+// This header is compiled by nvcc for the product.  It is also compilable by g++ for
+// tools/hostsim (a developer-only debugging harness, never loaded by the package).
+#pragma once
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define LM_HD __host__ __device__ __forceinline__
+#define LM_D __device__ __forceinline__
+#else
+#define LM_HD inline
+#define LM_D inline
+#endif
+
+namespace lmato {
+
+// Per-problem derived constants (LO:50-75, 107-109).
+struct Params {
+  double GM;      // G*M                         LO:50-51
+  double R0;      // lunar radius                LO:52
+  double Ft;      // thrust                      LO:61
+  double M0;      // wet mass                    LO:62
+  double S;       // distance scale = r_periapsis LO:73,107
+  double ms;      // mass scale in dynamics      LO:108 (2576 in the PDF original)
+  double mflow;   // M_dot / fuel_mass           LO:65
+  double asc;     // angle_doubledot_max / 3     LO:109
+  double T;       // final_time                  LO:38
+  double a_ub;    // angle upper bound           LO:94
+  double u_ub;    // |angledoubledot| bound      LO:96
+  double vt2;     // (periapsis_v / S)^2         LO:75,169
+  double rt;      // (R0 + S) / S                LO:161
+  double R0S;     // R0 / S                      LO:161
+  double tf_ub;   // min(1, 1/(mflow*T)): tf<=1 (LO:39) and mass<=1 (LO:83) at the last node
+  double fuel;    // fuel_mass (for final-mass output)
+};
+
+LM_HD void lm_sincos(double a, double* s, double* c) {
+#if defined(__CUDA_ARCH__)
+  sincos(a, s, c);
+#else
+  *s = sin(a);
+  *c = cos(a);
+#endif
+}
+
+// First-order quantities of the acceleration field at one node.
+struct Accel1 {
+  double ay, ax;                 // LO:127-136 (scaled: divided by S)
+  double ay_y, ay_x, ay_a, ay_m; // d ay / d (y, x, angle, mass), scaled coordinates
+  double ax_y, ax_x, ax_a, ax_m;
+  // retained intermediates for the second-order pass
+  double nx, ny, rinv, Tx, Ty, AT, eta, g3;
+};
+
+LM_HD void accel_first(const Params& P, double y, double x, double a, double m, Accel1& o) {
+  const double X = x * P.S;
+  const double Y = fma(y, P.S, P.R0);
+  const double r2 = fma(X, X, Y * Y);
+  const double rinv = 1.0 / sqrt(r2);
+  const double nx = X * rinv, ny = Y * rinv;
+  double s3, c3;
+  lm_sincos(3.0 * a, &s3, &c3);
+  const double Ty = fma(ny, c3, nx * s3);      // cos(psi - 3a)
+  const double Tx = fma(nx, c3, -ny * s3);     // sin(psi - 3a)
+  const double mden = 1.0 / (P.M0 - P.ms * m);
+  const double AT = P.Ft * mden;               // thrust acceleration [m/s^2]
+  const double eta = P.ms * mden;              // d ln(AT) / d mass
+  const double g2 = P.GM * rinv * rinv;        // GM / r^2
+  const double g3 = g2 * rinv;                 // GM / r^3
+  const double Sinv = 1.0 / P.S;
+  o.ay = (AT * Ty - g2 * ny) * Sinv;
+  o.ax = (AT * Tx - g2 * nx) * Sinv;
+  const double ATr = AT * rinv;
+  const double cross = 3.0 * g3 * nx * ny;
+  o.ay_y = ATr * nx * Tx - g3 * (1.0 - 3.0 * ny * ny);
+  o.ay_x = -ATr * ny * Tx + cross;
+  o.ax_y = -ATr * nx * Ty + cross;
+  o.ax_x = ATr * ny * Ty - g3 * (1.0 - 3.0 * nx * nx);
+  o.ay_a = 3.0 * AT * Tx * Sinv;
+  o.ax_a = -3.0 * AT * Ty * Sinv;
+  o.ay_m = AT * eta * Ty * Sinv;
+  o.ax_m = AT * eta * Tx * Sinv;
+  o.nx = nx; o.ny = ny; o.rinv = rinv; o.Tx = Tx; o.Ty = Ty; o.AT = AT; o.eta = eta; o.g3 = g3;
+}
+
+// Second derivatives of  Psi = l1*ay + l3*ax  w.r.t. (y, x, angle, mass), scaled coordinates.
+struct Accel2 {
+  double yy, yx, xx, ya, xa, aa, ym, xm, am, mm;
+};
+
+LM_HD void accel_second(const Params& P, const Accel1& f, double l1, double l3, Accel2& h) {
+  const double nx = f.nx, ny = f.ny, ri = f.rinv;
+  const double LT = fma(l1, f.Ty, l3 * f.Tx);    // lambda . thrust direction
+  const double LP = fma(l1, f.Tx, -l3 * f.Ty);   // -dLT/dbeta
+  // beta = psi - 3a ;  grad beta wrt (X, Y, a) = (ny/r, -nx/r, -3)
+  const double bX = ny * ri, bY = -nx * ri;
+  const double ri2 = ri * ri;
+  // thrust part of S*Psi : AT * LT(beta)
+  const double A = f.AT;
+  const double pXX = -2.0 * nx * ny * ri2, pYY = -pXX, pXY = (nx * nx - ny * ny) * ri2;
+  double HXX = A * (-LT * bX * bX - LP * pXX);
+  double HYY = A * (-LT * bY * bY - LP * pYY);
+  double HXY = A * (-LT * bX * bY - LP * pXY);
+  const double HXa = A * (3.0 * LT * bX);
+  const double HYa = A * (3.0 * LT * bY);
+  const double Haa = A * (-9.0 * LT);
+  // gravity part of S*Psi : -(GM)(l1*Y + l3*X)/r^3
+  const double ln = fma(l3, nx, l1 * ny);
+  const double k = 3.0 * f.g3 * ri;               // 3 GM / r^4
+  HXX += k * (2.0 * l3 * nx + ln - 5.0 * ln * nx * nx);
+  HYY += k * (2.0 * l1 * ny + ln - 5.0 * ln * ny * ny);
+  HXY += k * (l3 * ny + l1 * nx - 5.0 * ln * nx * ny);
+  const double S = P.S, Sinv = 1.0 / P.S;
+  h.yy = HYY * S; h.yx = HXY * S; h.xx = HXX * S;
+  h.ya = HYa;     h.xa = HXa;     h.aa = Haa * Sinv;
+  const double Ae = A * f.eta;
+  h.ym = -Ae * LP * bY;
+  h.xm = -Ae * LP * bX;
+  h.am = 3.0 * Ae * LP * Sinv;
+  h.mm = 2.0 * Ae * f.eta * LT * Sinv;
+}
+
+// Terminal constraint values and gradients at the last node (LO:161, 169, 173; the
+// orthogonality row is divided by S^2, which leaves its zero set unchanged).
+struct Terminal {
+  double g1, g2, g3;     // radius - rt ; speed^2 - vt2 ; r.v / S^2
+  double rT;             // scaled radius
+  double Yb;             // y + R0/S
+};
+
+LM_HD void terminal_eval(const Params& P, double y, double vy, double x, double vx, Terminal& t) {
+  t.Yb = y + P.R0S;
+  t.rT = sqrt(fma(t.Yb, t.Yb, x * x));
+  t.g1 = t.rT - P.rt;
+  t.g2 = fma(vx, vx, vy * vy) - P.vt2;
+  t.g3 = fma(t.Yb, vy, x * vx);
+}
+
+}  // namespace lmato

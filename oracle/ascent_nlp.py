@@ -493,34 +493,62 @@ class AscentNLP:
 
     # -- initial guess ------------------------------------------------------------------
     def initial_guess(self, tf0: float = 0.9) -> np.ndarray:
-        """A physically shaped start (the reference's all-zero cold start, LO:39/83-96,
-        is available with ``tf0=None``).  Pitch ramps up smoothly, states follow by
-        integrating the reference dynamics explicitly with that pitch."""
+        """Start point.  ``tf0=None`` gives the reference's all-zero cold start (LO:39,
+        83-96), which needs IPOPT's full restoration phase.  Otherwise: a dynamically
+        consistent roll-out of a bang-bang pitch-acceleration profile (+0.9 until t1, -0.9
+        until t1+t2, then 0), the shape of Angle_vs_Time.png.  The product builds the same
+        start on the device (csrc/ascent_ipm.cuh: init_guess) -- restated here, not shared."""
         nm, p, K, nv = self.nm, self.p, self.K, self.nv
         x = np.zeros(self.n)
         if tf0 is None:
             return x
+        tf0 = min(max(tf0, 1e-2), 0.99)
+        names = nm.names
         tau_pts = np.empty(K)
         for k in range(K):
             s, w = divmod(k, self.npts)
             tau_pts[k] = self.time[s] + (self.time[s + 1] - self.time[s]) * self.tau[w + 1]
-        theta = pitch_guess(tau_pts * tf0 * p.final_time, p)
-        traj = integrate_guess(np.concatenate([[0.0], tau_pts]) * tf0 * p.final_time,
-                               np.concatenate([[0.0], theta]), p)
+        t = np.concatenate([[0.0], tau_pts]) * tf0 * p.final_time
         v = np.zeros((nv, K))
-        names = nm.names
-        for n in ("y", "ydot", "x", "xdot", "ydoubledot", "xdoubledot", "mass"):
-            v[names.index(n)] = traj[n][1:]
-        ang = theta / 3.0
-        v[names.index("angle")] = np.clip(ang, 1e-3, p.angle_ub - 1e-3)
         if p.model == "elliptical":
-            t = np.concatenate([[0.0], tau_pts]) * tf0 * p.final_time
-            a0 = np.concatenate([[0.0], ang])
-            w = np.diff(a0) / np.diff(t)
-            w0 = np.concatenate([[0.0], w])
-            u = np.diff(w0) / np.diff(t) / p.asc
-            v[names.index("angledot")] = w
-            v[names.index("angledoubledot")] = np.clip(u, -0.9 * p.u_bound, 0.9 * p.u_bound)
+            a_tgt = min(0.40, 0.8 * p.angle_ub)
+            w_rem = 3.5e-4
+            ulev = 0.9 * p.u_bound
+            ueff = ulev * p.asc
+            t1 = math.sqrt(a_tgt / ueff)
+            t2 = max(t1 - w_rem / ueff, 0.0)
+        a = w = 0.0
+        y = yd = xx = xd = 0.0
+        a_lo, a_hi = 1e-2 * p.angle_ub, 0.99 * p.angle_ub
+        for k in range(1, K + 1):
+            dt = t[k] - t[k - 1]
+            tm = 0.5 * (t[k] + t[k - 1])
+            if p.model == "elliptical":
+                u = ulev if tm < t1 else (-ulev if tm < t1 + t2 else 0.0)
+                w += dt * p.asc * u
+                a += dt * w
+            else:   # circular: the pitch itself is the MV; ramp to ~35 deg then rise linearly
+                a = (0.2 + 0.45 * t[k] / t[-1])
+            ac = min(max(a, a_lo), a_hi)
+            m = p.mflow * t[k]
+            yn, xn, ydn, xdn = y + dt * yd, xx + dt * xd, yd, xd
+            for _ in range(3):
+                ydd, xdd = _accel_numeric(p, yn, xn, ac, m)
+                ydn, xdn = yd + dt * ydd, xd + dt * xdd
+                yn, xn = y + dt * ydn, xx + dt * xdn
+            y, yd, xx, xd = yn, ydn, xn, xdn
+            col = k - 1
+            v[names.index("y"), col] = y
+            v[names.index("ydot"), col] = yd
+            v[names.index("x"), col] = xx
+            v[names.index("xdot"), col] = xd
+            v[names.index("ydoubledot"), col] = ydd
+            v[names.index("xdoubledot"), col] = xdd
+            v[names.index("mass"), col] = min(m, 0.99)
+            v[names.index("angle"), col] = ac
+            if p.model == "elliptical":
+                v[names.index("angledot"), col] = w
+                v[names.index("angledoubledot"), col] = u
         x[: self.i_tf] = v.T.reshape(-1)
         x[self.i_tf] = tf0
         x[self.i_s1] = 1e-2
@@ -528,35 +556,13 @@ class AscentNLP:
         return x
 
 
-def pitch_guess(t: np.ndarray, p: AscentParams) -> np.ndarray:
-    """Physical pitch theta(t) [rad] used only to seed the solvers: smooth ramp to ~70 deg
-    in the first ~100 s, then a slow linear rise (shape of Angle_vs_Time.png)."""
-    t = np.asarray(t, float)
-    ramp = 1.2 * (1.0 - np.exp(-(t / 45.0) ** 2))
-    rise = 0.35 * np.clip((t - 60.0) / 370.0, 0.0, 1.0)
-    return np.minimum(ramp + rise, 3.0 * p.angle_ub - 0.05)
-
-
-def integrate_guess(t: np.ndarray, theta: np.ndarray, p: AscentParams) -> Dict[str, np.ndarray]:
-    """Semi-implicit Euler march of LO:114-136 in scaled units along a given pitch."""
-    n = len(t)
+def _accel_numeric(p: AscentParams, y, x, a, m):
+    """LO:127-136 evaluated numerically (scaled units)."""
     S, R0, GM = p.S, p.R0, p.GM
-    out = {k: np.zeros(n) for k in ("y", "ydot", "x", "xdot", "ydoubledot", "xdoubledot", "mass")}
-    y = yd = x = xd = 0.0
-    for k in range(1, n):
-        dt = t[k] - t[k - 1]
-        m = min(p.mflow * t[k], 0.999)
-        X, Y = x * S, y * S + R0
-        r = math.hypot(X, Y)
-        kk = p.Ft / ((p.M0 - p.mscale * m) * r)
-        c3, s3 = math.cos(theta[k]), math.sin(theta[k])
-        ydd = (kk * (Y * c3 + X * s3) - Y * GM / r ** 3) / S
-        xdd = (kk * (X * c3 - Y * s3) - X * GM / r ** 3) / S
-        yd += dt * ydd
-        xd += dt * xdd
-        y += dt * yd
-        x += dt * xd
-        for name, val in (("y", y), ("ydot", yd), ("x", x), ("xdot", xd),
-                          ("ydoubledot", ydd), ("xdoubledot", xdd), ("mass", m)):
-            out[name][k] = val
-    return out
+    X, Y = x * S, y * S + R0
+    r = math.hypot(X, Y)
+    kk = p.Ft / ((p.M0 - p.mscale * m) * r)
+    c3, s3 = math.cos(3 * a), math.sin(3 * a)
+    ydd = (kk * (Y * c3 + X * s3) - Y * GM / r ** 3) / S
+    xdd = (kk * (X * c3 - Y * s3) - X * GM / r ** 3) / S
+    return ydd, xdd

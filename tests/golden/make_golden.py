@@ -1,0 +1,73 @@
+"""Generate the golden fixtures in this directory with the CPU oracle.
+
+    python tests/golden/make_golden.py
+
+The reference itself (GEKKO + apm + IPOPT) cannot run in the authoring container, so the
+vectors come from the oracle restatement (oracle/ascent_nlp.py + oracle/ipm_reference.py)
+converged to a scaled KKT error of 1e-9; the oracle in turn is pinned to the reference's two
+published outputs by tests/test_oracle_golden.py.  Inputs are the seeded dispersions of
+SURVEY.md section 8(d) (lunar_module_ascent_trajectory_optimiser_b200/dispersions.py).
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from oracle.ascent_nlp import AscentNLP, AscentParams  # noqa: E402
+from oracle.ipm_reference import IPMOptions, solve_ipm  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+VAR_ROWS = ["y", "ydot", "ydoubledot", "x", "xdot", "xdoubledot", "angle", "angledot", "mass",
+            "angledoubledot"]
+
+
+def solve(p: AscentParams, nt=200, time=None, nodes=2, obj_scale=10.0, tol=1e-9):
+    nlp = AscentNLP(p, nt=nt, time=time, nodes=nodes, obj_scale=obj_scale)
+    r = solve_ipm(nlp, nlp.initial_guess(0.9), IPMOptions(tol=tol))
+    assert r.status == 0, (r.status, r.kkt_error)
+    nv = nlp.node_values(r.x)
+    names = [n for n in VAR_ROWS if n in nv]
+    traj = np.stack([nv[n] for n in names])
+    tf = nv["tf"]
+    fm = p.M0 - p.fuel_mass * nv["mass"][-1]
+    return dict(tf=tf, final_mass=fm, traj=traj, names=np.array(names), iters=r.iterations, kkt=r.kkt_error,
+                time=nlp.time)
+
+
+def main():
+    out = {}
+    # config 1: the reference script's defaults
+    s = solve(AscentParams())
+    np.savez(os.path.join(HERE, "elliptical_nominal_nt200.npz"), **s)
+    print("elliptical nominal tf_s", s["tf"] * 470, "iters", s["iters"])
+    # config 2: circular IB-document model
+    s = solve(AscentParams.circular())
+    np.savez(os.path.join(HERE, "circular_nominal_nt200.npz"), **s)
+    print("circular nominal tf_s", s["tf"] * 470, "iters", s["iters"])
+    # small mesh + non-uniform mesh
+    s = solve(AscentParams(), nt=40)
+    np.savez(os.path.join(HERE, "elliptical_nominal_nt40.npz"), **s)
+    t = np.linspace(0.0, 1.0, 60) ** 1.3
+    s = solve(AscentParams(), time=t)
+    np.savez(os.path.join(HERE, "elliptical_nominal_nonuniform60.npz"), **s)
+    # dispersions (config 4 draws: all six columns), first 8 of seed 11
+    import torch  # noqa: F401
+    from lunar_module_ascent_trajectory_optimiser_b200.dispersions import dispersed_params
+    dp = dispersed_params(8, seed=11)
+    rows = dp.rows().numpy()
+    tfs, fms, trajs = [], [], []
+    for b in range(rows.shape[1]):
+        p = AscentParams(Ft=rows[3, b], M0=rows[4, b], M_dot=rows[5, b], angle_doubledot_max=rows[7, b],
+                         r_periapsis=rows[8, b], r_apoapsis=rows[9, b])
+        s = solve(p)
+        tfs.append(s["tf"]); fms.append(s["final_mass"]); trajs.append(s["traj"])
+        print("dispersion", b, "tf_s", s["tf"] * 470, "iters", s["iters"])
+    np.savez(os.path.join(HERE, "elliptical_dispersions8_seed11_nt200.npz"), rows=rows, tf=np.array(tfs),
+             final_mass=np.array(fms), traj=np.stack(trajs), names=np.array(VAR_ROWS))
+
+
+if __name__ == "__main__":
+    main()

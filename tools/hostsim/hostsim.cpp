@@ -1,0 +1,85 @@
+// DEVELOPER TOOL -- NOT PART OF THE PRODUCT.
+//
+// Compiles the device solver core (csrc/ascent_ipm.cuh) with g++ so that the IPM control
+// logic can be stepped through on a box without a GPU.  It is not built by
+// __graft_entry__.build(), not loaded by the Python package, not used by any test as the
+// thing under test, and bench.py never calls it.  The product path is the CUDA library
+// only and fails loudly without it.
+//
+//   g++ -O2 -std=c++17 -I lunar_module_ascent_trajectory_optimiser_b200/csrc tools/hostsim/hostsim.cpp -o /tmp/hostsim
+//   /tmp/hostsim [nt] [seed dispersions...]
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <vector>
+#include <random>
+#include "ascent_ipm.cuh"
+
+using namespace lmato;
+
+static Params make_params(double Ft, double M0, double Mdot, double addm, double rp, double ra) {
+  Params P;
+  const double G = 6.674e-11, Mm = 7.346e22, R0 = 1738100.0, fuel = 2376.0, T = 470.0;
+  P.GM = G * Mm; P.R0 = R0; P.Ft = Ft; P.M0 = M0; P.S = rp; P.ms = fuel; P.mflow = Mdot / fuel;
+  P.asc = addm / 3.0; P.T = T; P.a_ub = M_PI / 3.0; P.u_ub = 1.0;
+  const double vt = std::sqrt(P.GM / (R0 + 0.5 * (rp + ra)));
+  P.vt2 = (vt / P.S) * (vt / P.S);
+  P.rt = (R0 + P.S) / P.S; P.R0S = R0 / P.S;
+  P.tf_ub = std::fmin(1.0, 1.0 / (P.mflow * T));
+  P.fuel = fuel;
+  return P;
+}
+
+int main(int argc, char** argv) {
+  int nt = argc > 1 ? atoi(argv[1]) : 200;
+  int nprob = argc > 2 ? atoi(argv[2]) : 1;
+  int verbose = argc > 3 ? atoi(argv[3]) : 0;
+  int only = argc > 4 ? atoi(argv[4]) : -1;
+  const int N = nt - 1;
+  std::vector<double> h(N + 1), tau(N + 1);
+  for (int k = 0; k <= N; ++k) { tau[k] = (double)k / N; h[k] = k ? tau[k] - tau[k - 1] : 0.0; }
+  Mesh M{N, h.data(), tau.data()};
+  Options O;
+  O.tol = 1e-8; O.mu_init = 0.1; O.obj_scale = 100.0; O.kappa_eps = 10.0; O.kappa_mu = 0.2; O.theta_mu = 1.5;
+  O.tau_min = 0.99; O.delta_c = 1e-8; O.tf_guess = 0.9; O.max_iter = 500; O.max_ls = 40;
+  if (getenv("OBJ")) O.obj_scale = atof(getenv("OBJ"));
+  if (getenv("MU0")) O.mu_init = atof(getenv("MU0"));
+  if (getenv("TOL")) O.tol = atof(getenv("TOL"));
+  if (getenv("TF0")) O.tf_guess = atof(getenv("TF0"));
+  if (getenv("DC")) O.delta_c = atof(getenv("DC"));
+  std::vector<double> ws((size_t)N_FIELDS * (N + 1), 0.0);
+  Ws W{ws.data(), 1, N + 1, 0};
+  std::mt19937_64 rng(11);
+  std::uniform_real_distribution<double> U(0.0, 1.0);
+  int nfail = 0, itsum = 0, itmax = 0;
+  for (int p = 0; p < nprob; ++p) {
+    double u[6];
+    for (int i = 0; i < 6; ++i) u[i] = (p == 0) ? 0.5 : U(rng);
+    const double Ft = 15346.0 * (1 + 0.02 * (2 * u[0] - 1));
+    const double Isp = 309.7 * (1 + 0.01 * (2 * u[1] - 1));
+    const double Mdot = (p == 0) ? 5.053 : Ft / (Isp * 9.807);
+    const double M0 = 4821.0 * (1 + 0.02 * (2 * u[2] - 1));
+    const double addm = 5e-4 * std::pow(2.0, 2 * u[3] - 1);
+    const double rp = 17703.0 * (1 + 0.10 * (2 * u[4] - 1));
+    const double ra = 88615.0 * (1 + 0.10 * (2 * u[5] - 1));
+    if (only >= 0 && p != only) continue;
+    Params P = make_params(Ft, M0, Mdot, addm, rp, ra);
+    std::fill(ws.begin(), ws.end(), 0.0);
+    SolveOut out;
+    ipm_solve(P, M, O, W, false, out);
+    itsum += out.iters; if (out.iters > itmax) itmax = out.iters;
+    if (out.status != 0) ++nfail;
+    if (verbose || nprob <= 20 || out.status != 0)
+      printf("p %4d status %d iters %3d kkt %.2e mu %.1e tf %.10f tf_s %.8f  (Ft %.1f M0 %.1f Mdot %.4f addm %.2e rp %.0f ra %.0f)\n",
+             p, out.status, out.iters, out.kkt, out.mu, out.tf, out.tf * P.T, Ft, M0, Mdot, addm, rp, ra);
+    if (p == 0 && nprob == 1) {
+      const int b = out.cur;
+      printf("final y %.9f x %.9f vy %.9f vx %.9f\n", W.it(b, F_Z + 0, N) * P.S, W.it(b, F_Z + 2, N) * P.S,
+             W.it(b, F_Z + 1, N) * P.S, W.it(b, F_Z + 3, N) * P.S);
+      printf("final mass %.9f\n", P.M0 - P.fuel * P.mflow * P.T * out.tf);
+    }
+  }
+  printf("solved %d problems: %d failures, mean iters %.1f, max %d\n", nprob, nfail, (double)itsum / nprob, itmax);
+  return 0;
+}
