@@ -79,7 +79,7 @@ enum {
 };
 
 typedef struct {
-  double tol;        /* scaled KKT tolerance (IPOPT `tol`); default 1e-8 */
+  double tol;        /* scaled KKT tolerance (IPOPT `tol`); default 1e-10 (see DESIGN.md "Tolerance") */
   double mu_init;    /* initial barrier parameter; default 0.1 */
   double obj_scale;  /* objective = obj_scale * tf; default 10 */
   double tf_guess;   /* initial scaled final time; default 0.9 */

@@ -126,7 +126,7 @@ class SolverOptions:
     max_iter: int = 20000          # LO:28
     otol: float = 1e-3             # LO:31 (recorded; the device IPM converges to `tol`)
     rtol: float = 1e-3             # LO:32
-    tol: float = 1e-8              # scaled KKT error at which a problem counts as converged
+    tol: float = 1e-10             # scaled KKT error at which a problem counts as converged
     mu_init: float = 0.1
     obj_scale: float = 10.0
     tf_guess: float = 0.9

@@ -181,7 +181,7 @@ const char* lmato_version(void) { return "lmato_b200 0.1 (sm_100a)"; }
 
 void lmato_default_options(lmato_options* o) {
   if (!o) return;
-  o->tol = 1e-8;
+  o->tol = 1e-10;
   o->mu_init = 0.1;
   o->obj_scale = 10.0;
   o->tf_guess = 0.9;

@@ -4,7 +4,7 @@
 
 The reference itself (GEKKO + apm + IPOPT) cannot run in the authoring container, so the
 vectors come from the oracle restatement (oracle/ascent_nlp.py + oracle/ipm_reference.py)
-converged to a scaled KKT error of 1e-9; the oracle in turn is pinned to the reference's two
+converged to a scaled KKT error of 1e-12; the oracle in turn is pinned to the reference's two
 published outputs by tests/test_oracle_golden.py.  Inputs are the seeded dispersions of
 SURVEY.md section 8(d) (lunar_module_ascent_trajectory_optimiser_b200/dispersions.py).
 """
@@ -24,7 +24,7 @@ VAR_ROWS = ["y", "ydot", "ydoubledot", "x", "xdot", "xdoubledot", "angle", "angl
             "angledoubledot"]
 
 
-def solve(p: AscentParams, nt=200, time=None, nodes=2, obj_scale=10.0, tol=1e-9):
+def solve(p: AscentParams, nt=200, time=None, nodes=2, obj_scale=10.0, tol=1e-12):
     nlp = AscentNLP(p, nt=nt, time=time, nodes=nodes, obj_scale=obj_scale)
     r = solve_ipm(nlp, nlp.initial_guess(0.9), IPMOptions(tol=tol))
     assert r.status == 0, (r.status, r.kkt_error)

@@ -18,6 +18,7 @@ VAR_ROWS = ["y", "ydot", "ydoubledot", "x", "xdot", "xdoubledot", "angle", "angl
 TF_RTOL = 1e-4
 MASS_RTOL = 1e-6
 STATE_RTOL = 1e-4
+CONTROL_RTOL = 5e-3
 
 
 @pytest.fixture(scope="module")
@@ -39,8 +40,12 @@ def _check_against(gold_tf, gold_fm, gold_traj, tf, fm, traj, tight=True):
     assert abs(tf - gold_tf) / gold_tf < TF_RTOL
     assert abs(fm - gold_fm) / gold_fm < MASS_RTOL
     scale = np.abs(gold_traj).max(axis=1, keepdims=True) + 1e-300
-    err = np.abs(traj - gold_traj) / scale
-    assert err.max() < STATE_RTOL, (err.max(axis=1))
+    err = (np.abs(traj - gold_traj) / scale).max(axis=1)
+    assert err[:9].max() < STATE_RTOL, err          # the nine GEKKO Vars (LO:83-95)
+    # The MV on the singular arc is a nearly flat direction of the NLP: it converges like
+    # O(mu / sigma_min) (2e-2 between tol 1e-9 and 1e-10, 9e-4 between 1e-10 and 1e-11 in the
+    # oracle itself), so it is held to a looser bar than the states.  See DESIGN.md "Tolerance".
+    assert err[9] < CONTROL_RTOL, err
     if tight:   # what is actually achieved
         assert abs(tf - gold_tf) / gold_tf < 1e-7
         assert abs(fm - gold_fm) / gold_fm < 1e-7
