@@ -84,8 +84,10 @@ typedef struct {
   double obj_scale;  /* objective = obj_scale * tf; default 10 */
   double tf_guess;   /* initial scaled final time; default 0.9 */
   double delta_c;    /* dual regularisation of the terminal equality row; default 1e-8 */
+  double mu_min_factor; /* barrier floor = mu_min_factor * tol; default 1e-3 (IPOPT uses 0.1) */
   int32_t max_iter;  /* LO:28 MAX_ITER; default 20000 (the reference's value) */
   int32_t max_ls;    /* max backtracking steps per iteration; default 40 */
+  int32_t n_polish;  /* Newton iterations taken after tol is first met; default 2 (DESIGN.md "Tolerance") */
 } lmato_options;
 
 /* Fill `o` with the defaults above. */

@@ -51,7 +51,7 @@ struct KArgs {
   int* status;
   int* iters;
   double* kkt;
-  double* ws;            // [N_FIELDS][N+1][slots]
+  double* ws;            // [N+1][slots/32][N_FIELDS][32]
   long slots;
   int N;
   const double* h;
@@ -84,6 +84,7 @@ __device__ __forceinline__ Params derive_params(const double* __restrict__ p, lo
   P.R0S = R0 / P.S;
   P.tf_ub = fmin(1.0, 1.0 / (P.mflow * P.T));
   P.fuel = fuel;
+  P.Sinv = 1.0 / P.S;
   return P;
 }
 
@@ -91,7 +92,8 @@ __global__ void __launch_bounds__(kBlock, kBlocksPerSM) ascent_ipm_kernel(KArgs 
   const long slot = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   const Mesh M{a.N, a.h, a.tau};
-  const Ws W{a.ws, a.slots, a.N + 1, slot};
+  const long nwarps = a.slots / LANES;
+  const Ws W{a.ws + ((slot / LANES) * N_FIELDS) * LANES + lane, nwarps * N_FIELDS * LANES};
   const int nt = a.N + 1;
   while (true) {
     int chunk = 0;
@@ -114,13 +116,14 @@ __global__ void __launch_bounds__(kBlock, kBlocksPerSM) ascent_ipm_kernel(KArgs 
 #pragma unroll
         for (int v = 0; v < LMATO_NVAR; ++v) t[((long)v * nt) * B + b] = 0.0;   // node 0 pinned
         for (int k = 1; k <= a.N; ++k) {
+          const double* sp = W.stage(k);
           double z[6];
 #pragma unroll
-          for (int i = 0; i < 6; ++i) z[i] = W.it(out.cur, F_Z + i, k);
-          const double u = W.it(out.cur, F_U, k);
+          for (int i = 0; i < 6; ++i) z[i] = WS_AT(sp, out.cur * N_ITER + F_Z + i);
+          const double u = WS_AT(sp, out.cur * N_ITER + F_U);
           const double m = P.mflow * P.T * a.tau[k] * out.tf;
-          Accel1 f;
-          accel_first(P, z[0], z[2], z[4], m, f);
+          struct { double ay, ax; } f;
+          accel_value(P, z[0], z[2], z[4], m, f.ay, f.ax);
           t[((long)LMATO_V_Y * nt + k) * B + b] = z[0];
           t[((long)LMATO_V_YDOT * nt + k) * B + b] = z[1];
           t[((long)LMATO_V_YDOUBLEDOT * nt + k) * B + b] = f.ay;
@@ -186,6 +189,8 @@ void lmato_default_options(lmato_options* o) {
   o->obj_scale = 10.0;
   o->tf_guess = 0.9;
   o->delta_c = 1e-8;
+  o->mu_min_factor = 1e-3;
+  o->n_polish = 2;
   o->max_iter = 20000;   // LO:28
   o->max_ls = 40;
 }
@@ -253,7 +258,8 @@ lmato_status_t lmato_destroy(lmato_handle* h) {
 lmato_status_t lmato_set_options(lmato_handle* h, const lmato_options* o) {
   if (!h || !o) { set_err("lmato_set_options: NULL argument"); return LMATO_ERR_INVALID; }
   if (!(o->tol > 0) || !(o->mu_init > 0) || !(o->obj_scale > 0) || !(o->delta_c > 0) ||
-      !(o->tf_guess > 0 && o->tf_guess < 1) || o->max_iter < 0 || o->max_ls < 1) {
+      !(o->tf_guess > 0 && o->tf_guess < 1) || o->max_iter < 0 || o->max_ls < 1 ||
+      !(o->mu_min_factor > 0 && o->mu_min_factor <= 1) || o->n_polish < 0) {
     set_err("lmato_set_options: option out of range");
     return LMATO_ERR_INVALID;
   }
@@ -311,6 +317,7 @@ lmato_status_t lmato_solve_batch(lmato_handle* h, const double* params, int64_t 
   a.O.kappa_eps = 10.0; a.O.kappa_mu = 0.2; a.O.theta_mu = 1.5; a.O.tau_min = 0.99;
   a.O.delta_c = h->opt.delta_c; a.O.tf_guess = h->opt.tf_guess;
   a.O.max_iter = h->opt.max_iter; a.O.max_ls = h->opt.max_ls;
+  a.O.mu_min_factor = h->opt.mu_min_factor; a.O.n_polish = h->opt.n_polish;
   const int grid = (int)(slots / kBlock);
   CUDA_TRY(cudaEventRecord(h->ev0, st));
   ascent_ipm_kernel<<<grid, kBlock, 0, st>>>(a);

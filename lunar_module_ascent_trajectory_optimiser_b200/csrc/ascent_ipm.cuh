@@ -3,16 +3,17 @@
 // Replaces, for this one model family, what the reference reaches through
 // m.solve() (LO:177): APMonitor's collocation transcription + AD + IPOPT/MA27.
 //   subsystem (1) transcription ......... stage defects below (backward Euler == GEKKO NODES=2, LO:25)
-//   subsystem (2) residual/Jacobian/Hessian  ascent_model.cuh + stage_build()
+//   subsystem (2) residual/Jacobian/Hessian  ascent_model.cuh + the Q assembly in riccati_backward()
 //   subsystem (3) KKT factorisation ...... riccati_backward() / riccati_forward(): stage-wise
 //                 block-tridiagonal LDL^T (Riccati recursion) with inertia read from the pivots
-//   subsystem (4) barrier / fraction-to-boundary / filter line search: ipm_iterate()
+//   subsystem (4) barrier / fraction-to-boundary / filter line search: ipm_solve()
 //
 // IPM = Waechter & Biegler, Math. Prog. 106 (2006) (the algorithm behind SOLVER=3, LO:26).
 //
-// Data layout: struct-of-arrays  ws[field][stage][slot]  with slot (= problem in flight)
-// fastest, so that the 32 lanes of a warp touch 32 consecutive doubles (256 B) for every
-// field of every stage.  All sweeps stream stage by stage through HBM.
+// Data layout (HBM): ws[stage][warp][field][lane] -- for one warp and one stage the N_FIELDS
+// fields are N_FIELDS consecutive 256-byte rows, so every field access is the stage pointer plus
+// a compile-time offset (no address arithmetic per access) and every warp access is one fully
+// coalesced, 256-byte-aligned transaction.  All sweeps stream stage by stage through HBM.
 #pragma once
 #include "ascent_model.cuh"
 
@@ -31,8 +32,10 @@ struct Options {
   double tau_min;        // 0.99
   double delta_c;        // dual regularisation of the terminal equality row
   double tf_guess;       // initial tf (scaled, 0..1)
+  double mu_min_factor;  // smallest barrier parameter = mu_min_factor * tol (IPOPT: 0.1)
   int max_iter;          // LO:28 MAX_ITER
   int max_ls;            // max backtracking steps
+  int n_polish;          // extra Newton iterations after the tolerance is first met
 };
 
 enum Status : int {
@@ -45,28 +48,31 @@ enum Status : int {
 };
 
 // ---------------------------------------------------------------------------------------
-// workspace fields
+// workspace fields (row index inside one [stage][warp] block; a row = 32 lanes)
 // ---------------------------------------------------------------------------------------
 enum : int {
-  // iterate (two ping-pong copies)
+  // iterate, two ping-pong copies at rows [0,17) and [17,34)
   F_Z = 0,          // 6: y, vy, x, vx, angle, angledot
   F_U = 6,          // 1
   F_LAM = 7,        // 6: defect multipliers
   F_ZLA = 13, F_ZUA = 14, F_ZLU = 15, F_ZUU = 16,
   N_ITER = 17,
-  // step
-  F_DS = 0,         // 6
-  F_DU = 6,
-  F_PI = 7,         // 6: new defect multipliers
+  // step, rows [34,47)
+  R_STEP = 2 * N_ITER,
+  F_DS = R_STEP + 0,   // 6
+  F_DU = R_STEP + 6,
+  F_PI = R_STEP + 7,   // 6: new defect multipliers
   N_STEP = 13,
-  // factor
-  F_K = 0,          // 7 feedback gains
-  F_KFF = 7,
-  F_P = 8,          // 28 packed symmetric cost-to-go Hessian P_{k-1}
-  F_PV = 36,        // 7 cost-to-go gradient p_{k-1}
-  N_FACT = 43,
-  N_FIELDS = 2 * N_ITER + N_STEP + N_FACT   // 90 doubles per stage per problem
+  // factor, rows [47,88)
+  R_FACT = R_STEP + N_STEP,
+  F_K = R_FACT + 0,    // 7 feedback gains
+  F_KFF = R_FACT + 7,
+  F_P = R_FACT + 8,    // 27: packed lower triangle of P_{k-1} without the (tf,tf) entry
+  F_PV = F_P + 27,     // 6: p_{k-1} without the tf entry
+  N_FACT = 8 + 27 + 6,
+  N_FIELDS = 2 * N_ITER + N_STEP + N_FACT   // 88 doubles per stage per problem
 };
+constexpr int LANES = 32;
 
 struct Mesh {
   int N;                 // number of steps (nt-1)
@@ -74,15 +80,13 @@ struct Mesh {
   const double* tau;     // tau[k] = time[k]
 };
 
+// View of one thread's column of the workspace.
 struct Ws {
-  double* base;          // [N_FIELDS][N+1][B]
-  long B;                // slots
-  int N1;                // N+1
-  long j;                // this thread's slot
-  LM_HD double& it(int buf, int f, int k) const { return base[((long)(buf * N_ITER + f) * N1 + k) * B + j]; }
-  LM_HD double& st(int f, int k) const { return base[((long)(2 * N_ITER + f) * N1 + k) * B + j]; }
-  LM_HD double& fa(int f, int k) const { return base[((long)(2 * N_ITER + N_STEP + f) * N1 + k) * B + j]; }
+  double* p;             // base + (warp * N_FIELDS) * 32 + lane
+  long SS;               // stage stride in doubles = n_warps * N_FIELDS * 32
+  LM_HD double* stage(int k) const { return p + (long)k * SS; }
 };
+#define WS_AT(sp, row) (sp)[(row) * LANES]
 
 constexpr int NFILT = 12;
 
@@ -107,20 +111,37 @@ struct Ctl {
 // ---------------------------------------------------------------------------------------
 // small helpers
 // ---------------------------------------------------------------------------------------
-LM_HD int pidx(int i, int j) {  // packed lower-triangular index, i >= j
+LM_HD constexpr int pidx(int i, int j) {  // packed lower-triangular index, i >= j
   return i * (i + 1) / 2 + j;
 }
 LM_HD double dmax(double a, double b) { return a > b ? a : b; }
 LM_HD double dmin(double a, double b) { return a < b ? a : b; }
+
+// 1/a, 1/b, 1/c, 1/d with a single division (all arguments are positive slacks in (0, ~2)).
+LM_HD void recip4(double a, double b, double c, double d, double& ia, double& ib, double& ic, double& id) {
+  const double ab = a * b, cd = c * d;
+  const double ip = 1.0 / (ab * cd);
+  const double iab = ip * cd, icd = ip * ab;
+  ia = iab * b; ib = iab * a; ic = icd * d; id = icd * c;
+}
+
+// kappa_Sigma safeguard (IPOPT eq. 16) written on the complementarity product so that the common
+// path has no division:  z in [mu/(kS d), kS mu/d]  <=>  z d in [mu/kS, kS mu].
+LM_HD double clip_mult(double z, double d, double mu) {
+  const double kS = 1e10;
+  const double c = z * d;
+  if (c > kS * mu) return kS * mu / d;
+  if (c < mu / kS) return mu / (kS * d);
+  return z;
+}
 
 // Stage Jacobian data: everything needed to apply E^{-1} and E^{-T}.
 //   E = d defect_k / d s_k  for s = (y, vy, x, vx, a, w, tf); d defect_k / d s_{k-1} = -I;
 //   d defect_k / d u_k = -beta e_5.
 struct StageJac {
   double al;                  // alpha = h*T*tf
-  double a2a, a2b, a2c, a2d;  // alpha^2 * (ay_y, ay_x, ax_y, ax_x)
-  double ala, alb, alc, ald;  // alpha   * (ay_y, ay_x, ax_y, ax_x)
-  double m11, m13, m31, m33;  // inverse of the 2x2 velocity block
+  double ala, alb, alc, ald;  // alpha * (ay_y, ay_x, ax_y, ax_x)
+  double m11, m13, m31, m33;  // inverse of the 2x2 velocity block (only after stagejac_invert)
   double ga1, ga3;            // alpha * (ay_a, ax_a)
   double e0, e1, e2, e3, e4, e5;  // tf column (negated entries of E)
   double beta;                // alpha * asc
@@ -131,18 +152,23 @@ LM_HD void stagejac_build(const Params& P, double kap, double tf, double taum /*
   const double al = kap * tf;
   J.al = al;
   J.ala = al * f.ay_y; J.alb = al * f.ay_x; J.alc = al * f.ax_y; J.ald = al * f.ax_x;
-  J.a2a = al * J.ala; J.a2b = al * J.alb; J.a2c = al * J.alc; J.a2d = al * J.ald;
-  const double d11 = 1.0 - J.a2a, d33 = 1.0 - J.a2d;
-  const double Dinv = 1.0 / (d11 * d33 - J.a2b * J.a2c);
-  J.m11 = d33 * Dinv; J.m13 = J.a2b * Dinv; J.m31 = J.a2c * Dinv; J.m33 = d11 * Dinv;
   J.ga1 = al * f.ay_a; J.ga3 = al * f.ax_a;
+  const double alt = al * taum;
   J.e0 = kap * vy;
-  J.e1 = kap * f.ay + al * f.ay_m * taum;
+  J.e1 = fma(kap, f.ay, alt * f.ay_m);
   J.e2 = kap * vx;
-  J.e3 = kap * f.ax + al * f.ax_m * taum;
+  J.e3 = fma(kap, f.ax, alt * f.ax_m);
   J.e4 = kap * w;
   J.e5 = kap * P.asc * u;
   J.beta = al * P.asc;
+}
+
+LM_HD void stagejac_invert(StageJac& J) {
+  const double al = J.al;
+  const double a2a = al * J.ala, a2b = al * J.alb, a2c = al * J.alc, a2d = al * J.ald;
+  const double d11 = 1.0 - a2a, d33 = 1.0 - a2d;
+  const double Dinv = 1.0 / (d11 * d33 - a2b * a2c);
+  J.m11 = d33 * Dinv; J.m13 = a2b * Dinv; J.m31 = a2c * Dinv; J.m33 = d11 * Dinv;
 }
 
 // v <- E^{-1} v
@@ -166,21 +192,25 @@ LM_HD void solveE(const StageJac& J, double* v) {
   v[5] = v5;
 }
 
+// w <- A11^T w, A11 = inverse of the (y, vy, x, vx) block of E
+LM_HD void applyA11T(const StageJac& J, double& w0, double& w1, double& w2, double& w3) {
+  const double t0 = w0 + J.ala * w1 + J.alc * w3;
+  const double t2 = w2 + J.alb * w1 + J.ald * w3;
+  const double n0 = J.m11 * t0 + J.m31 * t2;
+  const double n2 = J.m13 * t0 + J.m33 * t2;
+  w1 = fma(J.al, n0, w1);
+  w3 = fma(J.al, n2, w3);
+  w0 = n0; w2 = n2;
+}
+
 // g <- E^{-T} g
 LM_HD void solveET(const StageJac& J, double* g) {
-  // velocity/position block:  M^T w = g_p
-  const double t0 = g[0] + J.ala * g[1] + J.alc * g[3];
-  const double t2 = g[2] + J.alb * g[1] + J.ald * g[3];
-  // [1-a2a, -a2c; -a2b, 1-a2d] [w0; w2] = [t0; t2]  (transpose of the 2x2 in solveE)
-  const double w0 = J.m11 * t0 + J.m31 * t2;
-  const double w2 = J.m13 * t0 + J.m33 * t2;
-  const double w1 = fma(J.al, w0, g[1]);
-  const double w3 = fma(J.al, w2, g[3]);
+  double w0 = g[0], w1 = g[1], w2 = g[2], w3 = g[3];
+  applyA11T(J, w0, w1, w2, w3);
   const double gaw = J.ga1 * w1 + J.ga3 * w3;
   const double gew = J.e0 * w0 + J.e1 * w1 + J.e2 * w2 + J.e3 * w3;
-  const double g4 = g[4], g5 = g[5];
-  const double w4 = g4 + gaw;
-  const double w5 = g5 + J.al * w4;
+  const double w4 = g[4] + gaw;
+  const double w5 = g[5] + J.al * w4;
   const double w6 = g[6] + gew + J.e4 * w4 + J.e5 * w5;
   g[0] = w0; g[1] = w1; g[2] = w2; g[3] = w3; g[4] = w4; g[5] = w5; g[6] = w6;
 }
@@ -215,7 +245,7 @@ LM_HD GuessProfile guess_profile(const Params& P) {
   return g;
 }
 
-LM_HD void init_guess(const Params& P, const Mesh& M, const Options& O, const Ws& W, Scal& s) {
+LM_NOINLINE void init_guess(const Params& P, const Mesh& M, const Options& O, const Ws& W, Scal& s) {
   const int N = M.N;
   const double tf0 = dmin(dmax(O.tf_guess, 1e-2 * P.tf_ub), 0.99 * P.tf_ub);
   const GuessProfile g = guess_profile(P);
@@ -230,23 +260,26 @@ LM_HD void init_guess(const Params& P, const Mesh& M, const Options& O, const Ws
     a += dt * w;
     const double ac = dmin(dmax(a, a_lo), a_hi);
     const double m = P.mflow * P.T * M.tau[k] * tf0;
-    // backward-Euler step for (y, vy, x, vx): two fixed-point sweeps
+    // backward-Euler step for (y, vy, x, vx): three fixed-point sweeps
     double yn = y + dt * vy, xn = x + dt * vx, vyn = vy, vxn = vx;
     for (int itr = 0; itr < 3; ++itr) {
-      Accel1 f;
-      accel_first(P, yn, xn, ac, m, f);
-      vyn = vy + dt * f.ay; vxn = vx + dt * f.ax;
-      yn = y + dt * vyn;    xn = x + dt * vxn;
+      double ay, ax;
+      accel_value(P, yn, xn, ac, m, ay, ax);
+      vyn = vy + dt * ay; vxn = vx + dt * ax;
+      yn = y + dt * vyn;  xn = x + dt * vxn;
     }
     y = yn; vy = vyn; x = xn; vx = vxn;
-    W.it(0, F_Z + 0, k) = y;  W.it(0, F_Z + 1, k) = vy;
-    W.it(0, F_Z + 2, k) = x;  W.it(0, F_Z + 3, k) = vx;
-    W.it(0, F_Z + 4, k) = ac; W.it(0, F_Z + 5, k) = w;
-    W.it(0, F_U, k) = u;
-    for (int i = 0; i < 6; ++i) W.it(0, F_LAM + i, k) = 0.0;
-    W.it(0, F_ZLA, k) = 1.0; W.it(0, F_ZUA, k) = 1.0;
-    W.it(0, F_ZLU, k) = 1.0; W.it(0, F_ZUU, k) = 1.0;
-    for (int i = 0; i < N_STEP; ++i) W.st(i, k) = 0.0;
+    double* sp = W.stage(k);
+    WS_AT(sp, F_Z + 0) = y;  WS_AT(sp, F_Z + 1) = vy;
+    WS_AT(sp, F_Z + 2) = x;  WS_AT(sp, F_Z + 3) = vx;
+    WS_AT(sp, F_Z + 4) = ac; WS_AT(sp, F_Z + 5) = w;
+    WS_AT(sp, F_U) = u;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) WS_AT(sp, F_LAM + i) = 0.0;
+    WS_AT(sp, F_ZLA) = 1.0; WS_AT(sp, F_ZUA) = 1.0;
+    WS_AT(sp, F_ZLU) = 1.0; WS_AT(sp, F_ZUU) = 1.0;
+#pragma unroll
+    for (int i = 0; i < N_STEP; ++i) WS_AT(sp, R_STEP + i) = 0.0;
     t_prev = t;
   }
   s.tf = tf0;
@@ -260,57 +293,58 @@ LM_HD void init_guess(const Params& P, const Mesh& M, const Options& O, const Ws
 // ---------------------------------------------------------------------------------------
 struct TermStep { double dtf, dsg1, dsg2, dzs1, dzs2, dnu3, dzLt, dzUt; };
 
-LM_HD void eval_pass(const Params& P, const Mesh& M, const Options& O, const Ws& W, int src, int dst,
-                     const Scal& c0, const TermStep& ts, double mu, double alpha, double alpha_z,
-                     double alpha_lam, Scal& t) {
+LM_NOINLINE void eval_pass(const Params& P, const Mesh& M, const Options& O, const Ws& W, int src, int dst,
+                           const Scal& c0, const TermStep& ts, double mu, double alpha, double alpha_z,
+                           double alpha_lam, Scal& t) {
   const int N = M.N;
-  const double kS = 1e10;  // kappa_Sigma, IPOPT eq. (16)
   t.tf = c0.tf + alpha * ts.dtf;
   const double tf = t.tf;
+  const int so = src * N_ITER, dd = dst * N_ITER;
   double zp[6] = {0, 0, 0, 0, 0, 0};      // previous node's trial state
   double pend[6] = {0, 0, 0, 0, 0, 0};    // E_{k-1}^T lam_{k-1} + bound terms, awaiting -lam_k
   double theta = 0, prim = 0, dual = 0, sumlog = 0, cmin = 1e300, cmax = 0, slam = 0, sz = 0;
   double gtf = 0;                          // d Lagrangian / d tf accumulated over stages
   bool bad = false;
+  const double mT = P.mflow * P.T;
   for (int k = 1; k <= N; ++k) {
+    double* sp = W.stage(k);
     double z[6], lam[6];
+    const double a_old = WS_AT(sp, so + F_Z + 4), da = WS_AT(sp, F_DS + 4);
 #pragma unroll
-    for (int i = 0; i < 6; ++i) z[i] = fma(alpha, W.st(F_DS + i, k), W.it(src, F_Z + i, k));
-    const double u_old = W.it(src, F_U, k);
-    const double du = W.st(F_DU, k);
+    for (int i = 0; i < 6; ++i) z[i] = fma(alpha, WS_AT(sp, F_DS + i), WS_AT(sp, so + F_Z + i));
+    const double u_old = WS_AT(sp, so + F_U);
+    const double du = WS_AT(sp, F_DU);
     const double u = fma(alpha, du, u_old);
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
-      const double l0 = W.it(src, F_LAM + i, k);
-      lam[i] = fma(alpha_lam, W.st(F_PI + i, k) - l0, l0);
+      const double l0 = WS_AT(sp, so + F_LAM + i);
+      lam[i] = fma(alpha_lam, WS_AT(sp, F_PI + i) - l0, l0);
     }
-    // bound multipliers: dz = mu/d - z - (z/d) dx  (old d, old z), then kappa_Sigma clip
-    const double a_old = W.it(src, F_Z + 4, k), da = W.st(F_DS + 4, k);
-    double zla = W.it(src, F_ZLA, k), zua = W.it(src, F_ZUA, k);
-    double zlu = W.it(src, F_ZLU, k), zuu = W.it(src, F_ZUU, k);
+    // bound multipliers: dz = mu/d - z - (z/d) dx = (mu - z dx)/d - z  (old d, old z)
+    double zla = WS_AT(sp, so + F_ZLA), zua = WS_AT(sp, so + F_ZUA);
+    double zlu = WS_AT(sp, so + F_ZLU), zuu = WS_AT(sp, so + F_ZUU);
     {
-      const double dLa = a_old, dUa = P.a_ub - a_old, dLu = u_old + P.u_ub, dUu = P.u_ub - u_old;
-      zla += alpha_z * (mu / dLa - zla - zla / dLa * da);
-      zua += alpha_z * (mu / dUa - zua + zua / dUa * da);
-      zlu += alpha_z * (mu / dLu - zlu - zlu / dLu * du);
-      zuu += alpha_z * (mu / dUu - zuu + zuu / dUu * du);
+      double rLa, rUa, rLu, rUu;
+      recip4(a_old, P.a_ub - a_old, u_old + P.u_ub, P.u_ub - u_old, rLa, rUa, rLu, rUu);
+      zla += alpha_z * ((mu - zla * da) * rLa - zla);
+      zua += alpha_z * ((mu + zua * da) * rUa - zua);
+      zlu += alpha_z * ((mu - zlu * du) * rLu - zlu);
+      zuu += alpha_z * ((mu + zuu * du) * rUu - zuu);
     }
     const double dLa = z[4], dUa = P.a_ub - z[4], dLu = u + P.u_ub, dUu = P.u_ub - u;
     if (!(dLa > 0 && dUa > 0 && dLu > 0 && dUu > 0)) bad = true;
-    zla = dmax(dmin(zla, kS * mu / dLa), mu / (kS * dLa));
-    zua = dmax(dmin(zua, kS * mu / dUa), mu / (kS * dUa));
-    zlu = dmax(dmin(zlu, kS * mu / dLu), mu / (kS * dLu));
-    zuu = dmax(dmin(zuu, kS * mu / dUu), mu / (kS * dUu));
-    sumlog += log(dLa) + log(dUa) + log(dLu) + log(dUu);
+    zla = clip_mult(zla, dLa, mu); zua = clip_mult(zua, dUa, mu);
+    zlu = clip_mult(zlu, dLu, mu); zuu = clip_mult(zuu, dUu, mu);
+    sumlog += log((dLa * dUa) * (dLu * dUu));
     {
       const double c1 = dLa * zla, c2 = dUa * zua, c3 = dLu * zlu, c4 = dUu * zuu;
       cmin = dmin(cmin, dmin(dmin(c1, c2), dmin(c3, c4)));
       cmax = dmax(cmax, dmax(dmax(c1, c2), dmax(c3, c4)));
     }
-    sz += zla + zua + zlu + zuu;
+    sz += (zla + zua) + (zlu + zuu);
     // dynamics
     const double kap = M.h[k] * P.T;
-    const double taum = P.mflow * P.T * M.tau[k];
+    const double taum = mT * M.tau[k];
     Accel1 f;
     accel_first(P, z[0], z[2], z[4], taum * tf, f);
     StageJac J;
@@ -341,10 +375,10 @@ LM_HD void eval_pass(const Params& P, const Mesh& M, const Options& O, const Ws&
     gtf -= J.e0 * lam[0] + J.e1 * lam[1] + J.e2 * lam[2] + J.e3 * lam[3] + J.e4 * lam[4] + J.e5 * lam[5];
     // write trial iterate
 #pragma unroll
-    for (int i = 0; i < 6; ++i) { W.it(dst, F_Z + i, k) = z[i]; W.it(dst, F_LAM + i, k) = lam[i]; zp[i] = z[i]; }
-    W.it(dst, F_U, k) = u;
-    W.it(dst, F_ZLA, k) = zla; W.it(dst, F_ZUA, k) = zua;
-    W.it(dst, F_ZLU, k) = zlu; W.it(dst, F_ZUU, k) = zuu;
+    for (int i = 0; i < 6; ++i) { WS_AT(sp, dd + F_Z + i) = z[i]; WS_AT(sp, dd + F_LAM + i) = lam[i]; zp[i] = z[i]; }
+    WS_AT(sp, dd + F_U) = u;
+    WS_AT(sp, dd + F_ZLA) = zla; WS_AT(sp, dd + F_ZUA) = zua;
+    WS_AT(sp, dd + F_ZLU) = zlu; WS_AT(sp, dd + F_ZUU) = zuu;
   }
   // terminal node
   t.sg1 = c0.sg1 + alpha * ts.dsg1;
@@ -356,16 +390,16 @@ LM_HD void eval_pass(const Params& P, const Mesh& M, const Options& O, const Ws&
   t.zUt = c0.zUt + alpha_z * ts.dzUt;
   const double dLt = tf, dUt = P.tf_ub - tf;
   if (!(t.sg1 > 0 && t.sg2 > 0 && dLt > 0 && dUt > 0)) bad = true;
-  t.zs1 = dmax(dmin(t.zs1, kS * mu / t.sg1), mu / (kS * t.sg1));
-  t.zs2 = dmax(dmin(t.zs2, kS * mu / t.sg2), mu / (kS * t.sg2));
-  t.zLt = dmax(dmin(t.zLt, kS * mu / dLt), mu / (kS * dLt));
-  t.zUt = dmax(dmin(t.zUt, kS * mu / dUt), mu / (kS * dUt));
+  t.zs1 = clip_mult(t.zs1, t.sg1, mu);
+  t.zs2 = clip_mult(t.zs2, t.sg2, mu);
+  t.zLt = clip_mult(t.zLt, dLt, mu);
+  t.zUt = clip_mult(t.zUt, dUt, mu);
   Terminal T;
   terminal_eval(P, zp[0], zp[1], zp[2], zp[3], T);
   const double c1 = T.g1 - t.sg1, c2 = T.g2 - t.sg2, c3 = T.g3;
   theta += fabs(c1) + fabs(c2) + fabs(c3);
   prim = dmax(prim, dmax(fabs(c1), dmax(fabs(c2), fabs(c3))));
-  sumlog += log(t.sg1) + log(t.sg2) + log(dLt) + log(dUt);
+  sumlog += log((t.sg1 * t.sg2) * (dLt * dUt));
   {
     const double q1 = t.sg1 * t.zs1, q2 = t.sg2 * t.zs2, q3 = dLt * t.zLt, q4 = dUt * t.zUt;
     cmin = dmin(cmin, dmin(dmin(q1, q2), dmin(q3, q4)));
@@ -395,22 +429,41 @@ LM_HD void eval_pass(const Params& P, const Mesh& M, const Options& O, const Ws&
 // ---------------------------------------------------------------------------------------
 // backward Riccati sweep = block LDL^T of the KKT matrix in stage order.
 // Returns false if a pivot shows wrong inertia (caller increases delta_w and retries).
+//
+// Per stage:  W = Q_k + P_k,  Wt = Abar^T W Abar  with  Abar = E_k^{-1} = T1 T2 T3,
+//   T1 = diag(A11, I)   A11 = inverse of the (y,vy,x,vx) block of E          (4x4, applied as an operator)
+//   T2 = [I C; 0 I]     C = [ga | 0 | e]  couples (angle, tf) into the velocity rows
+//   T3 = diag(I, A22)   A22 = [[1, al, e4+al*e5], [0, 1, e5], [0, 0, 1]]      (angle, angledot, tf chain)
+// then the control is condensed (it enters through the angledot row only).
 // ---------------------------------------------------------------------------------------
-LM_HD bool riccati_backward(const Params& P, const Mesh& M, const Options& O, const Ws& W, int src,
-                            const Scal& c0, double mu, double dw, bool ls, double* dtf_out, double* p0_out) {
+LM_NOINLINE bool riccati_backward(const Params& P, const Mesh& M, const Options& O, const Ws& W, int src,
+                                  const Scal& c0, double mu, double dw, bool ls, double* dtf_out, double* p0_out) {
   // ls == true: least-squares multiplier estimate (IPOPT section 3.6): Hessian := I, defects := 0,
   // gradient := grad f - zL + zU; the forward sweep then returns the multipliers in F_PI.
   const int N = M.N;
   const double tf = c0.tf;
-  double Pm[28];   // packed lower triangle of the cost-to-go Hessian
+  const int so = src * N_ITER;
+  const double mT = P.mflow * P.T;
+  // cost-to-go Hessian in blocks: A = (p,p) 4x4 symmetric (full storage), B = (p,q) 4x3,
+  // Cq = (q,q) 3x3 symmetric (upper triangle used); p = (y,vy,x,vx), q = (angle, angledot, tf)
+  double A[4][4], Bm[4][3], C00, C01, C02, C11, C12, C22;
   double pv[7];
 #pragma unroll
-  for (int i = 0; i < 28; ++i) Pm[i] = 0.0;
+  for (int i = 0; i < 4; ++i) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) A[i][j] = 0.0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) Bm[i][j] = 0.0;
+  }
+  C00 = C01 = C02 = C11 = C12 = C22 = 0.0;
 #pragma unroll
   for (int i = 0; i < 7; ++i) pv[i] = 0.0;
   double zn[6];    // state at node k
+  {
+    const double* sp = W.stage(N);
 #pragma unroll
-  for (int i = 0; i < 6; ++i) zn[i] = W.it(src, F_Z + i, N);
+    for (int i = 0; i < 6; ++i) zn[i] = WS_AT(sp, so + F_Z + i);
+  }
   // ---- terminal contributions (added to stage N's Q and q) ----
   {
     Terminal T;
@@ -434,157 +487,205 @@ LM_HD bool riccati_backward(const Params& P, const Mesh& M, const Options& O, co
     // Hessian: w_i grad grad^T + multipliers * second derivatives (mult of g1,g2 = -zs)
     const double r3 = rinv * rinv * rinv;
     const double h1yy = zn[2] * zn[2] * r3, h1xx = T.Yb * T.Yb * r3, h1yx = -T.Yb * zn[2] * r3;
-    Pm[pidx(0, 0)] = w1 * g1y * g1y - hz1 * h1yy + w3 * G3[0] * G3[0];
-    Pm[pidx(2, 0)] = w1 * g1x * g1y - hz1 * h1yx + w3 * G3[2] * G3[0];
-    Pm[pidx(2, 2)] = w1 * g1x * g1x - hz1 * h1xx + w3 * G3[2] * G3[2];
-    Pm[pidx(1, 1)] = w2 * G2y * G2y - 2.0 * hz2 + w3 * G3[1] * G3[1];
-    Pm[pidx(3, 1)] = w2 * G2x * G2y + w3 * G3[3] * G3[1];
-    Pm[pidx(3, 3)] = w2 * G2x * G2x - 2.0 * hz2 + w3 * G3[3] * G3[3];
-    Pm[pidx(1, 0)] = w3 * G3[1] * G3[0] + hn3;
-    Pm[pidx(3, 0)] = w3 * G3[3] * G3[0];
-    Pm[pidx(2, 1)] = w3 * G3[2] * G3[1];
-    Pm[pidx(3, 2)] = w3 * G3[3] * G3[2] + hn3;
+    A[0][0] = w1 * g1y * g1y - hz1 * h1yy + w3 * G3[0] * G3[0];
+    A[2][0] = w1 * g1x * g1y - hz1 * h1yx + w3 * G3[2] * G3[0];
+    A[2][2] = w1 * g1x * g1x - hz1 * h1xx + w3 * G3[2] * G3[2];
+    A[1][1] = w2 * G2y * G2y - 2.0 * hz2 + w3 * G3[1] * G3[1];
+    A[3][1] = w2 * G2x * G2y + w3 * G3[3] * G3[1];
+    A[3][3] = w2 * G2x * G2x - 2.0 * hz2 + w3 * G3[3] * G3[3];
+    A[1][0] = w3 * G3[1] * G3[0] + hn3;
+    A[3][0] = w3 * G3[3] * G3[0];
+    A[2][1] = w3 * G3[2] * G3[1];
+    A[3][2] = w3 * G3[3] * G3[2] + hn3;
+    A[0][1] = A[1][0]; A[0][2] = A[2][0]; A[0][3] = A[3][0]; A[1][2] = A[2][1]; A[1][3] = A[3][1]; A[2][3] = A[3][2];
     // tf: objective, bound barrier, regularisation
     const double dLt = tf, dUt = P.tf_ub - tf;
     pv[6] = ls ? O.obj_scale - c0.zLt + c0.zUt : O.obj_scale - mu / dLt + mu / dUt;
-    Pm[pidx(6, 6)] = ls ? 1.0 : c0.zLt / dLt + c0.zUt / dUt + dw;
+    C22 = ls ? 1.0 : c0.zLt / dLt + c0.zUt / dUt + dw;
   }
   bool ok = true;
   for (int k = N; k >= 1; --k) {
+    double* sp = W.stage(k);
     double lam[6], zm[6];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) lam[i] = W.it(src, F_LAM + i, k);
+    for (int i = 0; i < 6; ++i) lam[i] = WS_AT(sp, so + F_LAM + i);
     if (k > 1) {
+      const double* sm = W.stage(k - 1);
 #pragma unroll
-      for (int i = 0; i < 6; ++i) zm[i] = W.it(src, F_Z + i, k - 1);
+      for (int i = 0; i < 6; ++i) zm[i] = WS_AT(sm, so + F_Z + i);
     } else {
 #pragma unroll
       for (int i = 0; i < 6; ++i) zm[i] = 0.0;
     }
-    const double u = W.it(src, F_U, k);
-    const double zla = W.it(src, F_ZLA, k), zua = W.it(src, F_ZUA, k);
-    const double zlu = W.it(src, F_ZLU, k), zuu = W.it(src, F_ZUU, k);
+    const double u = WS_AT(sp, so + F_U);
+    const double zla = WS_AT(sp, so + F_ZLA), zua = WS_AT(sp, so + F_ZUA);
+    const double zlu = WS_AT(sp, so + F_ZLU), zuu = WS_AT(sp, so + F_ZUU);
     const double kap = M.h[k] * P.T;
-    const double taum = P.mflow * P.T * M.tau[k];
+    const double taum = mT * M.tau[k];
     Accel1 f;
     accel_first(P, zn[0], zn[2], zn[4], taum * tf, f);
     StageJac J;
     stagejac_build(P, kap, tf, taum, f, zn[1], zn[3], zn[5], u, J);
+    stagejac_invert(J);
     const double al = J.al;
     // ---- W = Q_k + P_k (in place), g = q_k + p_k ----
-    const double dLa = zn[4], dUa = P.a_ub - zn[4];
-    const double dLu = u + P.u_ub, dUu = P.u_ub - u;
     double R, r, sig;
     if (!ls) {
+      double rLa, rUa, rLu, rUu;
+      recip4(zn[4], P.a_ub - zn[4], u + P.u_ub, P.u_ub - u, rLa, rUa, rLu, rUu);
       Accel2 h2;
       accel_second(P, f, lam[1], lam[3], h2);
-      Pm[pidx(0, 0)] += -al * h2.yy + dw;
-      Pm[pidx(2, 0)] += -al * h2.yx;
-      Pm[pidx(2, 2)] += -al * h2.xx + dw;
-      Pm[pidx(4, 0)] += -al * h2.ya;
-      Pm[pidx(4, 2)] += -al * h2.xa;
-      Pm[pidx(4, 4)] += -al * h2.aa + zla / dLa + zua / dUa + dw;
-      Pm[pidx(1, 1)] += dw; Pm[pidx(3, 3)] += dw; Pm[pidx(5, 5)] += dw;
+      A[0][0] += -al * h2.yy + dw;
+      { const double t = -al * h2.yx; A[2][0] += t; A[0][2] += t; }
+      A[2][2] += -al * h2.xx + dw;
+      A[1][1] += dw; A[3][3] += dw;
+      Bm[0][0] += -al * h2.ya;
+      Bm[2][0] += -al * h2.xa;
+      C00 += -al * h2.aa + zla * rLa + zua * rUa + dw;
+      C11 += dw;
       const double Phy = lam[1] * f.ay_y + lam[3] * f.ax_y;
       const double Phx = lam[1] * f.ay_x + lam[3] * f.ax_x;
       const double Pha = lam[1] * f.ay_a + lam[3] * f.ax_a;
       const double Phm = lam[1] * f.ay_m + lam[3] * f.ax_m;
-      Pm[pidx(6, 0)] += -kap * Phy - al * h2.ym * taum;
-      Pm[pidx(6, 2)] += -kap * Phx - al * h2.xm * taum;
-      Pm[pidx(6, 4)] += -kap * Pha - al * h2.am * taum;
-      Pm[pidx(6, 1)] += -kap * lam[0];
-      Pm[pidx(6, 3)] += -kap * lam[2];
-      Pm[pidx(6, 5)] += -kap * lam[4];
-      Pm[pidx(6, 6)] += -2.0 * kap * Phm * taum - al * h2.mm * taum * taum;
-      pv[4] += -mu / dLa + mu / dUa;
-      R = zlu / dLu + zuu / dUu + dw;
-      r = -mu / dLu + mu / dUu;
+      const double alt = al * taum;
+      Bm[0][2] += -kap * Phy - alt * h2.ym;
+      Bm[2][2] += -kap * Phx - alt * h2.xm;
+      Bm[1][2] += -kap * lam[0];
+      Bm[3][2] += -kap * lam[2];
+      C02 += -kap * Pha - alt * h2.am;
+      C12 += -kap * lam[4];
+      C22 += -2.0 * kap * Phm * taum - alt * h2.mm * taum;
+      pv[4] += mu * (rUa - rLa);
+      R = zlu * rLu + zuu * rUu + dw;
+      r = mu * (rUu - rLu);
       sig = -kap * lam[5] * P.asc;   // u-tf cross term
     } else {
 #pragma unroll
-      for (int i = 0; i < 6; ++i) Pm[pidx(i, i)] += 1.0;
+      for (int i = 0; i < 4; ++i) A[i][i] += 1.0;
+      C00 += 1.0; C11 += 1.0;
       pv[4] += -zla + zua;
       R = 1.0; r = -zlu + zuu; sig = 0.0;
     }
     // ---- defect ----
-    double c[7];
-    c[0] = zn[0] - zm[0] - al * zn[1];
-    c[1] = zn[1] - zm[1] - al * f.ay;
-    c[2] = zn[2] - zm[2] - al * zn[3];
-    c[3] = zn[3] - zm[3] - al * f.ax;
-    c[4] = zn[4] - zm[4] - al * zn[5];
-    c[5] = zn[5] - zm[5] - J.beta * u;
-    c[6] = 0.0;
-    if (ls) {
+    double c[6];
+    if (!ls) {
+      c[0] = zn[0] - zm[0] - al * zn[1];
+      c[1] = zn[1] - zm[1] - al * f.ay;
+      c[2] = zn[2] - zm[2] - al * zn[3];
+      c[3] = zn[3] - zm[3] - al * f.ax;
+      c[4] = zn[4] - zm[4] - al * zn[5];
+      c[5] = zn[5] - zm[5] - J.beta * u;
+    } else {
 #pragma unroll
       for (int i = 0; i < 6; ++i) c[i] = 0.0;
     }
-    // ---- congruence  Wt = E^{-T} W E^{-1} ----
-    double Wf[7][7];
+    // ---- T1: A <- A11^T A A11,  B <- A11^T B ----
 #pragma unroll
-    for (int i = 0; i < 7; ++i)
+    for (int j = 0; j < 4; ++j) applyA11T(J, A[0][j], A[1][j], A[2][j], A[3][j]);
 #pragma unroll
-      for (int j = 0; j <= i; ++j) { Wf[i][j] = Pm[pidx(i, j)]; Wf[j][i] = Wf[i][j]; }
+    for (int i = 0; i < 4; ++i) applyA11T(J, A[i][0], A[i][1], A[i][2], A[i][3]);
 #pragma unroll
-    for (int j = 0; j < 7; ++j) {        // columns: E^{-T} W
-      double col[7];
+    for (int j = 0; j < 3; ++j) applyA11T(J, Bm[0][j], Bm[1][j], Bm[2][j], Bm[3][j]);
+    // ---- T2: couple (angle, tf) into the velocity rows ----
+    {
+      double AC0[4], AC2[4];
 #pragma unroll
-      for (int i = 0; i < 7; ++i) col[i] = Wf[i][j];
-      solveET(J, col);
+      for (int i = 0; i < 4; ++i) {
+        AC0[i] = A[i][1] * J.ga1 + A[i][3] * J.ga3;
+        AC2[i] = A[i][0] * J.e0 + A[i][1] * J.e1 + A[i][2] * J.e2 + A[i][3] * J.e3;
+      }
+      double CtB0[3], CtB2[3];
 #pragma unroll
-      for (int i = 0; i < 7; ++i) Wf[i][j] = col[i];
+      for (int j = 0; j < 3; ++j) {
+        CtB0[j] = J.ga1 * Bm[1][j] + J.ga3 * Bm[3][j];
+        CtB2[j] = J.e0 * Bm[0][j] + J.e1 * Bm[1][j] + J.e2 * Bm[2][j] + J.e3 * Bm[3][j];
+      }
+      const double CtAC00 = J.ga1 * AC0[1] + J.ga3 * AC0[3];
+      const double CtAC02 = J.ga1 * AC2[1] + J.ga3 * AC2[3];
+      const double CtAC22 = J.e0 * AC2[0] + J.e1 * AC2[1] + J.e2 * AC2[2] + J.e3 * AC2[3];
+      C00 += 2.0 * CtB0[0] + CtAC00;
+      C01 += CtB0[1];
+      C02 += CtB0[2] + CtB2[0] + CtAC02;
+      C12 += CtB2[1];
+      C22 += 2.0 * CtB2[2] + CtAC22;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { Bm[i][0] += AC0[i]; Bm[i][2] += AC2[i]; }
     }
+    // ---- T3: (angle, angledot, tf) chain ----
+    {
+      const double s = J.e4 + al * J.e5, e5 = J.e5;
 #pragma unroll
-    for (int i = 0; i < 7; ++i) {        // rows: (.) E^{-1}  ==  E^{-T} applied to the row as a vector
-      double row[7];
-#pragma unroll
-      for (int j = 0; j < 7; ++j) row[j] = Wf[i][j];
-      solveET(J, row);
-#pragma unroll
-      for (int j = 0; j < 7; ++j) Wf[i][j] = row[j];
+      for (int i = 0; i < 4; ++i) {
+        const double b0 = Bm[i][0], b1 = Bm[i][1];
+        Bm[i][2] += s * b0 + e5 * b1;
+        Bm[i][1] = fma(al, b0, b1);
+      }
+      // X = Cq A22 (rows), then A22^T X
+      const double x00 = C00, x01 = al * C00 + C01, x02 = s * C00 + e5 * C01 + C02;
+      const double x11 = al * C01 + C11, x12 = s * C01 + e5 * C11 + C12;   // row 1 of X: [C01, x11, x12]
+      const double x21 = al * C02 + C12, x22 = s * C02 + e5 * C12 + C22;   // row 2 of X: [C02, x21, x22]
+      C00 = x00; C01 = x01; C02 = x02;
+      C11 = al * x01 + x11;
+      C12 = al * x02 + x12;
+      C22 = s * x02 + e5 * x12 + x22;
+      (void)x21;
     }
     solveET(J, pv);                      // g~ = E^{-T} (q + p)
-    // ---- condense the control ----
+    // ---- condense the control (enters through the angledot row: q-index 1) ----
     const double beta = J.beta;
-    const double Ruu = R + beta * beta * Wf[5][5];
+    const double Ruu = R + beta * beta * C11;
     double Rux[7];
 #pragma unroll
-    for (int i = 0; i < 7; ++i) Rux[i] = beta * 0.5 * (Wf[5][i] + Wf[i][5]);
-    Rux[6] += sig;
+    for (int i = 0; i < 4; ++i) Rux[i] = beta * Bm[i][1];
+    Rux[4] = beta * C01; Rux[5] = beta * C11; Rux[6] = beta * C12 + sig;
     double rx[7];
 #pragma unroll
-    for (int i = 0; i < 7; ++i) {
-      double acc = pv[i];
-#pragma unroll
-      for (int j = 0; j < 6; ++j) acc -= 0.5 * (Wf[i][j] + Wf[j][i]) * c[j];
-      rx[i] = acc;
-    }
+    for (int i = 0; i < 4; ++i)
+      rx[i] = pv[i] - (A[i][0] * c[0] + A[i][1] * c[1] + A[i][2] * c[2] + A[i][3] * c[3] + Bm[i][0] * c[4] + Bm[i][1] * c[5]);
+    rx[4] = pv[4] - (Bm[0][0] * c[0] + Bm[1][0] * c[1] + Bm[2][0] * c[2] + Bm[3][0] * c[3] + C00 * c[4] + C01 * c[5]);
+    rx[5] = pv[5] - (Bm[0][1] * c[0] + Bm[1][1] * c[1] + Bm[2][1] * c[2] + Bm[3][1] * c[3] + C01 * c[4] + C11 * c[5]);
+    rx[6] = pv[6] - (Bm[0][2] * c[0] + Bm[1][2] * c[1] + Bm[2][2] * c[2] + Bm[3][2] * c[3] + C02 * c[4] + C12 * c[5]);
     const double ru = r + beta * rx[5];
     if (!(Ruu > 0.0) || !(Ruu < 1e300)) ok = false;
     const double Rinv = 1.0 / Ruu;
 #pragma unroll
-    for (int i = 0; i < 7; ++i) W.fa(F_K + i, k) = -Rux[i] * Rinv;
-    W.fa(F_KFF, k) = -ru * Rinv;
+    for (int i = 0; i < 7; ++i) WS_AT(sp, F_K + i) = -Rux[i] * Rinv;
+    WS_AT(sp, F_KFF) = -ru * Rinv;
+    double RuxS[7];
 #pragma unroll
-    for (int i = 0; i < 7; ++i) {
+    for (int i = 0; i < 7; ++i) RuxS[i] = Rux[i] * Rinv;
+    // P_{k-1} = Wt - Rux Rux^T / Ruu   (symmetrised), stored packed (rows 0..6, lower triangle)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
 #pragma unroll
       for (int j = 0; j <= i; ++j) {
-        const double v = 0.5 * (Wf[i][j] + Wf[j][i]) - Rux[i] * Rux[j] * Rinv;
-        Pm[pidx(i, j)] = v;
-        W.fa(F_P + pidx(i, j), k) = v;
+        const double v = 0.5 * (A[i][j] + A[j][i]) - Rux[i] * RuxS[j];
+        A[i][j] = v; A[j][i] = v;
+        WS_AT(sp, F_P + pidx(i, j)) = v;
       }
-      pv[i] = rx[i] - Rux[i] * ru * Rinv;
-      W.fa(F_PV + i, k) = pv[i];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const double v = Bm[i][j] - Rux[i] * RuxS[4 + j];
+        Bm[i][j] = v;
+        WS_AT(sp, F_P + pidx(4 + j, i)) = v;
+      }
     }
+    C00 -= Rux[4] * RuxS[4]; C01 -= Rux[4] * RuxS[5]; C02 -= Rux[4] * RuxS[6];
+    C11 -= Rux[5] * RuxS[5]; C12 -= Rux[5] * RuxS[6]; C22 -= Rux[6] * RuxS[6];
+    WS_AT(sp, F_P + pidx(4, 4)) = C00; WS_AT(sp, F_P + pidx(5, 4)) = C01; WS_AT(sp, F_P + pidx(6, 4)) = C02;
+    WS_AT(sp, F_P + pidx(5, 5)) = C11; WS_AT(sp, F_P + pidx(6, 5)) = C12;
+#pragma unroll
+    for (int i = 0; i < 7; ++i) pv[i] = rx[i] - RuxS[i] * ru;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) WS_AT(sp, F_PV + i) = pv[i];
 #pragma unroll
     for (int i = 0; i < 6; ++i) zn[i] = zm[i];
     if (!ok) return false;
   }
   // free initial tf: minimise 0.5 P66 dtf^2 + p6 dtf
-  const double P66 = Pm[pidx(6, 6)];
-  if (!(P66 > 0.0)) return false;
-  *dtf_out = -pv[6] / P66;
-  *p0_out = P66;
+  if (!(C22 > 0.0)) return false;
+  *dtf_out = -pv[6] / C22;
+  *p0_out = C22;
   return true;
 }
 
@@ -593,38 +694,61 @@ LM_HD bool riccati_backward(const Params& P, const Mesh& M, const Options& O, co
 // ---------------------------------------------------------------------------------------
 struct StepInfo { double a_max, a_z, dphi, dxmax, pimax; };
 
-LM_HD void riccati_forward(const Params& P, const Mesh& M, const Options& O, const Ws& W, int src,
-                           const Scal& c0, double mu, double tau, double dtf, bool ls, TermStep& ts, StepInfo& si) {
+// running maximum of num/den (den > 0) without dividing: keeps the pair
+struct RatioMax {
+  double n, d;
+  LM_HD void init() { n = 0.0; d = 1.0; }
+  LM_HD void push(double num, double den) { if (num * d > n * den) { n = num; d = den; } }
+};
+
+LM_NOINLINE void riccati_forward(const Params& P, const Mesh& M, const Options& O, const Ws& W, int src,
+                                 const Scal& c0, double mu, double tau, double dtf, bool ls, TermStep& ts,
+                                 StepInfo& si) {
   const int N = M.N;
   const double tf = c0.tf;
+  const int so = src * N_ITER;
+  const double mT = P.mflow * P.T;
   double ds[7] = {0, 0, 0, 0, 0, 0, dtf};
   double zm[6] = {0, 0, 0, 0, 0, 0};
-  double amax = 1.0, az = 1.0, dphi = 0.0, dxmax = fabs(dtf), pimax = 0.0;
+  double dphi = 0.0, dxmax = fabs(dtf), pimax = 0.0;
+  RatioMax rp, rz;      // max of (-dx/slack) over primal bounds, (-dz/z) over bound multipliers
+  rp.init(); rz.init();
   const double cw = ls ? 0.0 : 1.0;   // defects are dropped in the least-squares mode
   for (int k = 1; k <= N; ++k) {
+    double* sp = W.stage(k);
     double zn[6];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) zn[i] = W.it(src, F_Z + i, k);
-    const double u = W.it(src, F_U, k);
+    for (int i = 0; i < 6; ++i) zn[i] = WS_AT(sp, so + F_Z + i);
+    const double u = WS_AT(sp, so + F_U);
     const double kap = M.h[k] * P.T;
-    const double taum = P.mflow * P.T * M.tau[k];
+    const double taum = mT * M.tau[k];
     Accel1 f;
     accel_first(P, zn[0], zn[2], zn[4], taum * tf, f);
     StageJac J;
     stagejac_build(P, kap, tf, taum, f, zn[1], zn[3], zn[5], u, J);
+    stagejac_invert(J);
     const double al = J.al;
-    // new multipliers  pi_k = -(P_{k-1} ds_{k-1} + p_{k-1})
+    // new multipliers  pi_k = -(P_{k-1} ds_{k-1} + p_{k-1}),  rows 0..5
+    {
+      double acc[6];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      double acc = W.fa(F_PV + i, k);
+      for (int i = 0; i < 6; ++i) acc[i] = WS_AT(sp, F_PV + i);
 #pragma unroll
-      for (int j = 0; j < 7; ++j) acc = fma(W.fa(F_P + (i >= j ? pidx(i, j) : pidx(j, i)), k), ds[j], acc);
-      W.st(F_PI + i, k) = -acc;
-      pimax = dmax(pimax, fabs(acc));
+      for (int i = 0; i < 7; ++i) {
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+          if (i == 6 && j == 6) continue;
+          const double pij = WS_AT(sp, F_P + pidx(i, j));
+          if (i < 6) acc[i] = fma(pij, ds[j], acc[i]);
+          if (j < i && j < 6) acc[j] = fma(pij, ds[i], acc[j]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 6; ++i) { WS_AT(sp, F_PI + i) = -acc[i]; pimax = dmax(pimax, fabs(acc[i])); }
     }
-    double du = W.fa(F_KFF, k);
+    double du = WS_AT(sp, F_KFF);
 #pragma unroll
-    for (int i = 0; i < 7; ++i) du = fma(W.fa(F_K + i, k), ds[i], du);
+    for (int i = 0; i < 7; ++i) du = fma(WS_AT(sp, F_K + i), ds[i], du);
     double xi[7];
     xi[0] = ds[0] - cw * (zn[0] - zm[0] - al * zn[1]);
     xi[1] = ds[1] - cw * (zn[1] - zm[1] - al * f.ay);
@@ -635,27 +759,23 @@ LM_HD void riccati_forward(const Params& P, const Mesh& M, const Options& O, con
     xi[6] = dtf;
     solveE(J, xi);
 #pragma unroll
-    for (int i = 0; i < 6; ++i) { ds[i] = xi[i]; W.st(F_DS + i, k) = xi[i]; zm[i] = zn[i]; dxmax = dmax(dxmax, fabs(xi[i])); }
-    W.st(F_DU, k) = du;
+    for (int i = 0; i < 6; ++i) { ds[i] = xi[i]; WS_AT(sp, F_DS + i) = xi[i]; zm[i] = zn[i]; dxmax = dmax(dxmax, fabs(xi[i])); }
+    WS_AT(sp, F_DU) = du;
     dxmax = dmax(dxmax, fabs(du));
     // fraction to the boundary (IPOPT eq. 15) for angle and control, and their multipliers
     const double da = ds[4];
     const double dLa = zn[4], dUa = P.a_ub - zn[4], dLu = u + P.u_ub, dUu = P.u_ub - u;
-    if (da < 0) amax = dmin(amax, -tau * dLa / da);
-    if (da > 0) amax = dmin(amax, tau * dUa / da);
-    if (du < 0) amax = dmin(amax, -tau * dLu / du);
-    if (du > 0) amax = dmin(amax, tau * dUu / du);
-    const double zla = W.it(src, F_ZLA, k), zua = W.it(src, F_ZUA, k);
-    const double zlu = W.it(src, F_ZLU, k), zuu = W.it(src, F_ZUU, k);
-    const double d1 = mu / dLa - zla - zla / dLa * da;
-    const double d2 = mu / dUa - zua + zua / dUa * da;
-    const double d3 = mu / dLu - zlu - zlu / dLu * du;
-    const double d4 = mu / dUu - zuu + zuu / dUu * du;
-    if (d1 < 0) az = dmin(az, -tau * zla / d1);
-    if (d2 < 0) az = dmin(az, -tau * zua / d2);
-    if (d3 < 0) az = dmin(az, -tau * zlu / d3);
-    if (d4 < 0) az = dmin(az, -tau * zuu / d4);
-    dphi += (-mu / dLa + mu / dUa) * da + (-mu / dLu + mu / dUu) * du;
+    rp.push(-da, dLa); rp.push(da, dUa); rp.push(-du, dLu); rp.push(du, dUu);
+    const double zla = WS_AT(sp, so + F_ZLA), zua = WS_AT(sp, so + F_ZUA);
+    const double zlu = WS_AT(sp, so + F_ZLU), zuu = WS_AT(sp, so + F_ZUU);
+    double rLa, rUa, rLu, rUu;
+    recip4(dLa, dUa, dLu, dUu, rLa, rUa, rLu, rUu);
+    const double d1 = (mu - zla * da) * rLa - zla;
+    const double d2 = (mu + zua * da) * rUa - zua;
+    const double d3 = (mu - zlu * du) * rLu - zlu;
+    const double d4 = (mu + zuu * du) * rUu - zuu;
+    rz.push(-d1, zla); rz.push(-d2, zua); rz.push(-d3, zlu); rz.push(-d4, zuu);
+    dphi += mu * ((rUa - rLa) * da + (rUu - rLu) * du);
   }
   // terminal slacks and multipliers
   {
@@ -674,18 +794,15 @@ LM_HD void riccati_forward(const Params& P, const Mesh& M, const Options& O, con
     const double dLt = tf, dUt = P.tf_ub - tf;
     ts.dzLt = mu / dLt - c0.zLt - c0.zLt / dLt * dtf;
     ts.dzUt = mu / dUt - c0.zUt + c0.zUt / dUt * dtf;
-    if (ts.dsg1 < 0) amax = dmin(amax, -tau * c0.sg1 / ts.dsg1);
-    if (ts.dsg2 < 0) amax = dmin(amax, -tau * c0.sg2 / ts.dsg2);
-    if (dtf < 0) amax = dmin(amax, -tau * dLt / dtf);
-    if (dtf > 0) amax = dmin(amax, tau * dUt / dtf);
-    if (ts.dzs1 < 0) az = dmin(az, -tau * c0.zs1 / ts.dzs1);
-    if (ts.dzs2 < 0) az = dmin(az, -tau * c0.zs2 / ts.dzs2);
-    if (ts.dzLt < 0) az = dmin(az, -tau * c0.zLt / ts.dzLt);
-    if (ts.dzUt < 0) az = dmin(az, -tau * c0.zUt / ts.dzUt);
+    rp.push(-ts.dsg1, c0.sg1); rp.push(-ts.dsg2, c0.sg2); rp.push(-dtf, dLt); rp.push(dtf, dUt);
+    rz.push(-ts.dzs1, c0.zs1); rz.push(-ts.dzs2, c0.zs2); rz.push(-ts.dzLt, c0.zLt); rz.push(-ts.dzUt, c0.zUt);
     dphi += (O.obj_scale - mu / dLt + mu / dUt) * dtf - mu / c0.sg1 * ts.dsg1 - mu / c0.sg2 * ts.dsg2;
     dxmax = dmax(dxmax, dmax(fabs(ts.dsg1), fabs(ts.dsg2)));
   }
-  si.a_max = amax; si.a_z = az; si.dphi = dphi; si.dxmax = dxmax; si.pimax = pimax;
+  // alpha_max = min(1, tau / max ratio)
+  si.a_max = (rp.n * 1.0 > tau * rp.d) ? tau * rp.d / rp.n : 1.0;
+  si.a_z = (rz.n * 1.0 > tau * rz.d) ? tau * rz.d / rz.n : 1.0;
+  si.dphi = dphi; si.dxmax = dxmax; si.pimax = pimax;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -699,9 +816,12 @@ LM_HD double kkt_error(const Scal& s, double mu, int n_eq, int n_bd) {
   return dmax(dmax(s.dual_inf / sd, s.prim_inf), comp / sc);
 }
 
+// IPOPT's Compare_le: a <= b up to 10 machine epsilons of a reference magnitude.
+LM_HD bool cmp_le(double a, double b, double ref) { return a - b <= 2.2204460492503131e-15 * fabs(ref); }
+
 LM_HD bool filter_ok(const Ctl& c, double th, double ph) {
   for (int i = 0; i < c.nf; ++i)
-    if (th >= c.ft[i] && ph >= c.fp[i]) return false;
+    if (!cmp_le(th, c.ft[i], c.ft[i]) && !cmp_le(ph, c.fp[i], c.fp[i])) return false;
   return true;
 }
 
@@ -718,7 +838,7 @@ LM_HD void filter_add(Ctl& c, double th, double ph) {
   c.nf = n;
 }
 
-// One complete solve of one problem.  `W.j` selects the slot.  Output goes to the caller.
+// One complete solve of one problem.  Output goes to the caller.
 struct SolveOut { double tf; int status; int iters; double kkt; double mu; int cur; };
 
 LM_HD void ipm_solve(const Params& P, const Mesh& M, const Options& O, const Ws& W, bool have_guess,
@@ -754,19 +874,34 @@ LM_HD void ipm_solve(const Params& P, const Mesh& M, const Options& O, const Ws&
   ctl.theta_max = 1e4 * dmax(1.0, cur.theta);
   ctl.theta_min = 1e-4 * dmax(1.0, cur.theta);
   double err0 = 1e300;
+  int polish_left = -1;
+  bool polishing = false;
   while (true) {
     err0 = kkt_error(cur, 0.0, n_eq, n_bd);
-    if (err0 <= O.tol) { ctl.status = ST_CONVERGED; break; }
-    if (ctl.iter >= O.max_iter) { ctl.status = ST_MAX_ITER; break; }
     // barrier parameter update (IPOPT eq. 7)
-    bool mu_changed = false;
-    while (kkt_error(cur, ctl.mu, n_eq, n_bd) <= O.kappa_eps * ctl.mu && ctl.mu > O.tol / 10.0 * (1.0 + 1e-12)) {
-      ctl.mu = dmax(O.tol / 10.0, dmin(O.kappa_mu * ctl.mu, pow(ctl.mu, O.theta_mu)));
+    const double mu_min = O.tol * O.mu_min_factor;
+    // (the sub-problem tolerance kappa_eps*mu is floored at tol: below that it would ask for more
+    //  than the final test does, and more than FP64 can deliver for the dual residual)
+    while (kkt_error(cur, ctl.mu, n_eq, n_bd) <= dmax(O.kappa_eps * ctl.mu, O.tol) && ctl.mu > mu_min * (1.0 + 1e-12)) {
+      ctl.mu = dmax(mu_min, dmin(O.kappa_mu * ctl.mu, ctl.mu * sqrt(ctl.mu)));   // theta_mu = 1.5
       ctl.tau = dmax(O.tau_min, 1.0 - ctl.mu);
       ctl.nf = 0;
-      mu_changed = true;
     }
-    (void)mu_changed;
+    // Converged = scaled KKT error <= tol with the barrier parameter at its floor.  Requiring the
+    // floor pins the final point on the central path: the control on the singular arc is a nearly
+    // flat direction of this NLP and moves like O(mu / sigma_min) (DESIGN.md "Tolerance").
+    if (err0 <= O.tol && ctl.mu <= mu_min * (1.0 + 1e-12)) {
+      // Newton converges quadratically here; `n_polish` more iterations take the point from
+      // "residual <= tol" to the FP64 floor, which is what makes two implementations agree on the
+      // weakly determined control.  A polish step that fails leaves the converged point in place.
+      if (polish_left < 0) polish_left = O.n_polish;
+      if (polish_left == 0) { ctl.status = ST_CONVERGED; break; }
+      --polish_left;
+      polishing = true;
+    } else {
+      polishing = false;
+    }
+    if (ctl.iter >= O.max_iter) { ctl.status = polishing ? ST_CONVERGED : ST_MAX_ITER; break; }
     // factorisation with inertia correction (IPOPT Algorithm IC)
     double dw = 0.0, dtf = 0.0, p0 = 0.0;
     bool fact_ok = false;
@@ -776,11 +911,11 @@ LM_HD void ipm_solve(const Params& P, const Mesh& M, const Options& O, const Ws&
       else dw *= (ctl.dw_last == 0.0) ? 100.0 : 8.0;
       if (dw > 1e40) break;
     }
-    if (!fact_ok) { ctl.status = ST_INERTIA_FAIL; break; }
+    if (!fact_ok) { ctl.status = polishing ? ST_CONVERGED : ST_INERTIA_FAIL; break; }
     if (dw > 0.0) ctl.dw_last = dw;
     StepInfo si;
     riccati_forward(P, M, O, W, src, cur, ctl.mu, ctl.tau, dtf, false, ts, si);
-    if (!(si.dphi == si.dphi) || !(si.dxmax < 1e300)) { ctl.status = ST_NUMERICAL; break; }
+    if (!(si.dphi == si.dphi) || !(si.dxmax < 1e300)) { ctl.status = polishing ? ST_CONVERGED : ST_NUMERICAL; break; }
     // filter line search (IPOPT section 2.3)
     const double theta = cur.theta;
     const double phi = cur.fobj - ctl.mu * cur.sumlog;
@@ -788,24 +923,33 @@ LM_HD void ipm_solve(const Params& P, const Mesh& M, const Options& O, const Ws&
     const double g_th = 1e-5, g_ph = 1e-8, s_th = 1.1, s_ph = 2.3, eta = 1e-8, delta = 1.0;
     double alpha = si.a_max;
     bool accepted = false, ftype = false;
-    for (int ls = 0; ls < O.max_ls; ++ls) {
+    // switching condition (IPOPT eq. 19): alpha * (-dphi)^s_ph > delta * theta^s_th.  The two powers
+    // do not depend on alpha, so they are evaluated once per iteration.
+    const bool sw_possible = (theta <= ctl.theta_min) && (dphi < 0.0);
+    const double sw_lhs = sw_possible ? pow(-dphi, s_ph) : 0.0;
+    const double sw_rhs = sw_possible ? delta * pow(theta, s_th) : 0.0;
+    for (int lsi = 0; lsi < O.max_ls; ++lsi) {
       eval_pass(P, M, O, W, src, 1 - src, cur, ts, ctl.mu, alpha, si.a_z, alpha, trial);
       const double th_t = trial.theta;
       const double ph_t = trial.fobj - ctl.mu * trial.sumlog;
       bool ok = (th_t <= ctl.theta_max) && (ph_t == ph_t) && (ph_t < 1e299) && filter_ok(ctl, th_t, ph_t);
       if (ok) {
-        ftype = (theta <= ctl.theta_min) && (dphi < 0.0) &&
-                (alpha * pow(-dphi, s_ph) > delta * pow(theta, s_th));
-        if (ftype) ok = ph_t <= phi + eta * alpha * dphi + 2.2e-15 * fabs(phi);
-        else ok = (th_t <= (1.0 - g_th) * theta) || (ph_t <= phi - g_ph * theta);
+        ftype = sw_possible && (alpha * sw_lhs > sw_rhs);
+        if (ftype) ok = cmp_le(ph_t - phi, eta * alpha * dphi, phi);
+        else ok = cmp_le(th_t, (1.0 - g_th) * theta, theta) || cmp_le(ph_t - phi, -g_ph * theta, phi);
       }
+      // Terminal phase (analogue of IPOPT's tiny-step rule): once the violation is below tol before
+      // and after the step and the merit changes by less than tol (relative), both filter measures
+      // are rounding noise and cannot rank points any more; the Newton step is taken as is.
+      if (!ok && lsi == 0 && theta <= O.tol && th_t <= O.tol && (ph_t == ph_t) &&
+          fabs(ph_t - phi) <= O.tol * dmax(1.0, fabs(phi))) { ok = true; ftype = true; }
       if (ok) { accepted = true; break; }
       alpha *= 0.5;
     }
 #if defined(LMATO_TRACE) && !defined(__CUDA_ARCH__)
     if (!accepted) printf("LS FAIL theta %.3e phi %.6e dphi %.3e amax %.3e dx %.2e th_t %.3e ph_t %.6e\n", theta, phi, dphi, si.a_max, si.dxmax, trial.theta, trial.fobj - ctl.mu * trial.sumlog);
 #endif
-    if (!accepted) { ctl.status = ST_LINESEARCH_FAIL; break; }
+    if (!accepted) { ctl.status = polishing ? ST_CONVERGED : ST_LINESEARCH_FAIL; break; }
     if (!ftype) filter_add(ctl, (1.0 - g_th) * theta, phi - g_ph * theta);
     cur = trial; src = 1 - src;
     ++ctl.iter;

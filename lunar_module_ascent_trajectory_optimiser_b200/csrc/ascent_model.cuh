@@ -22,9 +22,11 @@
 #if defined(__CUDACC__)
 #define LM_HD __host__ __device__ __forceinline__
 #define LM_D __device__ __forceinline__
+#define LM_NOINLINE __host__ __device__ __noinline__
 #else
 #define LM_HD inline
 #define LM_D inline
+#define LM_NOINLINE
 #endif
 
 namespace lmato {
@@ -47,7 +49,16 @@ struct Params {
   double R0S;     // R0 / S                      LO:161
   double tf_ub;   // min(1, 1/(mflow*T)): tf<=1 (LO:39) and mass<=1 (LO:83) at the last node
   double fuel;    // fuel_mass (for final-mass output)
+  double Sinv;    // 1 / S
 };
+
+LM_HD double lm_rsqrt(double x) {
+#if defined(__CUDA_ARCH__)
+  return rsqrt(x);
+#else
+  return 1.0 / sqrt(x);
+#endif
+}
 
 LM_HD void lm_sincos(double a, double* s, double* c) {
 #if defined(__CUDA_ARCH__)
@@ -71,7 +82,7 @@ LM_HD void accel_first(const Params& P, double y, double x, double a, double m, 
   const double X = x * P.S;
   const double Y = fma(y, P.S, P.R0);
   const double r2 = fma(X, X, Y * Y);
-  const double rinv = 1.0 / sqrt(r2);
+  const double rinv = lm_rsqrt(r2);
   const double nx = X * rinv, ny = Y * rinv;
   double s3, c3;
   lm_sincos(3.0 * a, &s3, &c3);
@@ -82,7 +93,7 @@ LM_HD void accel_first(const Params& P, double y, double x, double a, double m, 
   const double eta = P.ms * mden;              // d ln(AT) / d mass
   const double g2 = P.GM * rinv * rinv;        // GM / r^2
   const double g3 = g2 * rinv;                 // GM / r^3
-  const double Sinv = 1.0 / P.S;
+  const double Sinv = P.Sinv;
   o.ay = (AT * Ty - g2 * ny) * Sinv;
   o.ax = (AT * Tx - g2 * nx) * Sinv;
   const double ATr = AT * rinv;
@@ -96,6 +107,21 @@ LM_HD void accel_first(const Params& P, double y, double x, double a, double m, 
   o.ay_m = AT * eta * Ty * Sinv;
   o.ax_m = AT * eta * Tx * Sinv;
   o.nx = nx; o.ny = ny; o.rinv = rinv; o.Tx = Tx; o.Ty = Ty; o.AT = AT; o.eta = eta; o.g3 = g3;
+}
+
+// Acceleration values only (LO:127-136), used by the start-point roll-out and the output pass.
+LM_HD void accel_value(const Params& P, double y, double x, double a, double m, double& ay, double& ax) {
+  const double X = x * P.S;
+  const double Y = fma(y, P.S, P.R0);
+  const double r2 = fma(X, X, Y * Y);
+  const double rinv = lm_rsqrt(r2);
+  const double nx = X * rinv, ny = Y * rinv;
+  double s3, c3;
+  lm_sincos(3.0 * a, &s3, &c3);
+  const double AT = P.Ft / (P.M0 - P.ms * m);
+  const double g2 = P.GM * rinv * rinv;
+  ay = (AT * fma(ny, c3, nx * s3) - g2 * ny) * P.Sinv;
+  ax = (AT * fma(nx, c3, -ny * s3) - g2 * nx) * P.Sinv;
 }
 
 // Second derivatives of  Psi = l1*ay + l3*ax  w.r.t. (y, x, angle, mass), scaled coordinates.
@@ -125,7 +151,7 @@ LM_HD void accel_second(const Params& P, const Accel1& f, double l1, double l3, 
   HXX += k * (2.0 * l3 * nx + ln - 5.0 * ln * nx * nx);
   HYY += k * (2.0 * l1 * ny + ln - 5.0 * ln * ny * ny);
   HXY += k * (l3 * ny + l1 * nx - 5.0 * ln * nx * ny);
-  const double S = P.S, Sinv = 1.0 / P.S;
+  const double S = P.S, Sinv = P.Sinv;
   h.yy = HYY * S; h.yx = HXY * S; h.xx = HXX * S;
   h.ya = HYa;     h.xa = HXa;     h.aa = Haa * Sinv;
   const double Ae = A * f.eta;

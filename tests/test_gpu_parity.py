@@ -18,7 +18,7 @@ VAR_ROWS = ["y", "ydot", "ydoubledot", "x", "xdot", "xdoubledot", "angle", "angl
 TF_RTOL = 1e-4
 MASS_RTOL = 1e-6
 STATE_RTOL = 1e-4
-CONTROL_RTOL = 5e-3
+CONTROL_RTOL = 2e-4
 
 
 @pytest.fixture(scope="module")
@@ -42,9 +42,11 @@ def _check_against(gold_tf, gold_fm, gold_traj, tf, fm, traj, tight=True):
     scale = np.abs(gold_traj).max(axis=1, keepdims=True) + 1e-300
     err = (np.abs(traj - gold_traj) / scale).max(axis=1)
     assert err[:9].max() < STATE_RTOL, err          # the nine GEKKO Vars (LO:83-95)
-    # The MV on the singular arc is a nearly flat direction of the NLP: it converges like
-    # O(mu / sigma_min) (2e-2 between tol 1e-9 and 1e-10, 9e-4 between 1e-10 and 1e-11 in the
-    # oracle itself), so it is held to a looser bar than the states.  See DESIGN.md "Tolerance".
+    # The MV on the singular arc is a nearly flat direction of the NLP: it moves like
+    # O(mu / sigma_min) along the central path (2e-2 between tol 1e-9 and 1e-10 in the oracle
+    # itself).  The fixtures and the device solver therefore end at the same barrier parameter
+    # (1e-13); at that point the two implementations agree on the control too.  See DESIGN.md
+    # "Tolerance".
     assert err[9] < CONTROL_RTOL, err
     if tight:   # what is actually achieved
         assert abs(tf - gold_tf) / gold_tf < 1e-7

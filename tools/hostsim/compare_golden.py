@@ -1,0 +1,26 @@
+"""Developer tool: run the g++ build of the device solver core on the golden dispersion inputs
+and report deviations from tests/golden (no GPU needed).  Not part of the product or the tests."""
+import ctypes as C, os, subprocess, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+so = "/tmp/libhostsim.so"
+subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-I",
+                       os.path.join(ROOT, "lunar_module_ascent_trajectory_optimiser_b200", "csrc"),
+                       os.path.join(ROOT, "tools", "hostsim", "hostsim.cpp"), "-o", so])
+L = C.CDLL(so)
+tol = float(sys.argv[1]) if len(sys.argv) > 1 else 1e-10
+mmf = float(sys.argv[2]) if len(sys.argv) > 2 else 1e-3
+g = np.load(os.path.join(ROOT, "tests", "golden", "elliptical_dispersions8_seed11_nt200.npz"))
+nt = 200
+worst = np.zeros(10)
+for b in range(8):
+    raw = np.ascontiguousarray(g["rows"][:, b])
+    traj = np.empty((10, nt)); tf = C.c_double(); it = C.c_int(); kkt = C.c_double()
+    st = L.hostsim_solve(raw.ctypes.data_as(C.c_void_p), nt, None, C.c_double(tol), C.c_double(10.0), C.c_double(mmf),
+                         traj.ctypes.data_as(C.c_void_p), C.byref(tf), C.byref(it), C.byref(kkt))
+    gt = g["traj"][b]
+    err = (np.abs(traj - gt) / np.abs(gt).max(axis=1, keepdims=True)).max(axis=1)
+    worst = np.maximum(worst, err)
+    print(b, "status", st, "iters", it.value, "kkt %.1e" % kkt.value, "tf rel %.1e" % (abs(tf.value - g["tf"][b]) / g["tf"][b]),
+          "angledot %.1e control %.1e others %.1e" % (err[7], err[9], np.delete(err, [7, 9]).max()))
+print("worst per row:", " ".join("%.1e" % e for e in worst))

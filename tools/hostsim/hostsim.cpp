@@ -27,7 +27,7 @@ static Params make_params(double Ft, double M0, double Mdot, double addm, double
   P.vt2 = (vt / P.S) * (vt / P.S);
   P.rt = (R0 + P.S) / P.S; P.R0S = R0 / P.S;
   P.tf_ub = std::fmin(1.0, 1.0 / (P.mflow * T));
-  P.fuel = fuel;
+  P.fuel = fuel; P.Sinv = 1.0 / P.S;
   return P;
 }
 
@@ -41,15 +41,17 @@ int main(int argc, char** argv) {
   for (int k = 0; k <= N; ++k) { tau[k] = (double)k / N; h[k] = k ? tau[k] - tau[k - 1] : 0.0; }
   Mesh M{N, h.data(), tau.data()};
   Options O;
-  O.tol = 1e-8; O.mu_init = 0.1; O.obj_scale = 100.0; O.kappa_eps = 10.0; O.kappa_mu = 0.2; O.theta_mu = 1.5;
-  O.tau_min = 0.99; O.delta_c = 1e-8; O.tf_guess = 0.9; O.max_iter = 500; O.max_ls = 40;
+  O.tol = 1e-10; O.mu_init = 0.1; O.obj_scale = 10.0; O.kappa_eps = 10.0; O.kappa_mu = 0.2; O.theta_mu = 1.5;
+  O.tau_min = 0.99; O.delta_c = 1e-8; O.tf_guess = 0.9; O.max_iter = 500; O.max_ls = 40; O.mu_min_factor = 1e-3; O.n_polish = 2;
+  if (getenv("MMF")) O.mu_min_factor = atof(getenv("MMF"));
+  if (getenv("NPOL")) O.n_polish = atoi(getenv("NPOL"));
   if (getenv("OBJ")) O.obj_scale = atof(getenv("OBJ"));
   if (getenv("MU0")) O.mu_init = atof(getenv("MU0"));
   if (getenv("TOL")) O.tol = atof(getenv("TOL"));
   if (getenv("TF0")) O.tf_guess = atof(getenv("TF0"));
   if (getenv("DC")) O.delta_c = atof(getenv("DC"));
-  std::vector<double> ws((size_t)N_FIELDS * (N + 1), 0.0);
-  Ws W{ws.data(), 1, N + 1, 0};
+  std::vector<double> ws((size_t)N_FIELDS * LANES * (N + 1), 0.0);   // one warp block, lane 0 used
+  Ws W{ws.data(), (long)N_FIELDS * LANES};
   std::mt19937_64 rng(11);
   std::uniform_real_distribution<double> U(0.0, 1.0);
   int nfail = 0, itsum = 0, itmax = 0;
@@ -75,11 +77,48 @@ int main(int argc, char** argv) {
              p, out.status, out.iters, out.kkt, out.mu, out.tf, out.tf * P.T, Ft, M0, Mdot, addm, rp, ra);
     if (p == 0 && nprob == 1) {
       const int b = out.cur;
-      printf("final y %.9f x %.9f vy %.9f vx %.9f\n", W.it(b, F_Z + 0, N) * P.S, W.it(b, F_Z + 2, N) * P.S,
-             W.it(b, F_Z + 1, N) * P.S, W.it(b, F_Z + 3, N) * P.S);
+      const double* sp = W.stage(N);
+      printf("final y %.9f x %.9f vy %.9f vx %.9f\n", WS_AT(sp, b * N_ITER + F_Z + 0) * P.S, WS_AT(sp, b * N_ITER + F_Z + 2) * P.S,
+             WS_AT(sp, b * N_ITER + F_Z + 1) * P.S, WS_AT(sp, b * N_ITER + F_Z + 3) * P.S);
       printf("final mass %.9f\n", P.M0 - P.fuel * P.mflow * P.T * out.tf);
     }
   }
   printf("solved %d problems: %d failures, mean iters %.1f, max %d\n", nprob, nfail, (double)itsum / nprob, itmax);
   return 0;
+}
+
+// ctypes entry for developer-side comparisons against tests/golden (NOT the product path).
+extern "C" int hostsim_solve(const double* raw14, int nt, const double* time, double tol, double obj_scale,
+                             double mu_min_factor, double* traj /* [10][nt] */, double* tf_out, int* iters, double* kkt) {
+  const int N = nt - 1;
+  std::vector<double> h(N + 1), tau(N + 1);
+  for (int k = 0; k <= N; ++k) { tau[k] = time ? time[k] : (double)k / N; h[k] = k ? tau[k] - tau[k - 1] : 0.0; }
+  Mesh M{N, h.data(), tau.data()};
+  Options O;
+  O.tol = tol; O.mu_init = 0.1; O.obj_scale = obj_scale; O.kappa_eps = 10.0; O.kappa_mu = 0.2; O.theta_mu = 1.5;
+  O.tau_min = 0.99; O.delta_c = 1e-8; O.tf_guess = 0.9; O.max_iter = 500; O.max_ls = 40; O.mu_min_factor = mu_min_factor; O.n_polish = getenv("NPOL") ? atoi(getenv("NPOL")) : 2;
+  Params P;
+  const double* r = raw14;
+  P.GM = r[0] * r[1]; P.R0 = r[2]; P.Ft = r[3]; P.M0 = r[4]; P.S = r[8]; P.ms = r[11]; P.mflow = r[5] / r[6];
+  P.asc = r[7] / 3.0; P.T = r[10]; P.a_ub = r[12]; P.u_ub = r[13];
+  const double vt = std::sqrt(P.GM / (P.R0 + 0.5 * (r[8] + r[9])));
+  P.vt2 = (vt / P.S) * (vt / P.S); P.rt = (P.R0 + P.S) / P.S; P.R0S = P.R0 / P.S;
+  P.tf_ub = std::fmin(1.0, 1.0 / (P.mflow * P.T)); P.fuel = r[6]; P.Sinv = 1.0 / P.S;
+  std::vector<double> ws((size_t)N_FIELDS * LANES * (N + 1), 0.0);
+  Ws W{ws.data(), (long)N_FIELDS * LANES};
+  SolveOut out;
+  ipm_solve(P, M, O, W, false, out);
+  *tf_out = out.tf; *iters = out.iters; *kkt = out.kkt;
+  for (int v = 0; v < 10; ++v) traj[v * nt] = 0.0;
+  for (int k = 1; k <= N; ++k) {
+    const double* sp = W.stage(k);
+    double z[6];
+    for (int i = 0; i < 6; ++i) z[i] = WS_AT(sp, out.cur * N_ITER + F_Z + i);
+    const double m = P.mflow * P.T * tau[k] * out.tf;
+    double ay, ax;
+    accel_value(P, z[0], z[2], z[4], m, ay, ax);
+    const double vals[10] = {z[0], z[1], ay, z[2], z[3], ax, z[4], z[5], m, WS_AT(sp, out.cur * N_ITER + F_U)};
+    for (int v = 0; v < 10; ++v) traj[v * nt + k] = vals[v];
+  }
+  return out.status;
 }
