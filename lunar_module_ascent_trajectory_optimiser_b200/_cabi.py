@@ -13,7 +13,7 @@ import sys
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblmato_b200.so")
+LIB_PATH = os.environ.get("LMATO_LIB_OVERRIDE") or os.path.join(_HERE, "liblmato_b200.so")   # override: developer A/B builds only
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 

@@ -39,8 +39,11 @@ void set_err(const char* fmt, const char* a = "", const char* b = "") {
     }                                                                         \
   } while (0)
 
+#ifndef LMATO_BLOCKS_PER_SM
+#define LMATO_BLOCKS_PER_SM 4
+#endif
 constexpr int kBlock = 64;          // threads per CTA (2 warps)
-constexpr int kBlocksPerSM = 4;     // 256 threads/SM at <=255 registers
+constexpr int kBlocksPerSM = LMATO_BLOCKS_PER_SM;   // 4 -> 256 threads/SM at <=255 registers
 
 struct KArgs {
   const double* params;  // [NPARAM][B]

@@ -63,14 +63,13 @@ enum : int {
   F_DU = R_STEP + 6,
   F_PI = R_STEP + 7,   // 6: new defect multipliers
   N_STEP = 13,
-  // factor, rows [47,88)
+  // factor, rows [47,55): only the feedback law leaves the SM (the cost-to-go P, p stays in
+  // registers during the backward sweep; multipliers are recovered by an adjoint recursion)
   R_FACT = R_STEP + N_STEP,
   F_K = R_FACT + 0,    // 7 feedback gains
   F_KFF = R_FACT + 7,
-  F_P = R_FACT + 8,    // 27: packed lower triangle of P_{k-1} without the (tf,tf) entry
-  F_PV = F_P + 27,     // 6: p_{k-1} without the tf entry
-  N_FACT = 8 + 27 + 6,
-  N_FIELDS = 2 * N_ITER + N_STEP + N_FACT   // 88 doubles per stage per problem
+  N_FACT = 8,
+  N_FIELDS = 2 * N_ITER + N_STEP + N_FACT   // 55 doubles per stage per problem
 };
 constexpr int LANES = 32;
 
@@ -87,6 +86,34 @@ struct Ws {
   LM_HD double* stage(int k) const { return p + (long)k * SS; }
 };
 #define WS_AT(sp, row) (sp)[(row) * LANES]
+
+// Software prefetch of workspace rows into L1.  The sweeps are latency-bound otherwise: with 255
+// registers per thread only 8 warps are resident per SM, far too few to hide an HBM round trip
+// per stage.  A prefetch costs no registers; issued PF_DIST stages ahead it turns the dependent
+// load at the top of each stage into an L1 hit.
+#ifndef LMATO_PF_DIST
+#define LMATO_PF_DIST 1
+#endif
+#ifndef LMATO_PF_LEVEL
+#define LMATO_PF_LEVEL 1
+#endif
+constexpr int PF_DIST = LMATO_PF_DIST;
+LM_HD void pf_row(const double* sp, int row) {
+#if defined(__CUDA_ARCH__)
+#if LMATO_PF_LEVEL == 1
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(sp + row * LANES));
+#elif LMATO_PF_LEVEL == 2
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(sp + row * LANES));
+#endif
+#else
+  (void)sp; (void)row;
+#endif
+}
+template <int R0, int R1>
+LM_HD void pf_rows(const double* sp, int base) {
+#pragma unroll
+  for (int r = R0; r < R1; ++r) pf_row(sp, base + r);
+}
 
 constexpr int NFILT = 12;
 
@@ -288,44 +315,242 @@ LM_NOINLINE void init_guess(const Params& P, const Mesh& M, const Options& O, co
 }
 
 // ---------------------------------------------------------------------------------------
-// evaluation pass: trial point  x + alpha*dx  (alpha=0: the current point).
-// Writes the trial iterate into buffer `dst`, returns its merit / error ingredients.
+// shared building blocks of the Newton system (used by the factorisation AND by the adjoint
+// recursion, so that both see exactly the same Hessian)
 // ---------------------------------------------------------------------------------------
 struct TermStep { double dtf, dsg1, dsg2, dzs1, dzs2, dnu3, dzLt, dzUt; };
 
+// Terminal rows condensed onto the last node (LO:161, 169, 173): Hessian block on (y,vy,x,vx)
+// [lower triangle], gradient, and the tf entries (objective + tf bound barrier).
+struct TermQP { double H[4][4]; double g[4]; double g6, H66; };
+
+LM_HD void terminal_qp(const Params& P, const Options& O, const Scal& c0, const double* zn, double mu,
+                       double dw, bool ls, TermQP& q) {
+  Terminal T;
+  terminal_eval(P, zn[0], zn[1], zn[2], zn[3], T);
+  const double rinv = 1.0 / T.rT;
+  const double g1y = T.Yb * rinv, g1x = zn[2] * rinv;
+  const double i1 = 1.0 / c0.sg1, i2 = 1.0 / c0.sg2;
+  const double w1 = ls ? 1.0 : c0.zs1 * i1, w2 = ls ? 1.0 : c0.zs2 * i2, w3 = 1.0 / O.delta_c;
+  const double c1 = T.g1 - c0.sg1, c2 = T.g2 - c0.sg2;
+  // gradient terms: grad g_i * (w_i c_i - mu/sg_i), grad g3 * (nu3 + g3/delta_c)
+  const double q1 = ls ? -c0.zs1 : w1 * c1 - mu * i1;
+  const double q2 = ls ? -c0.zs2 : w2 * c2 - mu * i2;
+  const double q3 = ls ? 0.0 : c0.nu3 + T.g3 * w3;
+  const double hz1 = ls ? 0.0 : c0.zs1, hz2 = ls ? 0.0 : c0.zs2, hn3 = ls ? 0.0 : c0.nu3;
+  const double G2y = 2.0 * zn[1], G2x = 2.0 * zn[3];
+  const double G3[4] = {zn[1], T.Yb, zn[3], zn[2]};     // grad g3 wrt (y, vy, x, vx)
+  q.g[0] = g1y * q1 + G3[0] * q3;
+  q.g[1] = G2y * q2 + G3[1] * q3;
+  q.g[2] = g1x * q1 + G3[2] * q3;
+  q.g[3] = G2x * q2 + G3[3] * q3;
+  // Hessian: w_i grad grad^T + multipliers * second derivatives (mult of g1,g2 = -zs)
+  const double r3 = rinv * rinv * rinv;
+  const double h1yy = zn[2] * zn[2] * r3, h1xx = T.Yb * T.Yb * r3, h1yx = -T.Yb * zn[2] * r3;
+  q.H[0][0] = w1 * g1y * g1y - hz1 * h1yy + w3 * G3[0] * G3[0];
+  q.H[2][0] = w1 * g1x * g1y - hz1 * h1yx + w3 * G3[2] * G3[0];
+  q.H[2][2] = w1 * g1x * g1x - hz1 * h1xx + w3 * G3[2] * G3[2];
+  q.H[1][1] = w2 * G2y * G2y - 2.0 * hz2 + w3 * G3[1] * G3[1];
+  q.H[3][1] = w2 * G2x * G2y + w3 * G3[3] * G3[1];
+  q.H[3][3] = w2 * G2x * G2x - 2.0 * hz2 + w3 * G3[3] * G3[3];
+  q.H[1][0] = w3 * G3[1] * G3[0] + hn3;
+  q.H[3][0] = w3 * G3[3] * G3[0];
+  q.H[2][1] = w3 * G3[2] * G3[1];
+  q.H[3][2] = w3 * G3[3] * G3[2] + hn3;
+  q.H[0][1] = q.H[1][0]; q.H[0][2] = q.H[2][0]; q.H[0][3] = q.H[3][0];
+  q.H[1][2] = q.H[2][1]; q.H[1][3] = q.H[3][1]; q.H[2][3] = q.H[3][2];
+  const double tf = c0.tf;
+  const double dLt = tf, dUt = P.tf_ub - tf;
+  q.g6 = ls ? O.obj_scale - c0.zLt + c0.zUt : O.obj_scale - mu / dLt + mu / dUt;
+  q.H66 = ls ? 1.0 : c0.zLt / dLt + c0.zUt / dUt + dw;
+}
+
+// Stage Hessian of the barrier Lagrangian on s = (y,vy,x,vx,a,w,tf) and u (sparse).
+struct StageQ {
+  double q00, q02, q22, q04, q24, q44;        // (y,x,a) block (includes delta_w and Sigma_a)
+  double q06, q16, q26, q36, q46, q56, q66;   // tf column
+  double d;                                   // diagonal of the (vy, vx, w) entries (= delta_w or 1)
+  double q4;                                  // gradient entry of `angle`
+  double R, r, sig;                           // control: Hessian, gradient, u-tf cross term
+};
+
+LM_HD void stage_hessian(const Params& P, const Accel1& f, const StageJac& J, double kap, double taum,
+                         const double* lam, double a, double u, double zla, double zua, double zlu,
+                         double zuu, double mu, double dw, bool ls, StageQ& q) {
+  if (!ls) {
+    double rLa, rUa, rLu, rUu;
+    recip4(a, P.a_ub - a, u + P.u_ub, P.u_ub - u, rLa, rUa, rLu, rUu);
+    Accel2 h2;
+    accel_second(P, f, lam[1], lam[3], h2);
+    const double al = J.al, alt = al * taum;
+    q.q00 = -al * h2.yy + dw;
+    q.q02 = -al * h2.yx;
+    q.q22 = -al * h2.xx + dw;
+    q.q04 = -al * h2.ya;
+    q.q24 = -al * h2.xa;
+    q.q44 = -al * h2.aa + zla * rLa + zua * rUa + dw;
+    q.d = dw;
+    const double Phy = lam[1] * f.ay_y + lam[3] * f.ax_y;
+    const double Phx = lam[1] * f.ay_x + lam[3] * f.ax_x;
+    const double Pha = lam[1] * f.ay_a + lam[3] * f.ax_a;
+    const double Phm = lam[1] * f.ay_m + lam[3] * f.ax_m;
+    q.q06 = -kap * Phy - alt * h2.ym;
+    q.q26 = -kap * Phx - alt * h2.xm;
+    q.q46 = -kap * Pha - alt * h2.am;
+    q.q16 = -kap * lam[0];
+    q.q36 = -kap * lam[2];
+    q.q56 = -kap * lam[4];
+    q.q66 = -2.0 * kap * Phm * taum - alt * h2.mm * taum;
+    q.q4 = mu * (rUa - rLa);
+    q.R = zlu * rLu + zuu * rUu + dw;
+    q.r = mu * (rUu - rLu);
+    q.sig = -kap * lam[5] * P.asc;   // u-tf cross term
+  } else {
+    q.q00 = 1.0; q.q02 = 0.0; q.q22 = 1.0; q.q04 = 0.0; q.q24 = 0.0; q.q44 = 1.0; q.d = 1.0;
+    q.q06 = q.q16 = q.q26 = q.q36 = q.q46 = q.q56 = q.q66 = 0.0;
+    q.q4 = -zla + zua;
+    q.R = 1.0; q.r = -zlu + zuu; q.sig = 0.0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// evaluation pass: trial point  x + alpha*dx  (alpha=0: the current point), swept from the
+// last node to the first.  Writes the trial iterate into buffer `dst` and returns its merit /
+// KKT-error ingredients.
+//
+// mode EV_READ_PI : the new defect multipliers pi_k are read from the workspace;
+// mode EV_NEWTON  : they are first computed by the adjoint recursion of the Newton system,
+//                     E_k^T pi_k = pi_{k+1} - (Q_k ds_k + q_k)      (old point, old multipliers)
+//                   and stored (a later back-tracking trial reads them).  This is what lets the
+//                   factorisation keep only the feedback gains: the 33 doubles of P_{k-1}, p_{k-1}
+//                   per stage never travel through HBM.
+// mode EV_LSQ     : same recursion for the least-squares multiplier estimate (Q = I).
+// ---------------------------------------------------------------------------------------
+enum : int { EV_READ_PI = 0, EV_NEWTON = 1, EV_LSQ = 2 };
+
 LM_NOINLINE void eval_pass(const Params& P, const Mesh& M, const Options& O, const Ws& W, int src, int dst,
-                           const Scal& c0, const TermStep& ts, double mu, double alpha, double alpha_z,
-                           double alpha_lam, Scal& t) {
+                           const Scal& c0, const TermStep& ts, double mu, double dw, double alpha,
+                           double alpha_z, double alpha_lam, int mode, Scal& t, double* pimax_out) {
   const int N = M.N;
-  t.tf = c0.tf + alpha * ts.dtf;
+  const double tf0 = c0.tf, dtf = ts.dtf;
+  t.tf = tf0 + alpha * dtf;
   const double tf = t.tf;
   const int so = src * N_ITER, dd = dst * N_ITER;
-  double zp[6] = {0, 0, 0, 0, 0, 0};      // previous node's trial state
-  double pend[6] = {0, 0, 0, 0, 0, 0};    // E_{k-1}^T lam_{k-1} + bound terms, awaiting -lam_k
+  const double mT = P.mflow * P.T;
+  const bool ls = (mode == EV_LSQ);
   double theta = 0, prim = 0, dual = 0, sumlog = 0, cmin = 1e300, cmax = 0, slam = 0, sz = 0;
   double gtf = 0;                          // d Lagrangian / d tf accumulated over stages
+  double pimax = 0;
   bool bad = false;
-  const double mT = P.mflow * P.T;
-  for (int k = 1; k <= N; ++k) {
-    double* sp = W.stage(k);
-    double z[6], lam[6];
-    const double a_old = WS_AT(sp, so + F_Z + 4), da = WS_AT(sp, F_DS + 4);
+  // ---- terminal scalars of the trial point ----
+  t.sg1 = c0.sg1 + alpha * ts.dsg1;
+  t.sg2 = c0.sg2 + alpha * ts.dsg2;
+  t.nu3 = c0.nu3 + alpha_lam * ts.dnu3;
+  t.zs1 = c0.zs1 + alpha_z * ts.dzs1;
+  t.zs2 = c0.zs2 + alpha_z * ts.dzs2;
+  t.zLt = c0.zLt + alpha_z * ts.dzLt;
+  t.zUt = c0.zUt + alpha_z * ts.dzUt;
+  {
+    const double dLt = tf, dUt = P.tf_ub - tf;
+    if (!(t.sg1 > 0 && t.sg2 > 0 && dLt > 0 && dUt > 0)) bad = true;
+    t.zs1 = clip_mult(t.zs1, t.sg1, mu);
+    t.zs2 = clip_mult(t.zs2, t.sg2, mu);
+    t.zLt = clip_mult(t.zLt, dLt, mu);
+    t.zUt = clip_mult(t.zUt, dUt, mu);
+    sumlog += log((t.sg1 * t.sg2) * (dLt * dUt));
+    const double q1 = t.sg1 * t.zs1, q2 = t.sg2 * t.zs2, q3 = dLt * t.zLt, q4 = dUt * t.zUt;
+    cmin = dmin(cmin, dmin(dmin(q1, q2), dmin(q3, q4)));
+    cmax = dmax(cmax, dmax(dmax(q1, q2), dmax(q3, q4)));
+    sz += t.zs1 + t.zs2 + t.zLt + t.zUt;
+    slam += t.zs1 + t.zs2 + fabs(t.nu3);
+    gtf += O.obj_scale - t.zLt + t.zUt;
+  }
+  // state of node k at the old point and its step (software-pipelined: node k-1 is loaded while
+  // node k is processed, because the defect of node k needs the trial state of node k-1)
+  double zo[6], ds[6];
+  {
+    const double* sp = W.stage(N);
 #pragma unroll
-    for (int i = 0; i < 6; ++i) z[i] = fma(alpha, WS_AT(sp, F_DS + i), WS_AT(sp, so + F_Z + i));
+    for (int i = 0; i < 6; ++i) { zo[i] = WS_AT(sp, so + F_Z + i); ds[i] = WS_AT(sp, F_DS + i); }
+  }
+  double lam_next[6] = {0, 0, 0, 0, 0, 0};   // trial multipliers of node k+1
+  double pi_next[6] = {0, 0, 0, 0, 0, 0};    // adjoint of node k+1
+  for (int k = N; k >= 1; --k) {
+    double* sp = W.stage(k);
+    if (k - PF_DIST >= 1) {            // rows this sweep will read PF_DIST stages from now
+      const double* pp = W.stage(k - PF_DIST);
+      pf_rows<F_U, N_ITER>(pp, so);                       // u, lam, bound multipliers
+      pf_row(pp, F_DU);
+      if (mode == EV_READ_PI) pf_rows<0, 6>(pp, F_PI);
+      if (k - PF_DIST - 1 >= 1) {
+        const double* pq = W.stage(k - PF_DIST - 1);
+        pf_rows<0, 6>(pq, so + F_Z);
+        pf_rows<0, 6>(pq, F_DS);
+      }
+    }
+    double z[6], zpo[6], dsp[6], zp[6], lam[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) z[i] = fma(alpha, ds[i], zo[i]);
+    if (k > 1) {
+      const double* sm = W.stage(k - 1);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        zpo[i] = WS_AT(sm, so + F_Z + i); dsp[i] = WS_AT(sm, F_DS + i);
+        zp[i] = fma(alpha, dsp[i], zpo[i]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) { zpo[i] = 0.0; dsp[i] = 0.0; zp[i] = 0.0; }
+    }
     const double u_old = WS_AT(sp, so + F_U);
     const double du = WS_AT(sp, F_DU);
     const double u = fma(alpha, du, u_old);
+    double lam_old[6];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      const double l0 = WS_AT(sp, so + F_LAM + i);
-      lam[i] = fma(alpha_lam, WS_AT(sp, F_PI + i) - l0, l0);
-    }
-    // bound multipliers: dz = mu/d - z - (z/d) dx = (mu - z dx)/d - z  (old d, old z)
+    for (int i = 0; i < 6; ++i) lam_old[i] = WS_AT(sp, so + F_LAM + i);
     double zla = WS_AT(sp, so + F_ZLA), zua = WS_AT(sp, so + F_ZUA);
     double zlu = WS_AT(sp, so + F_ZLU), zuu = WS_AT(sp, so + F_ZUU);
+    const double kap = M.h[k] * P.T;
+    const double taum = mT * M.tau[k];
+    // ---- new multipliers pi_k ----
+    double pi[6];
+    if (mode != EV_READ_PI) {
+      Accel1 f0;
+      accel_first(P, zo[0], zo[2], zo[4], taum * tf0, f0);
+      StageJac J0;
+      stagejac_build(P, kap, tf0, taum, f0, zo[1], zo[3], zo[5], u_old, J0);
+      stagejac_invert(J0);
+      StageQ q;
+      stage_hessian(P, f0, J0, kap, taum, lam_old, zo[4], u_old, zla, zua, zlu, zuu, mu, dw, ls, q);
+      double g[7];
+      g[0] = pi_next[0] - (q.q00 * ds[0] + q.q02 * ds[2] + q.q04 * ds[4] + q.q06 * dtf);
+      g[1] = pi_next[1] - (q.d * ds[1] + q.q16 * dtf);
+      g[2] = pi_next[2] - (q.q02 * ds[0] + q.q22 * ds[2] + q.q24 * ds[4] + q.q26 * dtf);
+      g[3] = pi_next[3] - (q.d * ds[3] + q.q36 * dtf);
+      g[4] = pi_next[4] - (q.q04 * ds[0] + q.q24 * ds[2] + q.q44 * ds[4] + q.q46 * dtf + q.q4);
+      g[5] = pi_next[5] - (q.d * ds[5] + q.q56 * dtf);
+      g[6] = 0.0;
+      if (k == N) {
+        TermQP tq;
+        terminal_qp(P, O, c0, zo, mu, dw, ls, tq);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          g[i] -= tq.H[i][0] * ds[0] + tq.H[i][1] * ds[1] + tq.H[i][2] * ds[2] + tq.H[i][3] * ds[3] + tq.g[i];
+      }
+      solveET(J0, g);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) { pi[i] = g[i]; WS_AT(sp, F_PI + i) = g[i]; pimax = dmax(pimax, fabs(g[i])); }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) pi[i] = WS_AT(sp, F_PI + i);
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) lam[i] = fma(alpha_lam, pi[i] - lam_old[i], lam_old[i]);
+    // ---- bound multipliers: dz = (mu - z dx)/d - z  (old d, old z), then the kappa_Sigma clip ----
     {
       double rLa, rUa, rLu, rUu;
-      recip4(a_old, P.a_ub - a_old, u_old + P.u_ub, P.u_ub - u_old, rLa, rUa, rLu, rUu);
+      recip4(zo[4], P.a_ub - zo[4], u_old + P.u_ub, P.u_ub - u_old, rLa, rUa, rLu, rUu);
+      const double da = ds[4];
       zla += alpha_z * ((mu - zla * da) * rLa - zla);
       zua += alpha_z * ((mu + zua * da) * rUa - zua);
       zlu += alpha_z * ((mu - zlu * du) * rLu - zlu);
@@ -342,9 +567,7 @@ LM_NOINLINE void eval_pass(const Params& P, const Mesh& M, const Options& O, con
       cmax = dmax(cmax, dmax(dmax(c1, c2), dmax(c3, c4)));
     }
     sz += (zla + zua) + (zlu + zuu);
-    // dynamics
-    const double kap = M.h[k] * P.T;
-    const double taum = mT * M.tau[k];
+    // ---- dynamics at the trial point ----
     Accel1 f;
     accel_first(P, z[0], z[2], z[4], taum * tf, f);
     StageJac J;
@@ -364,66 +587,47 @@ LM_NOINLINE void eval_pass(const Params& P, const Mesh& M, const Options& O, con
       prim = dmax(prim, ac);
       slam += fabs(lam[i]);
     }
-    // dual residual of the previous stage is complete once lam_k is known
-    if (k > 1) {
+    // ---- Lagrangian gradient wrt s_k: E_k^T lam_k - lam_{k+1} + bound / terminal terms ----
+    double res[6];
+    applyET6(J, lam, res);
+    res[4] += zua - zla;
+    if (k == N) {
+      Terminal T;
+      terminal_eval(P, z[0], z[1], z[2], z[3], T);
+      const double c1 = T.g1 - t.sg1, c2 = T.g2 - t.sg2, c3 = T.g3;
+      theta += fabs(c1) + fabs(c2) + fabs(c3);
+      prim = dmax(prim, dmax(fabs(c1), dmax(fabs(c2), fabs(c3))));
+      // multipliers of g1, g2 are -zs1, -zs2 (slack stationarity)
+      const double rinv = 1.0 / T.rT;
+      res[0] += -t.zs1 * T.Yb * rinv + t.nu3 * z[1];
+      res[2] += -t.zs1 * z[2] * rinv + t.nu3 * z[3];
+      res[1] += -t.zs2 * 2.0 * z[1] + t.nu3 * T.Yb;
+      res[3] += -t.zs2 * 2.0 * z[3] + t.nu3 * z[2];
+    } else {
 #pragma unroll
-      for (int i = 0; i < 6; ++i) dual = dmax(dual, fabs(pend[i] - lam[i]));
+      for (int i = 0; i < 6; ++i) res[i] -= lam_next[i];
     }
-    applyET6(J, lam, pend);
-    pend[4] += zua - zla;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) dual = dmax(dual, fabs(res[i]));
     dual = dmax(dual, fabs(-J.beta * lam[5] - zlu + zuu));     // d L / d u_k
     gtf -= J.e0 * lam[0] + J.e1 * lam[1] + J.e2 * lam[2] + J.e3 * lam[3] + J.e4 * lam[4] + J.e5 * lam[5];
-    // write trial iterate
+    // ---- write the trial iterate, shift the pipeline ----
 #pragma unroll
-    for (int i = 0; i < 6; ++i) { WS_AT(sp, dd + F_Z + i) = z[i]; WS_AT(sp, dd + F_LAM + i) = lam[i]; zp[i] = z[i]; }
+    for (int i = 0; i < 6; ++i) {
+      WS_AT(sp, dd + F_Z + i) = z[i]; WS_AT(sp, dd + F_LAM + i) = lam[i];
+      lam_next[i] = lam[i]; pi_next[i] = pi[i]; zo[i] = zpo[i]; ds[i] = dsp[i];
+    }
     WS_AT(sp, dd + F_U) = u;
     WS_AT(sp, dd + F_ZLA) = zla; WS_AT(sp, dd + F_ZUA) = zua;
     WS_AT(sp, dd + F_ZLU) = zlu; WS_AT(sp, dd + F_ZUU) = zuu;
   }
-  // terminal node
-  t.sg1 = c0.sg1 + alpha * ts.dsg1;
-  t.sg2 = c0.sg2 + alpha * ts.dsg2;
-  t.nu3 = c0.nu3 + alpha_lam * ts.dnu3;
-  t.zs1 = c0.zs1 + alpha_z * ts.dzs1;
-  t.zs2 = c0.zs2 + alpha_z * ts.dzs2;
-  t.zLt = c0.zLt + alpha_z * ts.dzLt;
-  t.zUt = c0.zUt + alpha_z * ts.dzUt;
-  const double dLt = tf, dUt = P.tf_ub - tf;
-  if (!(t.sg1 > 0 && t.sg2 > 0 && dLt > 0 && dUt > 0)) bad = true;
-  t.zs1 = clip_mult(t.zs1, t.sg1, mu);
-  t.zs2 = clip_mult(t.zs2, t.sg2, mu);
-  t.zLt = clip_mult(t.zLt, dLt, mu);
-  t.zUt = clip_mult(t.zUt, dUt, mu);
-  Terminal T;
-  terminal_eval(P, zp[0], zp[1], zp[2], zp[3], T);
-  const double c1 = T.g1 - t.sg1, c2 = T.g2 - t.sg2, c3 = T.g3;
-  theta += fabs(c1) + fabs(c2) + fabs(c3);
-  prim = dmax(prim, dmax(fabs(c1), dmax(fabs(c2), fabs(c3))));
-  sumlog += log((t.sg1 * t.sg2) * (dLt * dUt));
-  {
-    const double q1 = t.sg1 * t.zs1, q2 = t.sg2 * t.zs2, q3 = dLt * t.zLt, q4 = dUt * t.zUt;
-    cmin = dmin(cmin, dmin(dmin(q1, q2), dmin(q3, q4)));
-    cmax = dmax(cmax, dmax(dmax(q1, q2), dmax(q3, q4)));
-  }
-  sz += t.zs1 + t.zs2 + t.zLt + t.zUt;
-  slam += t.zs1 + t.zs2 + fabs(t.nu3);
-  // Lagrangian gradient at the last node: multipliers of g1,g2 are -zs1,-zs2 (slack stationarity)
-  {
-    const double rinv = 1.0 / T.rT;
-    pend[0] += -t.zs1 * T.Yb * rinv + t.nu3 * zp[1];
-    pend[2] += -t.zs1 * zp[2] * rinv + t.nu3 * zp[3];
-    pend[1] += -t.zs2 * 2.0 * zp[1] + t.nu3 * T.Yb;
-    pend[3] += -t.zs2 * 2.0 * zp[3] + t.nu3 * zp[2];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) dual = dmax(dual, fabs(pend[i]));
-  }
-  gtf += O.obj_scale - t.zLt + t.zUt;
   dual = dmax(dual, fabs(gtf));
   t.theta = theta;
   t.fobj = O.obj_scale * tf;
   t.sumlog = bad ? -1e300 : sumlog;
   t.prim_inf = prim; t.dual_inf = dual; t.cmin = cmin; t.cmax = cmax; t.sum_lam = slam; t.sum_z = sz;
   if (bad || !(theta == theta)) t.theta = 1e300;
+  if (pimax_out) *pimax_out = pimax;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -434,12 +638,13 @@ LM_NOINLINE void eval_pass(const Params& P, const Mesh& M, const Options& O, con
 //   T1 = diag(A11, I)   A11 = inverse of the (y,vy,x,vx) block of E          (4x4, applied as an operator)
 //   T2 = [I C; 0 I]     C = [ga | 0 | e]  couples (angle, tf) into the velocity rows
 //   T3 = diag(I, A22)   A22 = [[1, al, e4+al*e5], [0, 1, e5], [0, 0, 1]]      (angle, angledot, tf chain)
-// then the control is condensed (it enters through the angledot row only).
+// then the control is condensed (it enters through the angledot row only).  Only the feedback
+// gains K_k, k_k leave the SM; the cost-to-go P, p lives in registers.
 // ---------------------------------------------------------------------------------------
 LM_NOINLINE bool riccati_backward(const Params& P, const Mesh& M, const Options& O, const Ws& W, int src,
-                                  const Scal& c0, double mu, double dw, bool ls, double* dtf_out, double* p0_out) {
+                                  const Scal& c0, double mu, double dw, bool ls, double* dtf_out) {
   // ls == true: least-squares multiplier estimate (IPOPT section 3.6): Hessian := I, defects := 0,
-  // gradient := grad f - zL + zU; the forward sweep then returns the multipliers in F_PI.
+  // gradient := grad f - zL + zU.
   const int N = M.N;
   const double tf = c0.tf;
   const int so = src * N_ITER;
@@ -448,64 +653,34 @@ LM_NOINLINE bool riccati_backward(const Params& P, const Mesh& M, const Options&
   // Cq = (q,q) 3x3 symmetric (upper triangle used); p = (y,vy,x,vx), q = (angle, angledot, tf)
   double A[4][4], Bm[4][3], C00, C01, C02, C11, C12, C22;
   double pv[7];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) A[i][j] = 0.0;
-#pragma unroll
-    for (int j = 0; j < 3; ++j) Bm[i][j] = 0.0;
-  }
-  C00 = C01 = C02 = C11 = C12 = C22 = 0.0;
-#pragma unroll
-  for (int i = 0; i < 7; ++i) pv[i] = 0.0;
   double zn[6];    // state at node k
   {
     const double* sp = W.stage(N);
 #pragma unroll
     for (int i = 0; i < 6; ++i) zn[i] = WS_AT(sp, so + F_Z + i);
   }
-  // ---- terminal contributions (added to stage N's Q and q) ----
   {
-    Terminal T;
-    terminal_eval(P, zn[0], zn[1], zn[2], zn[3], T);
-    const double rinv = 1.0 / T.rT;
-    const double g1y = T.Yb * rinv, g1x = zn[2] * rinv;
-    const double w1 = ls ? 1.0 : c0.zs1 / c0.sg1, w2 = ls ? 1.0 : c0.zs2 / c0.sg2, w3 = 1.0 / O.delta_c;
-    const double c1 = T.g1 - c0.sg1, c2 = T.g2 - c0.sg2;
-    // gradient terms: grad g_i * (w_i c_i - mu/sg_i), grad g3 * (nu3 + g3/delta_c)
-    const double q1 = ls ? -c0.zs1 : w1 * c1 - mu / c0.sg1;
-    const double q2 = ls ? -c0.zs2 : w2 * c2 - mu / c0.sg2;
-    const double q3 = ls ? 0.0 : c0.nu3 + T.g3 * w3;
-    const double hz1 = ls ? 0.0 : c0.zs1, hz2 = ls ? 0.0 : c0.zs2, hn3 = ls ? 0.0 : c0.nu3;
-    const double G2y = 2.0 * zn[1], G2x = 2.0 * zn[3];
-    // g3 gradient wrt (y, vy, x, vx) = (vy, Yb, vx, x)
-    const double G3[4] = {zn[1], T.Yb, zn[3], zn[2]};
-    pv[0] = g1y * q1 + G3[0] * q3;
-    pv[1] = G2y * q2 + G3[1] * q3;
-    pv[2] = g1x * q1 + G3[2] * q3;
-    pv[3] = G2x * q2 + G3[3] * q3;
-    // Hessian: w_i grad grad^T + multipliers * second derivatives (mult of g1,g2 = -zs)
-    const double r3 = rinv * rinv * rinv;
-    const double h1yy = zn[2] * zn[2] * r3, h1xx = T.Yb * T.Yb * r3, h1yx = -T.Yb * zn[2] * r3;
-    A[0][0] = w1 * g1y * g1y - hz1 * h1yy + w3 * G3[0] * G3[0];
-    A[2][0] = w1 * g1x * g1y - hz1 * h1yx + w3 * G3[2] * G3[0];
-    A[2][2] = w1 * g1x * g1x - hz1 * h1xx + w3 * G3[2] * G3[2];
-    A[1][1] = w2 * G2y * G2y - 2.0 * hz2 + w3 * G3[1] * G3[1];
-    A[3][1] = w2 * G2x * G2y + w3 * G3[3] * G3[1];
-    A[3][3] = w2 * G2x * G2x - 2.0 * hz2 + w3 * G3[3] * G3[3];
-    A[1][0] = w3 * G3[1] * G3[0] + hn3;
-    A[3][0] = w3 * G3[3] * G3[0];
-    A[2][1] = w3 * G3[2] * G3[1];
-    A[3][2] = w3 * G3[3] * G3[2] + hn3;
-    A[0][1] = A[1][0]; A[0][2] = A[2][0]; A[0][3] = A[3][0]; A[1][2] = A[2][1]; A[1][3] = A[3][1]; A[2][3] = A[3][2];
-    // tf: objective, bound barrier, regularisation
-    const double dLt = tf, dUt = P.tf_ub - tf;
-    pv[6] = ls ? O.obj_scale - c0.zLt + c0.zUt : O.obj_scale - mu / dLt + mu / dUt;
-    C22 = ls ? 1.0 : c0.zLt / dLt + c0.zUt / dUt + dw;
+    TermQP tq;
+    terminal_qp(P, O, c0, zn, mu, dw, ls, tq);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) A[i][j] = tq.H[i][j];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) Bm[i][j] = 0.0;
+      pv[i] = tq.g[i];
+    }
+    C00 = C01 = C02 = C11 = C12 = 0.0;
+    C22 = tq.H66;
+    pv[4] = 0.0; pv[5] = 0.0; pv[6] = tq.g6;
   }
   bool ok = true;
   for (int k = N; k >= 1; --k) {
     double* sp = W.stage(k);
+    if (k - PF_DIST >= 1) {
+      pf_rows<F_U, N_ITER>(W.stage(k - PF_DIST), so);
+      if (k - PF_DIST - 1 >= 1) pf_rows<0, 6>(W.stage(k - PF_DIST - 1), so + F_Z);
+    }
     double lam[6], zm[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i) lam[i] = WS_AT(sp, so + F_LAM + i);
@@ -529,43 +704,17 @@ LM_NOINLINE bool riccati_backward(const Params& P, const Mesh& M, const Options&
     stagejac_invert(J);
     const double al = J.al;
     // ---- W = Q_k + P_k (in place), g = q_k + p_k ----
-    double R, r, sig;
-    if (!ls) {
-      double rLa, rUa, rLu, rUu;
-      recip4(zn[4], P.a_ub - zn[4], u + P.u_ub, P.u_ub - u, rLa, rUa, rLu, rUu);
-      Accel2 h2;
-      accel_second(P, f, lam[1], lam[3], h2);
-      A[0][0] += -al * h2.yy + dw;
-      { const double t = -al * h2.yx; A[2][0] += t; A[0][2] += t; }
-      A[2][2] += -al * h2.xx + dw;
-      A[1][1] += dw; A[3][3] += dw;
-      Bm[0][0] += -al * h2.ya;
-      Bm[2][0] += -al * h2.xa;
-      C00 += -al * h2.aa + zla * rLa + zua * rUa + dw;
-      C11 += dw;
-      const double Phy = lam[1] * f.ay_y + lam[3] * f.ax_y;
-      const double Phx = lam[1] * f.ay_x + lam[3] * f.ax_x;
-      const double Pha = lam[1] * f.ay_a + lam[3] * f.ax_a;
-      const double Phm = lam[1] * f.ay_m + lam[3] * f.ax_m;
-      const double alt = al * taum;
-      Bm[0][2] += -kap * Phy - alt * h2.ym;
-      Bm[2][2] += -kap * Phx - alt * h2.xm;
-      Bm[1][2] += -kap * lam[0];
-      Bm[3][2] += -kap * lam[2];
-      C02 += -kap * Pha - alt * h2.am;
-      C12 += -kap * lam[4];
-      C22 += -2.0 * kap * Phm * taum - alt * h2.mm * taum;
-      pv[4] += mu * (rUa - rLa);
-      R = zlu * rLu + zuu * rUu + dw;
-      r = mu * (rUu - rLu);
-      sig = -kap * lam[5] * P.asc;   // u-tf cross term
-    } else {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) A[i][i] += 1.0;
-      C00 += 1.0; C11 += 1.0;
-      pv[4] += -zla + zua;
-      R = 1.0; r = -zlu + zuu; sig = 0.0;
-    }
+    StageQ q;
+    stage_hessian(P, f, J, kap, taum, lam, zn[4], u, zla, zua, zlu, zuu, mu, dw, ls, q);
+    A[0][0] += q.q00;
+    A[2][0] += q.q02; A[0][2] += q.q02;
+    A[2][2] += q.q22;
+    A[1][1] += q.d; A[3][3] += q.d;
+    Bm[0][0] += q.q04; Bm[2][0] += q.q24;
+    C00 += q.q44; C11 += q.d;
+    Bm[0][2] += q.q06; Bm[1][2] += q.q16; Bm[2][2] += q.q26; Bm[3][2] += q.q36;
+    C02 += q.q46; C12 += q.q56; C22 += q.q66;
+    pv[4] += q.q4;
     // ---- defect ----
     double c[6];
     if (!ls) {
@@ -623,21 +772,20 @@ LM_NOINLINE bool riccati_backward(const Params& P, const Mesh& M, const Options&
       // X = Cq A22 (rows), then A22^T X
       const double x00 = C00, x01 = al * C00 + C01, x02 = s * C00 + e5 * C01 + C02;
       const double x11 = al * C01 + C11, x12 = s * C01 + e5 * C11 + C12;   // row 1 of X: [C01, x11, x12]
-      const double x21 = al * C02 + C12, x22 = s * C02 + e5 * C12 + C22;   // row 2 of X: [C02, x21, x22]
+      const double x22 = s * C02 + e5 * C12 + C22;                          // row 2 of X: [C02,  . , x22]
       C00 = x00; C01 = x01; C02 = x02;
       C11 = al * x01 + x11;
       C12 = al * x02 + x12;
       C22 = s * x02 + e5 * x12 + x22;
-      (void)x21;
     }
     solveET(J, pv);                      // g~ = E^{-T} (q + p)
     // ---- condense the control (enters through the angledot row: q-index 1) ----
     const double beta = J.beta;
-    const double Ruu = R + beta * beta * C11;
+    const double Ruu = q.R + beta * beta * C11;
     double Rux[7];
 #pragma unroll
     for (int i = 0; i < 4; ++i) Rux[i] = beta * Bm[i][1];
-    Rux[4] = beta * C01; Rux[5] = beta * C11; Rux[6] = beta * C12 + sig;
+    Rux[4] = beta * C01; Rux[5] = beta * C11; Rux[6] = beta * C12 + q.sig;
     double rx[7];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -645,39 +793,28 @@ LM_NOINLINE bool riccati_backward(const Params& P, const Mesh& M, const Options&
     rx[4] = pv[4] - (Bm[0][0] * c[0] + Bm[1][0] * c[1] + Bm[2][0] * c[2] + Bm[3][0] * c[3] + C00 * c[4] + C01 * c[5]);
     rx[5] = pv[5] - (Bm[0][1] * c[0] + Bm[1][1] * c[1] + Bm[2][1] * c[2] + Bm[3][1] * c[3] + C01 * c[4] + C11 * c[5]);
     rx[6] = pv[6] - (Bm[0][2] * c[0] + Bm[1][2] * c[1] + Bm[2][2] * c[2] + Bm[3][2] * c[3] + C02 * c[4] + C12 * c[5]);
-    const double ru = r + beta * rx[5];
+    const double ru = q.r + beta * rx[5];
     if (!(Ruu > 0.0) || !(Ruu < 1e300)) ok = false;
     const double Rinv = 1.0 / Ruu;
-#pragma unroll
-    for (int i = 0; i < 7; ++i) WS_AT(sp, F_K + i) = -Rux[i] * Rinv;
-    WS_AT(sp, F_KFF) = -ru * Rinv;
     double RuxS[7];
 #pragma unroll
-    for (int i = 0; i < 7; ++i) RuxS[i] = Rux[i] * Rinv;
-    // P_{k-1} = Wt - Rux Rux^T / Ruu   (symmetrised), stored packed (rows 0..6, lower triangle)
+    for (int i = 0; i < 7; ++i) { RuxS[i] = Rux[i] * Rinv; WS_AT(sp, F_K + i) = -RuxS[i]; }
+    WS_AT(sp, F_KFF) = -ru * Rinv;
+    // P_{k-1} = Wt - Rux Rux^T / Ruu   (symmetrised)
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
 #pragma unroll
       for (int j = 0; j <= i; ++j) {
         const double v = 0.5 * (A[i][j] + A[j][i]) - Rux[i] * RuxS[j];
         A[i][j] = v; A[j][i] = v;
-        WS_AT(sp, F_P + pidx(i, j)) = v;
       }
 #pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const double v = Bm[i][j] - Rux[i] * RuxS[4 + j];
-        Bm[i][j] = v;
-        WS_AT(sp, F_P + pidx(4 + j, i)) = v;
-      }
+      for (int j = 0; j < 3; ++j) Bm[i][j] -= Rux[i] * RuxS[4 + j];
     }
     C00 -= Rux[4] * RuxS[4]; C01 -= Rux[4] * RuxS[5]; C02 -= Rux[4] * RuxS[6];
     C11 -= Rux[5] * RuxS[5]; C12 -= Rux[5] * RuxS[6]; C22 -= Rux[6] * RuxS[6];
-    WS_AT(sp, F_P + pidx(4, 4)) = C00; WS_AT(sp, F_P + pidx(5, 4)) = C01; WS_AT(sp, F_P + pidx(6, 4)) = C02;
-    WS_AT(sp, F_P + pidx(5, 5)) = C11; WS_AT(sp, F_P + pidx(6, 5)) = C12;
 #pragma unroll
     for (int i = 0; i < 7; ++i) pv[i] = rx[i] - RuxS[i] * ru;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) WS_AT(sp, F_PV + i) = pv[i];
 #pragma unroll
     for (int i = 0; i < 6; ++i) zn[i] = zm[i];
     if (!ok) return false;
@@ -685,14 +822,13 @@ LM_NOINLINE bool riccati_backward(const Params& P, const Mesh& M, const Options&
   // free initial tf: minimise 0.5 P66 dtf^2 + p6 dtf
   if (!(C22 > 0.0)) return false;
   *dtf_out = -pv[6] / C22;
-  *p0_out = C22;
   return true;
 }
 
 // ---------------------------------------------------------------------------------------
-// forward sweep: recover the Newton step, fraction-to-boundary limits and d(phi)/d(alpha)
+// forward sweep: recover the primal Newton step, fraction-to-boundary limits and d(phi)/d(alpha)
 // ---------------------------------------------------------------------------------------
-struct StepInfo { double a_max, a_z, dphi, dxmax, pimax; };
+struct StepInfo { double a_max, a_z, dphi, dxmax; };
 
 // running maximum of num/den (den > 0) without dividing: keeps the pair
 struct RatioMax {
@@ -710,12 +846,18 @@ LM_NOINLINE void riccati_forward(const Params& P, const Mesh& M, const Options& 
   const double mT = P.mflow * P.T;
   double ds[7] = {0, 0, 0, 0, 0, 0, dtf};
   double zm[6] = {0, 0, 0, 0, 0, 0};
-  double dphi = 0.0, dxmax = fabs(dtf), pimax = 0.0;
+  double dphi = 0.0, dxmax = fabs(dtf);
   RatioMax rp, rz;      // max of (-dx/slack) over primal bounds, (-dz/z) over bound multipliers
   rp.init(); rz.init();
   const double cw = ls ? 0.0 : 1.0;   // defects are dropped in the least-squares mode
   for (int k = 1; k <= N; ++k) {
     double* sp = W.stage(k);
+    if (k + PF_DIST <= N) {
+      const double* pp = W.stage(k + PF_DIST);
+      pf_rows<F_Z, F_U + 1>(pp, so);
+      pf_rows<F_ZLA, N_ITER>(pp, so);
+      pf_rows<0, 8>(pp, F_K);
+    }
     double zn[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i) zn[i] = WS_AT(sp, so + F_Z + i);
@@ -728,24 +870,6 @@ LM_NOINLINE void riccati_forward(const Params& P, const Mesh& M, const Options& 
     stagejac_build(P, kap, tf, taum, f, zn[1], zn[3], zn[5], u, J);
     stagejac_invert(J);
     const double al = J.al;
-    // new multipliers  pi_k = -(P_{k-1} ds_{k-1} + p_{k-1}),  rows 0..5
-    {
-      double acc[6];
-#pragma unroll
-      for (int i = 0; i < 6; ++i) acc[i] = WS_AT(sp, F_PV + i);
-#pragma unroll
-      for (int i = 0; i < 7; ++i) {
-#pragma unroll
-        for (int j = 0; j <= i; ++j) {
-          if (i == 6 && j == 6) continue;
-          const double pij = WS_AT(sp, F_P + pidx(i, j));
-          if (i < 6) acc[i] = fma(pij, ds[j], acc[i]);
-          if (j < i && j < 6) acc[j] = fma(pij, ds[i], acc[j]);
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < 6; ++i) { WS_AT(sp, F_PI + i) = -acc[i]; pimax = dmax(pimax, fabs(acc[i])); }
-    }
     double du = WS_AT(sp, F_KFF);
 #pragma unroll
     for (int i = 0; i < 7; ++i) du = fma(WS_AT(sp, F_K + i), ds[i], du);
@@ -786,11 +910,15 @@ LM_NOINLINE void riccati_forward(const Params& P, const Mesh& M, const Options& 
     const double dg2 = 2.0 * zm[1] * ds[1] + 2.0 * zm[3] * ds[3];
     const double dg3 = zm[1] * ds[0] + T.Yb * ds[1] + zm[3] * ds[2] + zm[2] * ds[3];
     ts.dtf = dtf;
-    ts.dsg1 = dg1 + (T.g1 - c0.sg1);
-    ts.dsg2 = dg2 + (T.g2 - c0.sg2);
+    ts.dsg1 = dg1 + cw * (T.g1 - c0.sg1);
+    ts.dsg2 = dg2 + cw * (T.g2 - c0.sg2);
     ts.dnu3 = (dg3 + cw * T.g3) / O.delta_c;
-    ts.dzs1 = mu / c0.sg1 - c0.zs1 - c0.zs1 / c0.sg1 * ts.dsg1;
-    ts.dzs2 = mu / c0.sg2 - c0.zs2 - c0.zs2 / c0.sg2 * ts.dsg2;
+    if (!ls) {
+      ts.dzs1 = mu / c0.sg1 - c0.zs1 - c0.zs1 / c0.sg1 * ts.dsg1;
+      ts.dzs2 = mu / c0.sg2 - c0.zs2 - c0.zs2 / c0.sg2 * ts.dsg2;
+    } else {
+      ts.dzs1 = 0.0; ts.dzs2 = 0.0;
+    }
     const double dLt = tf, dUt = P.tf_ub - tf;
     ts.dzLt = mu / dLt - c0.zLt - c0.zLt / dLt * dtf;
     ts.dzUt = mu / dUt - c0.zUt + c0.zUt / dUt * dtf;
@@ -800,9 +928,9 @@ LM_NOINLINE void riccati_forward(const Params& P, const Mesh& M, const Options& 
     dxmax = dmax(dxmax, dmax(fabs(ts.dsg1), fabs(ts.dsg2)));
   }
   // alpha_max = min(1, tau / max ratio)
-  si.a_max = (rp.n * 1.0 > tau * rp.d) ? tau * rp.d / rp.n : 1.0;
-  si.a_z = (rz.n * 1.0 > tau * rz.d) ? tau * rz.d / rz.n : 1.0;
-  si.dphi = dphi; si.dxmax = dxmax; si.pimax = pimax;
+  si.a_max = (rp.n > tau * rp.d) ? tau * rp.d / rp.n : 1.0;
+  si.a_z = (rz.n > tau * rz.d) ? tau * rz.d / rz.n : 1.0;
+  si.dphi = dphi; si.dxmax = dxmax;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -858,17 +986,18 @@ LM_HD void ipm_solve(const Params& P, const Mesh& M, const Options& O, const Ws&
   // evaluate the starting point (alpha = 0 copies buffer 0 -> 1 with the safeguards applied)
   {
     // least-squares multipliers for the defect rows (IPOPT 3.6); discarded if too large
-    double dtf0 = 0.0, p00 = 0.0;
+    double dtf0 = 0.0, pimax = 0.0;
     StepInfo s0;
-    double al = 0.0;
-    if (riccati_backward(P, M, O, W, src, cur, ctl.mu, 0.0, true, &dtf0, &p00)) {
+    bool have = false;
+    if (riccati_backward(P, M, O, W, src, cur, ctl.mu, 0.0, true, &dtf0)) {
       riccati_forward(P, M, O, W, src, cur, ctl.mu, ctl.tau, dtf0, true, ts, s0);
-      if (s0.pimax <= 1e3 * dmax(1.0, O.obj_scale) && fabs(ts.dnu3) <= 1e3 * dmax(1.0, O.obj_scale)) al = 1.0;
+      eval_pass(P, M, O, W, src, 1 - src, cur, ts, ctl.mu, 0.0, 0.0, 0.0, 1.0, EV_LSQ, trial, &pimax);
+      have = pimax <= 1e3 * dmax(1.0, O.obj_scale) && fabs(ts.dnu3) <= 1e3 * dmax(1.0, O.obj_scale);
 #if defined(LMATO_TRACE) && !defined(__CUDA_ARCH__)
-      printf("LS multipliers: pimax %.3e dnu3 %.3e dtf %.3e -> %s\n", s0.pimax, ts.dnu3, dtf0, al > 0 ? "used" : "discarded");
+      printf("LS multipliers: pimax %.3e dnu3 %.3e dtf %.3e -> %s\n", pimax, ts.dnu3, dtf0, have ? "used" : "discarded");
 #endif
     }
-    eval_pass(P, M, O, W, src, 1 - src, cur, ts, ctl.mu, 0.0, 0.0, al, trial);
+    if (!have) eval_pass(P, M, O, W, src, 1 - src, cur, ts, ctl.mu, 0.0, 0.0, 0.0, 0.0, EV_READ_PI, trial, nullptr);
   }
   cur = trial; src = 1 - src;
   ctl.theta_max = 1e4 * dmax(1.0, cur.theta);
@@ -903,10 +1032,10 @@ LM_HD void ipm_solve(const Params& P, const Mesh& M, const Options& O, const Ws&
     }
     if (ctl.iter >= O.max_iter) { ctl.status = polishing ? ST_CONVERGED : ST_MAX_ITER; break; }
     // factorisation with inertia correction (IPOPT Algorithm IC)
-    double dw = 0.0, dtf = 0.0, p0 = 0.0;
+    double dw = 0.0, dtf = 0.0;
     bool fact_ok = false;
     for (int attempt = 0; attempt < 40; ++attempt) {
-      if (riccati_backward(P, M, O, W, src, cur, ctl.mu, dw, false, &dtf, &p0)) { fact_ok = true; break; }
+      if (riccati_backward(P, M, O, W, src, cur, ctl.mu, dw, false, &dtf)) { fact_ok = true; break; }
       if (dw == 0.0) dw = (ctl.dw_last == 0.0) ? 1e-4 : dmax(1e-20, ctl.dw_last / 3.0);
       else dw *= (ctl.dw_last == 0.0) ? 100.0 : 8.0;
       if (dw > 1e40) break;
@@ -929,7 +1058,8 @@ LM_HD void ipm_solve(const Params& P, const Mesh& M, const Options& O, const Ws&
     const double sw_lhs = sw_possible ? pow(-dphi, s_ph) : 0.0;
     const double sw_rhs = sw_possible ? delta * pow(theta, s_th) : 0.0;
     for (int lsi = 0; lsi < O.max_ls; ++lsi) {
-      eval_pass(P, M, O, W, src, 1 - src, cur, ts, ctl.mu, alpha, si.a_z, alpha, trial);
+      eval_pass(P, M, O, W, src, 1 - src, cur, ts, ctl.mu, dw, alpha, si.a_z, alpha,
+                lsi == 0 ? EV_NEWTON : EV_READ_PI, trial, nullptr);
       const double th_t = trial.theta;
       const double ph_t = trial.fobj - ctl.mu * trial.sumlog;
       bool ok = (th_t <= ctl.theta_max) && (ph_t == ph_t) && (ph_t < 1e299) && filter_ok(ctl, th_t, ph_t);
