@@ -138,6 +138,10 @@ lmato_status_t lmato_last_kernel_ms(lmato_handle* h, double* ms);
  * micro-benchmark; used as the roofline denominator, MEASURED_PEAKS.json has no FP64). */
 lmato_status_t lmato_measure_fp64_peak(lmato_handle* h, double* gflops);
 
+/* Device self-test of the solver's branch-free FP64 math (rcp, rsqrt, log, sin, cos) against the
+ * CUDA math library: max_err5 = {rel rcp, rel rsqrt, rel log, abs sin, abs cos}. */
+lmato_status_t lmato_selftest_math(lmato_handle* h, double* max_err5);
+
 const char* lmato_last_error(void);
 const char* lmato_version(void);
 

@@ -83,9 +83,10 @@ def lib() -> C.CDLL:
     L.lmato_kernel_launches.argtypes = [vp, C.POINTER(i64)]
     L.lmato_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_double)]
     L.lmato_measure_fp64_peak.argtypes = [vp, C.POINTER(C.c_double)]
+    L.lmato_selftest_math.argtypes = [vp, C.POINTER(C.c_double)]
     for name in ("lmato_create", "lmato_destroy", "lmato_set_options", "lmato_solve_batch",
                  "lmato_solve_batch_host", "lmato_workspace_bytes", "lmato_kernel_launches",
-                 "lmato_last_kernel_ms", "lmato_measure_fp64_peak"):
+                 "lmato_last_kernel_ms", "lmato_measure_fp64_peak", "lmato_selftest_math"):
         getattr(L, name).restype = C.c_int
     _lib = L
     return L
@@ -94,7 +95,7 @@ def lib() -> C.CDLL:
 EXPORTED_SYMBOLS = ["lmato_default_options", "lmato_create", "lmato_destroy", "lmato_set_options",
                     "lmato_solve_batch", "lmato_solve_batch_host", "lmato_workspace_bytes",
                     "lmato_kernel_launches", "lmato_last_kernel_ms", "lmato_measure_fp64_peak",
-                    "lmato_last_error", "lmato_version"]
+                    "lmato_selftest_math", "lmato_last_error", "lmato_version"]
 
 
 def check(rc: int, what: str) -> None:

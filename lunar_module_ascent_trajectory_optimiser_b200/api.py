@@ -271,6 +271,11 @@ class AscentSolver:
         _cabi.check(_cabi.lib().lmato_measure_fp64_peak(self._h, C.byref(g)), "lmato_measure_fp64_peak")
         return g.value
 
+    def selftest_math(self):
+        e = (C.c_double * 5)()
+        _cabi.check(_cabi.lib().lmato_selftest_math(self._h, e), "lmato_selftest_math")
+        return dict(zip(("rcp", "rsqrt", "log", "sin", "cos"), list(e)))
+
     # -- packaged result ----------------------------------------------------------------
     def solve(self, params: AscentParams, B: Optional[int] = None, trajectories: bool = True,
               on_device: bool = False) -> AscentBatchSolution:

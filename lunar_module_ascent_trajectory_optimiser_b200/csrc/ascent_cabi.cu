@@ -39,11 +39,9 @@ void set_err(const char* fmt, const char* a = "", const char* b = "") {
     }                                                                         \
   } while (0)
 
-#ifndef LMATO_BLOCKS_PER_SM
-#define LMATO_BLOCKS_PER_SM 4
-#endif
-constexpr int kBlock = 64;          // threads per CTA (2 warps)
-constexpr int kBlocksPerSM = LMATO_BLOCKS_PER_SM;   // 4 -> 256 threads/SM at <=255 registers
+// One CTA of 256 threads (8 warps) per SM: 255 registers x 256 threads fills the register file.
+constexpr int kBlock = 256;
+constexpr int kBlocksPerSM = 1;
 
 struct KArgs {
   const double* params;  // [NPARAM][B]
@@ -91,23 +89,65 @@ __device__ __forceinline__ Params derive_params(const double* __restrict__ p, lo
   return P;
 }
 
+// Params padded to an odd number of 8-byte words per thread so that the per-thread structs in
+// shared memory are bank-conflict free (stride 19 doubles = 38 words; 38 mod 32 = 6).
+struct alignas(8) ParamsSlot { Params p; double pad[(sizeof(Params) / 8) % 2 == 0 ? 1 : 2]; };
+
 __global__ void __launch_bounds__(kBlock, kBlocksPerSM) ascent_ipm_kernel(KArgs a) {
+  // The sweeps are separate (noinline) functions taking `const Params&`: keeping the per-problem
+  // constants in shared memory instead of the thread's local-memory stack removes a dozen
+  // L1-missing local loads from the critical path of every stage.
+  __shared__ ParamsSlot sP[kBlock];
+  __shared__ Options sO;
+  __shared__ Mesh sM;
+  if (threadIdx.x == 0) { sO = a.O; sM = Mesh{a.N, a.h, a.tau}; }
+  __syncthreads();
+  const Options& O = sO;
+  const Mesh& M = sM;
+  Params& P = sP[threadIdx.x].p;
   const long slot = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
-  const Mesh M{a.N, a.h, a.tau};
   const long nwarps = a.slots / LANES;
   const Ws W{a.ws + ((slot / LANES) * N_FIELDS) * LANES + lane, nwarps * N_FIELDS * LANES};
   const int nt = a.N + 1;
+  IpmState S;
+  bool active = false;        // this lane holds an unfinished problem
+  bool exhausted = false;     // the queue is empty (warp-uniform)
+  bool first = true;
+  long b = -1;
+  const int warps_per_block = kBlock / 32;
   while (true) {
-    int chunk = 0;
-    if (lane == 0) chunk = atomicAdd(a.counter, 1);
-    chunk = __shfl_sync(0xffffffffu, chunk, 0);
-    const long b = (long)chunk * 32 + lane;
-    if ((long)chunk * 32 >= a.B) break;
-    if (b < a.B) {
-      const Params P = derive_params(a.params, a.B, b);
+    // ---- a warp whose 32 problems are all finished claims the next 32 (warp-uniform branch) ----
+    if (!exhausted && !__any_sync(0xffffffffu, active)) {
+      // first chunk: static round-robin over CTAs (spreads a small batch over all SMs);
+      // afterwards: the device-wide queue
+      int chunk = 0;
+      if (first) {
+        chunk = (threadIdx.x / 32) * gridDim.x + blockIdx.x;
+        first = false;
+      } else {
+        if (lane == 0) chunk = atomicAdd(a.counter, 1) + gridDim.x * warps_per_block;
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+      }
+      if ((long)chunk * 32 >= a.B) {
+        exhausted = true;
+      } else {
+        b = (long)chunk * 32 + lane;
+        if (b < a.B) {
+          P = derive_params(a.params, a.B, b);
+          init_guess(P, M, O, W, S.cur);
+          ipm_begin(O, S);
+          active = true;
+        }
+      }
+    }
+    // ---- all eight warps of the SM start each iteration together: they then run the same sweep
+    //      (same code) at the same time, which keeps the 32 KB instruction cache effective ----
+    if (!__syncthreads_or(active ? 1 : 0)) break;
+    if (active && ipm_iterate(P, M, O, W, S)) {
+      active = false;
       SolveOut out;
-      ipm_solve(P, M, a.O, W, false, out);
+      ipm_result(S, out);
       a.tf[b] = out.tf;
       a.fmass[b] = P.M0 - P.fuel * (P.mflow * P.T * out.tf);   // mass(nt-1) = mflow*T*tf (LO:123)
       a.status[b] = out.status;
@@ -125,14 +165,14 @@ __global__ void __launch_bounds__(kBlock, kBlocksPerSM) ascent_ipm_kernel(KArgs 
           for (int i = 0; i < 6; ++i) z[i] = WS_AT(sp, out.cur * N_ITER + F_Z + i);
           const double u = WS_AT(sp, out.cur * N_ITER + F_U);
           const double m = P.mflow * P.T * a.tau[k] * out.tf;
-          struct { double ay, ax; } f;
-          accel_value(P, z[0], z[2], z[4], m, f.ay, f.ax);
+          double ay, ax;
+          accel_value(P, z[0], z[2], z[4], m, ay, ax);
           t[((long)LMATO_V_Y * nt + k) * B + b] = z[0];
           t[((long)LMATO_V_YDOT * nt + k) * B + b] = z[1];
-          t[((long)LMATO_V_YDOUBLEDOT * nt + k) * B + b] = f.ay;
+          t[((long)LMATO_V_YDOUBLEDOT * nt + k) * B + b] = ay;
           t[((long)LMATO_V_X * nt + k) * B + b] = z[2];
           t[((long)LMATO_V_XDOT * nt + k) * B + b] = z[3];
-          t[((long)LMATO_V_XDOUBLEDOT * nt + k) * B + b] = f.ax;
+          t[((long)LMATO_V_XDOUBLEDOT * nt + k) * B + b] = ax;
           t[((long)LMATO_V_ANGLE * nt + k) * B + b] = z[4];
           t[((long)LMATO_V_ANGLEDOT * nt + k) * B + b] = z[5];
           t[((long)LMATO_V_MASS * nt + k) * B + b] = m;
@@ -140,7 +180,6 @@ __global__ void __launch_bounds__(kBlock, kBlocksPerSM) ascent_ipm_kernel(KArgs 
         }
       }
     }
-    __syncwarp();
   }
 }
 
@@ -154,6 +193,24 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters) 
     a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
   }
   out[(long)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// Self-test of the branch-free math against the CUDA library: max relative errors of
+// rcp, rsqrt, log over [1e-40, 1e3] and max absolute errors of sin, cos over [0, 3.5].
+__global__ void math_selftest_kernel(double* out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double t = (double)i / (double)(n - 1);
+  const double x = exp(log(1e-40) + t * (log(1e3) - log(1e-40)));
+  const double a = 3.5 * t;
+  double s, c;
+  lm_sincos_small(a, &s, &c);
+  const double lx = log(x);
+  out[i * 5 + 0] = fabs(lm_rcp(x) * x - 1.0);
+  out[i * 5 + 1] = fabs(lm_rsqrt(x) * sqrt(x) - 1.0);
+  out[i * 5 + 2] = fabs(lm_log_pos(x) - lx) / fmax(fabs(lx), 1e-3);
+  out[i * 5 + 3] = fabs(s - sin(a));
+  out[i * 5 + 4] = fabs(c - cos(a));
 }
 
 }  // namespace
@@ -271,10 +328,10 @@ lmato_status_t lmato_set_options(lmato_handle* h, const lmato_options* o) {
 }
 
 static long slots_for(const lmato_handle* h, int64_t B) {
-  const long cap = (long)h->sm_count * kBlocksPerSM * kBlock;   // resident threads
-  long need = ((B + 31) / 32) * 32;
-  long s = need < cap ? need : cap;
-  return ((s + kBlock - 1) / kBlock) * kBlock;
+  // one CTA per SM, but never more CTAs than 32-problem chunks
+  const long chunks = (B + 31) / 32;
+  const long grid = chunks < (long)h->sm_count * kBlocksPerSM ? (chunks > 0 ? chunks : 1) : (long)h->sm_count * kBlocksPerSM;
+  return grid * kBlock;
 }
 
 lmato_status_t lmato_workspace_bytes(lmato_handle* h, int64_t B, int64_t* bytes) {
@@ -386,6 +443,25 @@ lmato_status_t lmato_solve_batch_host(lmato_handle* h, const double* params, int
   CUDA_TRY(cudaMemcpyAsync(out_status, d_st, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaMemcpyAsync(out_iters, d_it, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
+  return LMATO_OK;
+}
+
+lmato_status_t lmato_selftest_math(lmato_handle* h, double* max_err5) {
+  if (!h || !max_err5) { set_err("lmato_selftest_math: bad argument"); return LMATO_ERR_INVALID; }
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int n = 1 << 18;
+  double* d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, sizeof(double) * 5 * n));
+  math_selftest_kernel<<<(n + 255) / 256, 256>>>(d, n);
+  CUDA_TRY(cudaGetLastError());
+  std::vector<double> hbuf((size_t)5 * n);
+  CUDA_TRY(cudaMemcpy(hbuf.data(), d, sizeof(double) * 5 * n, cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  h->launches += 1;
+  for (int j = 0; j < 5; ++j) max_err5[j] = 0.0;
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < 5; ++j)
+      if (!(hbuf[(size_t)i * 5 + j] <= max_err5[j])) max_err5[j] = hbuf[(size_t)i * 5 + j];   // NaN-propagating max
   return LMATO_OK;
 }
 

@@ -147,7 +147,7 @@ LM_HD double dmin(double a, double b) { return a < b ? a : b; }
 // 1/a, 1/b, 1/c, 1/d with a single division (all arguments are positive slacks in (0, ~2)).
 LM_HD void recip4(double a, double b, double c, double d, double& ia, double& ib, double& ic, double& id) {
   const double ab = a * b, cd = c * d;
-  const double ip = 1.0 / (ab * cd);
+  const double ip = lm_rcp(ab * cd);
   const double iab = ip * cd, icd = ip * ab;
   ia = iab * b; ib = iab * a; ic = icd * d; id = icd * c;
 }
@@ -194,7 +194,7 @@ LM_HD void stagejac_invert(StageJac& J) {
   const double al = J.al;
   const double a2a = al * J.ala, a2b = al * J.alb, a2c = al * J.alc, a2d = al * J.ald;
   const double d11 = 1.0 - a2a, d33 = 1.0 - a2d;
-  const double Dinv = 1.0 / (d11 * d33 - a2b * a2c);
+  const double Dinv = lm_rcp(d11 * d33 - a2b * a2c);
   J.m11 = d33 * Dinv; J.m13 = a2b * Dinv; J.m31 = a2c * Dinv; J.m33 = d11 * Dinv;
 }
 
@@ -560,7 +560,7 @@ LM_NOINLINE void eval_pass(const Params& P, const Mesh& M, const Options& O, con
     if (!(dLa > 0 && dUa > 0 && dLu > 0 && dUu > 0)) bad = true;
     zla = clip_mult(zla, dLa, mu); zua = clip_mult(zua, dUa, mu);
     zlu = clip_mult(zlu, dLu, mu); zuu = clip_mult(zuu, dUu, mu);
-    sumlog += log((dLa * dUa) * (dLu * dUu));
+    sumlog += lm_log_pos((dLa * dUa) * (dLu * dUu));
     {
       const double c1 = dLa * zla, c2 = dUa * zua, c3 = dLu * zlu, c4 = dUu * zuu;
       cmin = dmin(cmin, dmin(dmin(c1, c2), dmin(c3, c4)));
@@ -795,7 +795,7 @@ LM_NOINLINE bool riccati_backward(const Params& P, const Mesh& M, const Options&
     rx[6] = pv[6] - (Bm[0][2] * c[0] + Bm[1][2] * c[1] + Bm[2][2] * c[2] + Bm[3][2] * c[3] + C02 * c[4] + C12 * c[5]);
     const double ru = q.r + beta * rx[5];
     if (!(Ruu > 0.0) || !(Ruu < 1e300)) ok = false;
-    const double Rinv = 1.0 / Ruu;
+    const double Rinv = lm_rcp(Ruu);
     double RuxS[7];
 #pragma unroll
     for (int i = 0; i < 7; ++i) { RuxS[i] = Rux[i] * Rinv; WS_AT(sp, F_K + i) = -RuxS[i]; }
@@ -966,47 +966,50 @@ LM_HD void filter_add(Ctl& c, double th, double ph) {
   c.nf = n;
 }
 
-// One complete solve of one problem.  Output goes to the caller.
-struct SolveOut { double tf; int status; int iters; double kkt; double mu; int cur; };
+// ---------------------------------------------------------------------------------------
+// Resumable per-problem driver.  ipm_begin() after the start point is in buffer 0;
+// ipm_iterate() performs one iteration (iteration 0 = least-squares multiplier estimate, IPOPT
+// section 3.6, which runs through the very same three sweeps) and returns true once the problem
+// is finished.  The CUDA kernel calls it in a loop with a block barrier in between so that all
+// warps of an SM run the same sweep at the same time (instruction-cache locality).
+// ---------------------------------------------------------------------------------------
+enum : int { PH_LSQ = 0, PH_NEWTON = 1 };
 
-LM_HD void ipm_solve(const Params& P, const Mesh& M, const Options& O, const Ws& W, bool have_guess,
-                     SolveOut& out) {
-  Scal cur, trial;
+struct IpmState {
+  Scal cur;
   Ctl ctl;
   TermStep ts;
-  ts.dtf = ts.dsg1 = ts.dsg2 = ts.dzs1 = ts.dzs2 = ts.dnu3 = ts.dzLt = ts.dzUt = 0.0;
-  if (!have_guess) init_guess(P, M, O, W, cur);
+  double err0;
+  int src;
+  int phase;
+  int polish_left;
+  bool polishing;
+};
+
+struct SolveOut { double tf; int status; int iters; double kkt; double mu; int cur; };
+
+LM_HD void ipm_begin(const Options& O, IpmState& S) {
+  S.ts.dtf = S.ts.dsg1 = S.ts.dsg2 = S.ts.dzs1 = S.ts.dzs2 = S.ts.dnu3 = S.ts.dzLt = S.ts.dzUt = 0.0;
+  S.ctl.mu = O.mu_init;
+  S.ctl.tau = dmax(O.tau_min, 1.0 - S.ctl.mu);
+  S.ctl.nf = 0; S.ctl.dw_last = 0.0; S.ctl.iter = 0; S.ctl.status = ST_RUNNING;
+  S.ctl.theta_max = 1e300; S.ctl.theta_min = 0.0;
+  S.err0 = 1e300;
+  S.src = 0;
+  S.phase = PH_LSQ;
+  S.polish_left = -1;
+  S.polishing = false;
+}
+
+LM_HD bool ipm_iterate(const Params& P, const Mesh& M, const Options& O, const Ws& W, IpmState& S) {
+  Ctl& ctl = S.ctl;
+  Scal& cur = S.cur;
   const int N = M.N;
   const int n_eq = 6 * N + 3;
   const int n_bd = 4 * N + 4;
-  ctl.mu = O.mu_init;
-  ctl.tau = dmax(O.tau_min, 1.0 - ctl.mu);
-  ctl.nf = 0; ctl.dw_last = 0.0; ctl.iter = 0; ctl.status = ST_RUNNING;
-  int src = 0;
-  // evaluate the starting point (alpha = 0 copies buffer 0 -> 1 with the safeguards applied)
-  {
-    // least-squares multipliers for the defect rows (IPOPT 3.6); discarded if too large
-    double dtf0 = 0.0, pimax = 0.0;
-    StepInfo s0;
-    bool have = false;
-    if (riccati_backward(P, M, O, W, src, cur, ctl.mu, 0.0, true, &dtf0)) {
-      riccati_forward(P, M, O, W, src, cur, ctl.mu, ctl.tau, dtf0, true, ts, s0);
-      eval_pass(P, M, O, W, src, 1 - src, cur, ts, ctl.mu, 0.0, 0.0, 0.0, 1.0, EV_LSQ, trial, &pimax);
-      have = pimax <= 1e3 * dmax(1.0, O.obj_scale) && fabs(ts.dnu3) <= 1e3 * dmax(1.0, O.obj_scale);
-#if defined(LMATO_TRACE) && !defined(__CUDA_ARCH__)
-      printf("LS multipliers: pimax %.3e dnu3 %.3e dtf %.3e -> %s\n", pimax, ts.dnu3, dtf0, have ? "used" : "discarded");
-#endif
-    }
-    if (!have) eval_pass(P, M, O, W, src, 1 - src, cur, ts, ctl.mu, 0.0, 0.0, 0.0, 0.0, EV_READ_PI, trial, nullptr);
-  }
-  cur = trial; src = 1 - src;
-  ctl.theta_max = 1e4 * dmax(1.0, cur.theta);
-  ctl.theta_min = 1e-4 * dmax(1.0, cur.theta);
-  double err0 = 1e300;
-  int polish_left = -1;
-  bool polishing = false;
-  while (true) {
-    err0 = kkt_error(cur, 0.0, n_eq, n_bd);
+  const bool ls = (S.phase == PH_LSQ);
+  if (!ls) {
+    S.err0 = kkt_error(cur, 0.0, n_eq, n_bd);
     // barrier parameter update (IPOPT eq. 7)
     const double mu_min = O.tol * O.mu_min_factor;
     // (the sub-problem tolerance kappa_eps*mu is floored at tol: below that it would ask for more
@@ -1019,76 +1022,114 @@ LM_HD void ipm_solve(const Params& P, const Mesh& M, const Options& O, const Ws&
     // Converged = scaled KKT error <= tol with the barrier parameter at its floor.  Requiring the
     // floor pins the final point on the central path: the control on the singular arc is a nearly
     // flat direction of this NLP and moves like O(mu / sigma_min) (DESIGN.md "Tolerance").
-    if (err0 <= O.tol && ctl.mu <= mu_min * (1.0 + 1e-12)) {
+    if (S.err0 <= O.tol && ctl.mu <= mu_min * (1.0 + 1e-12)) {
       // Newton converges quadratically here; `n_polish` more iterations take the point from
       // "residual <= tol" to the FP64 floor, which is what makes two implementations agree on the
       // weakly determined control.  A polish step that fails leaves the converged point in place.
-      if (polish_left < 0) polish_left = O.n_polish;
-      if (polish_left == 0) { ctl.status = ST_CONVERGED; break; }
-      --polish_left;
-      polishing = true;
+      if (S.polish_left < 0) S.polish_left = O.n_polish;
+      if (S.polish_left == 0) { ctl.status = ST_CONVERGED; return true; }
+      --S.polish_left;
+      S.polishing = true;
     } else {
-      polishing = false;
+      S.polishing = false;
     }
-    if (ctl.iter >= O.max_iter) { ctl.status = polishing ? ST_CONVERGED : ST_MAX_ITER; break; }
-    // factorisation with inertia correction (IPOPT Algorithm IC)
-    double dw = 0.0, dtf = 0.0;
-    bool fact_ok = false;
-    for (int attempt = 0; attempt < 40; ++attempt) {
-      if (riccati_backward(P, M, O, W, src, cur, ctl.mu, dw, false, &dtf)) { fact_ok = true; break; }
-      if (dw == 0.0) dw = (ctl.dw_last == 0.0) ? 1e-4 : dmax(1e-20, ctl.dw_last / 3.0);
-      else dw *= (ctl.dw_last == 0.0) ? 100.0 : 8.0;
-      if (dw > 1e40) break;
-    }
-    if (!fact_ok) { ctl.status = polishing ? ST_CONVERGED : ST_INERTIA_FAIL; break; }
-    if (dw > 0.0) ctl.dw_last = dw;
-    StepInfo si;
-    riccati_forward(P, M, O, W, src, cur, ctl.mu, ctl.tau, dtf, false, ts, si);
-    if (!(si.dphi == si.dphi) || !(si.dxmax < 1e300)) { ctl.status = polishing ? ST_CONVERGED : ST_NUMERICAL; break; }
-    // filter line search (IPOPT section 2.3)
-    const double theta = cur.theta;
-    const double phi = cur.fobj - ctl.mu * cur.sumlog;
-    const double dphi = si.dphi;
-    const double g_th = 1e-5, g_ph = 1e-8, s_th = 1.1, s_ph = 2.3, eta = 1e-8, delta = 1.0;
-    double alpha = si.a_max;
-    bool accepted = false, ftype = false;
-    // switching condition (IPOPT eq. 19): alpha * (-dphi)^s_ph > delta * theta^s_th.  The two powers
-    // do not depend on alpha, so they are evaluated once per iteration.
-    const bool sw_possible = (theta <= ctl.theta_min) && (dphi < 0.0);
-    const double sw_lhs = sw_possible ? pow(-dphi, s_ph) : 0.0;
-    const double sw_rhs = sw_possible ? delta * pow(theta, s_th) : 0.0;
-    for (int lsi = 0; lsi < O.max_ls; ++lsi) {
-      eval_pass(P, M, O, W, src, 1 - src, cur, ts, ctl.mu, dw, alpha, si.a_z, alpha,
-                lsi == 0 ? EV_NEWTON : EV_READ_PI, trial, nullptr);
-      const double th_t = trial.theta;
-      const double ph_t = trial.fobj - ctl.mu * trial.sumlog;
-      bool ok = (th_t <= ctl.theta_max) && (ph_t == ph_t) && (ph_t < 1e299) && filter_ok(ctl, th_t, ph_t);
-      if (ok) {
-        ftype = sw_possible && (alpha * sw_lhs > sw_rhs);
-        if (ftype) ok = cmp_le(ph_t - phi, eta * alpha * dphi, phi);
-        else ok = cmp_le(th_t, (1.0 - g_th) * theta, theta) || cmp_le(ph_t - phi, -g_ph * theta, phi);
-      }
-      // Terminal phase (analogue of IPOPT's tiny-step rule): once the violation is below tol before
-      // and after the step and the merit changes by less than tol (relative), both filter measures
-      // are rounding noise and cannot rank points any more; the Newton step is taken as is.
-      if (!ok && lsi == 0 && theta <= O.tol && th_t <= O.tol && (ph_t == ph_t) &&
-          fabs(ph_t - phi) <= O.tol * dmax(1.0, fabs(phi))) { ok = true; ftype = true; }
-      if (ok) { accepted = true; break; }
-      alpha *= 0.5;
-    }
-#if defined(LMATO_TRACE) && !defined(__CUDA_ARCH__)
-    if (!accepted) printf("LS FAIL theta %.3e phi %.6e dphi %.3e amax %.3e dx %.2e th_t %.3e ph_t %.6e\n", theta, phi, dphi, si.a_max, si.dxmax, trial.theta, trial.fobj - ctl.mu * trial.sumlog);
-#endif
-    if (!accepted) { ctl.status = polishing ? ST_CONVERGED : ST_LINESEARCH_FAIL; break; }
-    if (!ftype) filter_add(ctl, (1.0 - g_th) * theta, phi - g_ph * theta);
-    cur = trial; src = 1 - src;
-    ++ctl.iter;
-#if defined(LMATO_TRACE) && !defined(__CUDA_ARCH__)
-    printf("%3d tf %.8f th %.3e err %.3e mu %.1e a %.3e az %.3e dw %.1e dphi %.2e dx %.2e nf %d %s\n", ctl.iter, cur.tf,
-           cur.theta, err0, ctl.mu, alpha, si.a_z, dw, dphi, si.dxmax, ctl.nf, ftype ? "f" : "h");
-#endif
+    if (ctl.iter >= O.max_iter) { ctl.status = S.polishing ? ST_CONVERGED : ST_MAX_ITER; return true; }
   }
-  out.tf = cur.tf; out.status = ctl.status; out.iters = ctl.iter; out.kkt = err0; out.mu = ctl.mu; out.cur = src;
+  const bool polishing = S.polishing;
+  // factorisation with inertia correction (IPOPT Algorithm IC)
+  double dw = 0.0, dtf = 0.0;
+  bool fact_ok = false;
+  for (int attempt = 0; attempt < 40; ++attempt) {
+    if (riccati_backward(P, M, O, W, S.src, cur, ctl.mu, dw, ls, &dtf)) { fact_ok = true; break; }
+    if (ls) break;
+    if (dw == 0.0) dw = (ctl.dw_last == 0.0) ? 1e-4 : dmax(1e-20, ctl.dw_last / 3.0);
+    else dw *= (ctl.dw_last == 0.0) ? 100.0 : 8.0;
+    if (dw > 1e40) break;
+  }
+  Scal trial;
+  if (ls) {
+    // least-squares multipliers for the defect rows; discarded if the solve failed or they are huge
+    bool have = false;
+    if (fact_ok) {
+      StepInfo s0;
+      double pimax = 0.0;
+      riccati_forward(P, M, O, W, S.src, cur, ctl.mu, ctl.tau, dtf, true, S.ts, s0);
+      eval_pass(P, M, O, W, S.src, 1 - S.src, cur, S.ts, ctl.mu, 0.0, 0.0, 0.0, 1.0, EV_LSQ, trial, &pimax);
+      have = pimax <= 1e3 * dmax(1.0, O.obj_scale) && fabs(S.ts.dnu3) <= 1e3 * dmax(1.0, O.obj_scale);
+#if defined(LMATO_TRACE) && !defined(__CUDA_ARCH__)
+      printf("LS multipliers: pimax %.3e dnu3 %.3e dtf %.3e -> %s\n", pimax, S.ts.dnu3, dtf, have ? "used" : "discarded");
+#endif
+    }
+    if (!have) eval_pass(P, M, O, W, S.src, 1 - S.src, cur, S.ts, ctl.mu, 0.0, 0.0, 0.0, 0.0, EV_READ_PI, trial, nullptr);
+    cur = trial; S.src = 1 - S.src;
+    ctl.theta_max = 1e4 * dmax(1.0, cur.theta);
+    ctl.theta_min = 1e-4 * dmax(1.0, cur.theta);
+    S.phase = PH_NEWTON;
+    return false;
+  }
+  if (!fact_ok) { ctl.status = polishing ? ST_CONVERGED : ST_INERTIA_FAIL; return true; }
+  if (dw > 0.0) ctl.dw_last = dw;
+  StepInfo si;
+  riccati_forward(P, M, O, W, S.src, cur, ctl.mu, ctl.tau, dtf, false, S.ts, si);
+  if (!(si.dphi == si.dphi) || !(si.dxmax < 1e300)) { ctl.status = polishing ? ST_CONVERGED : ST_NUMERICAL; return true; }
+  // filter line search (IPOPT section 2.3)
+  const double theta = cur.theta;
+  const double phi = cur.fobj - ctl.mu * cur.sumlog;
+  const double dphi = si.dphi;
+  const double g_th = 1e-5, g_ph = 1e-8, s_th = 1.1, s_ph = 2.3, eta = 1e-8, delta = 1.0;
+  double alpha = si.a_max;
+  bool accepted = false, ftype = false;
+  // switching condition (IPOPT eq. 19): alpha * (-dphi)^s_ph > delta * theta^s_th.  The two powers
+  // do not depend on alpha, so they are evaluated once per iteration.
+  const bool sw_possible = (theta <= ctl.theta_min) && (dphi < 0.0);
+  const double sw_lhs = sw_possible ? pow(-dphi, s_ph) : 0.0;
+  const double sw_rhs = sw_possible ? delta * pow(theta, s_th) : 0.0;
+  for (int lsi = 0; lsi < O.max_ls; ++lsi) {
+    eval_pass(P, M, O, W, S.src, 1 - S.src, cur, S.ts, ctl.mu, dw, alpha, si.a_z, alpha,
+              lsi == 0 ? EV_NEWTON : EV_READ_PI, trial, nullptr);
+    const double th_t = trial.theta;
+    const double ph_t = trial.fobj - ctl.mu * trial.sumlog;
+    bool ok = (th_t <= ctl.theta_max) && (ph_t == ph_t) && (ph_t < 1e299) && filter_ok(ctl, th_t, ph_t);
+    if (ok) {
+      ftype = sw_possible && (alpha * sw_lhs > sw_rhs);
+      if (ftype) ok = cmp_le(ph_t - phi, eta * alpha * dphi, phi);
+      else ok = cmp_le(th_t, (1.0 - g_th) * theta, theta) || cmp_le(ph_t - phi, -g_ph * theta, phi);
+    }
+    // Terminal phase (analogue of IPOPT's tiny-step rule): once the violation is below tol before
+    // and after the step and the merit changes by less than tol (relative), both filter measures
+    // are rounding noise and cannot rank points any more; the Newton step is taken as is.
+    if (!ok && lsi == 0 && theta <= O.tol && th_t <= O.tol && (ph_t == ph_t) &&
+        fabs(ph_t - phi) <= O.tol * dmax(1.0, fabs(phi))) { ok = true; ftype = true; }
+    if (ok) { accepted = true; break; }
+    alpha *= 0.5;
+  }
+#if defined(LMATO_TRACE) && !defined(__CUDA_ARCH__)
+  if (!accepted) printf("LS FAIL theta %.3e phi %.6e dphi %.3e amax %.3e dx %.2e th_t %.3e ph_t %.6e\n", theta, phi, dphi, si.a_max, si.dxmax, trial.theta, trial.fobj - ctl.mu * trial.sumlog);
+#endif
+  if (!accepted) { ctl.status = polishing ? ST_CONVERGED : ST_LINESEARCH_FAIL; return true; }
+  if (!ftype) filter_add(ctl, (1.0 - g_th) * theta, phi - g_ph * theta);
+  cur = trial; S.src = 1 - S.src;
+  ++ctl.iter;
+#if defined(LMATO_TRACE) && !defined(__CUDA_ARCH__)
+  printf("%3d tf %.8f th %.3e err %.3e mu %.1e a %.3e az %.3e dw %.1e dphi %.2e dx %.2e nf %d %s\n", ctl.iter, cur.tf,
+         cur.theta, S.err0, ctl.mu, alpha, si.a_z, dw, dphi, si.dxmax, ctl.nf, ftype ? "f" : "h");
+#endif
+  return false;
+}
+
+LM_HD void ipm_result(const IpmState& S, SolveOut& out) {
+  out.tf = S.cur.tf; out.status = S.ctl.status; out.iters = S.ctl.iter; out.kkt = S.err0; out.mu = S.ctl.mu;
+  out.cur = S.src;
+}
+
+// One complete solve of one problem (host simulator; the kernel interleaves ipm_iterate with barriers).
+LM_HD void ipm_solve(const Params& P, const Mesh& M, const Options& O, const Ws& W, bool have_guess,
+                     SolveOut& out) {
+  IpmState S;
+  if (!have_guess) init_guess(P, M, O, W, S.cur);
+  ipm_begin(O, S);
+  while (!ipm_iterate(P, M, O, W, S)) {}
+  ipm_result(S, out);
 }
 
 }  // namespace lmato

@@ -52,11 +52,106 @@ struct Params {
   double Sinv;    // 1 / S
 };
 
+// ---------------------------------------------------------------------------------------
+// Branch-free FP64 math for the inner loops.  Every argument in the sweeps is a normal, positive,
+// bounded number (slacks, radii, masses) or an angle in [0, pi], so the library routines'
+// special-case branches (denormals, infinities, huge-argument reduction) are dead weight: they
+// split every stage body into dozens of small basic blocks (one BSSY/BSYNC pair per rcp / rsqrt /
+// sincos), which starves the two warps per scheduler of instruction-level parallelism.  These
+// versions are straight-line code: hardware seed (MUFU) + Newton, or fdlibm's kernels.
+// ---------------------------------------------------------------------------------------
+LM_HD double lm_rcp(double x) {
+#if defined(__CUDA_ARCH__)
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+#else
+  return 1.0 / x;
+#endif
+}
+
 LM_HD double lm_rsqrt(double x) {
 #if defined(__CUDA_ARCH__)
-  return rsqrt(x);
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double h = 0.5 * x;
+  double e = fma(-h * y, y, 0.5);
+  y = fma(y, e, y);
+  e = fma(-h * y, y, 0.5);
+  y = fma(y, e, y);
+  e = fma(-h * y, y, 0.5);
+  return fma(y, e, y);
 #else
   return 1.0 / sqrt(x);
+#endif
+}
+
+// sin and cos for |a| <= ~3.5 (here: 3*angle in [0, pi]).  Quadrant reduction with a two-term
+// Cody-Waite split of pi/2, then the fdlibm kernels on [-pi/4, pi/4] (error < 1 ulp each).
+LM_HD void lm_sincos_small(double a, double* sn, double* cs) {
+#if defined(__CUDA_ARCH__)
+  const double kq = rint(a * 0.63661977236758138);          // a * 2/pi
+  double r = fma(-kq, 1.5707963267948966, a);               // pi/2 hi
+  r = fma(-kq, 6.123233995736766e-17, r);                   // pi/2 lo
+  const double z = r * r;
+  // sin kernel
+  double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+  ps = fma(ps, z, 2.75573137070700676789e-06);
+  ps = fma(ps, z, -1.98412698298579493134e-04);
+  ps = fma(ps, z, 8.33333333332248946124e-03);
+  ps = fma(ps, z, -1.66666666666666324348e-01);
+  const double s = fma(r * z, ps, r);
+  // cos kernel
+  double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+  pc = fma(pc, z, -2.75573143513906633035e-07);
+  pc = fma(pc, z, 2.48015872894767294178e-05);
+  pc = fma(pc, z, -1.38888888888741095749e-03);
+  pc = fma(pc, z, 4.16666666666666019037e-02);
+  const double c = fma(z * z, pc, fma(-0.5, z, 1.0));
+  const int q = (int)kq & 3;
+  const double s1 = (q & 1) ? c : s;
+  const double c1 = (q & 1) ? s : c;
+  *sn = (q & 2) ? -s1 : s1;
+  *cs = ((q + 1) & 2) ? -c1 : c1;
+#else
+  *sn = sin(a);
+  *cs = cos(a);
+#endif
+}
+
+// Natural logarithm of a positive normal double (fdlibm e_log.c core, straight-line).
+LM_HD double lm_log_pos(double x) {
+#if defined(__CUDA_ARCH__)
+  int hx = __double2hiint(x);
+  const int lx = __double2loint(x);
+  int k = (hx >> 20) - 1023;
+  hx &= 0x000fffff;
+  const int i = (hx + 0x95f64) & 0x100000;                  // mantissa >= sqrt(2): halve it
+  const double m = __hiloint2double(hx | (i ^ 0x3ff00000), lx);
+  k += (i >> 20);
+  const double f = m - 1.0;
+  const double sden = lm_rcp(2.0 + f);
+  const double s = f * sden;
+  const double dk = (double)k;
+  const double z = s * s;
+  const double w = z * z;
+  double t1 = fma(w, 1.531383769920937332e-01, 2.222219843214978396e-01);   // Lg6, Lg4
+  t1 = fma(t1, w, 3.999999999940941908e-01);                                 // Lg2
+  t1 *= w;
+  double t2 = fma(w, 1.479819860511658591e-01, 1.818357216161805012e-01);   // Lg7, Lg5
+  t2 = fma(t2, w, 2.857142874366239149e-01);                                 // Lg3
+  t2 = fma(t2, w, 6.666666666666735130e-01);                                 // Lg1
+  const double R = fma(t2, z, t1);
+  const double hfsq = 0.5 * f * f;
+  // log(x) = k*ln2_hi - ((hfsq - (s*(hfsq+R) + k*ln2_lo)) - f)
+  return fma(dk, 6.93147180369123816490e-01, -((hfsq - fma(s, hfsq + R, dk * 1.90821492927058770002e-10)) - f));
+#else
+  return log(x);
 #endif
 }
 
@@ -85,10 +180,10 @@ LM_HD void accel_first(const Params& P, double y, double x, double a, double m, 
   const double rinv = lm_rsqrt(r2);
   const double nx = X * rinv, ny = Y * rinv;
   double s3, c3;
-  lm_sincos(3.0 * a, &s3, &c3);
+  lm_sincos_small(3.0 * a, &s3, &c3);
   const double Ty = fma(ny, c3, nx * s3);      // cos(psi - 3a)
   const double Tx = fma(nx, c3, -ny * s3);     // sin(psi - 3a)
-  const double mden = 1.0 / (P.M0 - P.ms * m);
+  const double mden = lm_rcp(P.M0 - P.ms * m);
   const double AT = P.Ft * mden;               // thrust acceleration [m/s^2]
   const double eta = P.ms * mden;              // d ln(AT) / d mass
   const double g2 = P.GM * rinv * rinv;        // GM / r^2
@@ -117,8 +212,8 @@ LM_HD void accel_value(const Params& P, double y, double x, double a, double m, 
   const double rinv = lm_rsqrt(r2);
   const double nx = X * rinv, ny = Y * rinv;
   double s3, c3;
-  lm_sincos(3.0 * a, &s3, &c3);
-  const double AT = P.Ft / (P.M0 - P.ms * m);
+  lm_sincos_small(3.0 * a, &s3, &c3);
+  const double AT = P.Ft * lm_rcp(P.M0 - P.ms * m);
   const double g2 = P.GM * rinv * rinv;
   ay = (AT * fma(ny, c3, nx * s3) - g2 * ny) * P.Sinv;
   ax = (AT * fma(nx, c3, -ny * s3) - g2 * nx) * P.Sinv;

@@ -192,3 +192,13 @@ def test_infeasible_draw_surfaces_as_status(lm):
     assert int(sol.status[0]) == 0 and int(sol.status[2]) == 0
     assert int(sol.status[1]) != 0
     assert float(sol.tf[0]) == float(sol.tf[2])
+
+
+def test_branch_free_math_matches_cuda_library(lm):
+    """The sweeps use straight-line rcp / rsqrt / log / sincos (csrc/ascent_model.cuh); on the device
+    they must agree with the CUDA math library to a few ulp over the ranges the solver uses."""
+    solver = lm.AscentSolver(lm.Mesh(nt=20), lm.SolverOptions(), device=0)
+    e = solver.selftest_math()
+    assert e["rcp"] < 5e-16 and e["rsqrt"] < 5e-16, e
+    assert e["log"] < 1e-15, e
+    assert e["sin"] < 5e-16 and e["cos"] < 5e-16, e
