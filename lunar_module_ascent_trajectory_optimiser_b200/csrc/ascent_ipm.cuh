@@ -278,6 +278,13 @@ LM_NOINLINE void init_guess(const Params& P, const Mesh& M, const Options& O, co
   const GuessProfile g = guess_profile(P);
   double y = 0, vy = 0, x = 0, vx = 0, a = 0, w = 0, t_prev = 0;
   const double a_lo = 1e-2 * P.a_ub, a_hi = 0.99 * P.a_ub;
+  {
+    // node 0 is pinned at zero (LO:145-151): keep its state / step rows as literal zeros so that
+    // the sweeps can read "node k-1" without a special case at k = 1
+    double* s0 = W.stage(0);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { WS_AT(s0, F_Z + i) = 0.0; WS_AT(s0, N_ITER + F_Z + i) = 0.0; WS_AT(s0, F_DS + i) = 0.0; }
+  }
   for (int k = 1; k <= N; ++k) {
     const double t = M.tau[k] * tf0 * P.T;
     const double dt = t - t_prev;
@@ -491,16 +498,13 @@ LM_NOINLINE void eval_pass(const Params& P, const Mesh& M, const Options& O, con
     double z[6], zpo[6], dsp[6], zp[6], lam[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i) z[i] = fma(alpha, ds[i], zo[i]);
-    if (k > 1) {
-      const double* sm = W.stage(k - 1);
+    {
+      const double* sm = W.stage(k - 1);          // node 0 rows are zeros
 #pragma unroll
       for (int i = 0; i < 6; ++i) {
         zpo[i] = WS_AT(sm, so + F_Z + i); dsp[i] = WS_AT(sm, F_DS + i);
         zp[i] = fma(alpha, dsp[i], zpo[i]);
       }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 6; ++i) { zpo[i] = 0.0; dsp[i] = 0.0; zp[i] = 0.0; }
     }
     const double u_old = WS_AT(sp, so + F_U);
     const double du = WS_AT(sp, F_DU);
@@ -558,8 +562,15 @@ LM_NOINLINE void eval_pass(const Params& P, const Mesh& M, const Options& O, con
     }
     const double dLa = z[4], dUa = P.a_ub - z[4], dLu = u + P.u_ub, dUu = P.u_ub - u;
     if (!(dLa > 0 && dUa > 0 && dLu > 0 && dUu > 0)) bad = true;
-    zla = clip_mult(zla, dLa, mu); zua = clip_mult(zua, dUa, mu);
-    zlu = clip_mult(zlu, dLu, mu); zuu = clip_mult(zuu, dUu, mu);
+    {
+      // kappa_Sigma safeguard: one (rarely taken) branch for the four multipliers of the node
+      const double c1 = dLa * zla, c2 = dUa * zua, c3 = dLu * zlu, c4 = dUu * zuu;
+      const double hi = 1e10 * mu, lo = 1e-10 * mu;
+      if (dmax(dmax(c1, c2), dmax(c3, c4)) > hi || dmin(dmin(c1, c2), dmin(c3, c4)) < lo) {
+        zla = clip_mult(zla, dLa, mu); zua = clip_mult(zua, dUa, mu);
+        zlu = clip_mult(zlu, dLu, mu); zuu = clip_mult(zuu, dUu, mu);
+      }
+    }
     sumlog += lm_log_pos((dLa * dUa) * (dLu * dUu));
     {
       const double c1 = dLa * zla, c2 = dUa * zua, c3 = dLu * zlu, c4 = dUu * zuu;
@@ -684,13 +695,10 @@ LM_NOINLINE bool riccati_backward(const Params& P, const Mesh& M, const Options&
     double lam[6], zm[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i) lam[i] = WS_AT(sp, so + F_LAM + i);
-    if (k > 1) {
-      const double* sm = W.stage(k - 1);
+    {
+      const double* sm = W.stage(k - 1);          // node 0 rows are zeros
 #pragma unroll
       for (int i = 0; i < 6; ++i) zm[i] = WS_AT(sm, so + F_Z + i);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 6; ++i) zm[i] = 0.0;
     }
     const double u = WS_AT(sp, so + F_U);
     const double zla = WS_AT(sp, so + F_ZLA), zua = WS_AT(sp, so + F_ZUA);
