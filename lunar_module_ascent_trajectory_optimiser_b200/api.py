@@ -185,6 +185,7 @@ class AscentSolver:
         self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
         self.time = self.mesh.grid()
         self.nt = int(self.time.shape[0])
+        self.model = model
         model_id = {"elliptical": 0, "circular": 1}.get(model)
         if model_id is None:
             raise ValueError(f"unknown model {model!r}")
@@ -213,10 +214,24 @@ class AscentSolver:
             pass
 
     # -- raw entry points ---------------------------------------------------------------
-    def solve_rows(self, rows: torch.Tensor, trajectories: bool = True) -> Dict[str, torch.Tensor]:
+    def alloc_outputs(self, B: int, trajectories: bool = True, on_device: bool = True) -> Dict[str, torch.Tensor]:
+        """Result buffers for ``solve_rows(..., out=...)`` (device memory or pinned host memory)."""
+        kw = dict(device=self.device) if on_device else dict(pin_memory=True)
+        return {
+            "traj": torch.empty((_cabi.NVAR, self.nt, B), dtype=torch.float64, **kw) if trajectories else None,
+            "tf": torch.empty(B, dtype=torch.float64, **kw),
+            "final_mass": torch.empty(B, dtype=torch.float64, **kw),
+            "status": torch.empty(B, dtype=torch.int32, **kw),
+            "iterations": torch.empty(B, dtype=torch.int32, **kw),
+            "kkt": torch.empty(B, dtype=torch.float64, **kw),
+        }
+
+    def solve_rows(self, rows: torch.Tensor, trajectories: bool = True,
+                   out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
         """``rows``: ``[NPARAM, B]`` float64.  CUDA tensor -> device entry point, results stay on
         the device (asynchronous on the current stream).  CPU tensor -> host entry point
-        (H2D + solve + D2H, synchronous), results in pinned host memory."""
+        (H2D + solve + D2H, synchronous), results in pinned host memory.  ``out``: buffers from
+        :meth:`alloc_outputs` to write into (avoids re-allocating ~1 GB of trajectories per call)."""
         L = _cabi.lib()
         if rows.dtype != torch.float64 or rows.dim() != 2 or rows.shape[0] != _cabi.NPARAM:
             raise ValueError("rows must be float64 [NPARAM, B]")
@@ -225,15 +240,13 @@ class AscentSolver:
         on_dev = rows.is_cuda
         if on_dev and rows.device != self.device:
             raise ValueError(f"rows live on {rows.device}, solver on {self.device}")
-        kw = dict(device=self.device) if on_dev else dict(pin_memory=True)
-        out = {
-            "traj": torch.empty((_cabi.NVAR, self.nt, B), dtype=torch.float64, **kw) if trajectories else None,
-            "tf": torch.empty(B, dtype=torch.float64, **kw),
-            "final_mass": torch.empty(B, dtype=torch.float64, **kw),
-            "status": torch.empty(B, dtype=torch.int32, **kw),
-            "iterations": torch.empty(B, dtype=torch.int32, **kw),
-            "kkt": torch.empty(B, dtype=torch.float64, **kw),
-        }
+        if out is None:
+            out = self.alloc_outputs(B, trajectories, on_dev)
+        else:
+            if out["tf"].shape[0] != B or out["tf"].is_cuda != on_dev or (trajectories and out["traj"] is None):
+                raise ValueError("out buffers do not match this call (batch size / placement / trajectories)")
+            if not trajectories:
+                out = dict(out, traj=None)
         if B == 0:
             return out
         ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p()
@@ -283,17 +296,24 @@ class AscentSolver:
         if not on_device:
             rows = rows.pin_memory()
         raw = self.solve_rows(rows, trajectories)
-        return package_solution(raw, rows, self.time)
+        return package_solution(raw, rows, self.time, self.model)
 
 
-def package_solution(raw: Dict[str, torch.Tensor], rows: torch.Tensor, time: torch.Tensor) -> AscentBatchSolution:
+def package_solution(raw: Dict[str, torch.Tensor], rows: torch.Tensor, time: torch.Tensor,
+                     model: str = "elliptical") -> AscentBatchSolution:
     traj = raw["traj"]
     states: Dict[str, torch.Tensor] = {}
     control = None
     if traj is not None:
         for i, name in enumerate(_cabi.VAR_ROWS):
             states[name] = traj[i].transpose(0, 1)      # [B, nt] view
-        control = states.pop("angledoubledot")
+        if model == "circular":
+            # PDF p.27 src 54-73: the Vars are y, ydot, ydoubledot, x, xdot, xdoubledot, mass and the
+            # MV is `angle`; angledot / angledoubledot do not exist in that model
+            states.pop("angledot"); states.pop("angledoubledot")
+            control = states.pop("angle")
+        else:
+            control = states.pop("angledoubledot")
     T = rows[_cabi.PARAM_ROWS.index("final_time")]
     return AscentBatchSolution(tf=raw["tf"], tf_seconds=raw["tf"] * T.to(raw["tf"].device), states=states,
                                control=control, final_mass=raw["final_mass"], status=raw["status"],
@@ -406,11 +426,11 @@ def optimise_batch(params: AscentParams, mesh: Optional[Mesh] = None,
         raw = sharded_solve(dev_rows, lambda r: solver.solve_rows(r, trajectories), g)
         if not on_dev:
             raw = {k: (v.cpu() if v is not None else None) for k, v in raw.items()}
-        return package_solution(raw, rows, solver.time)
+        return package_solution(raw, rows, solver.time, params.model)
     if not on_dev:
         rows = rows.pin_memory()
     raw = solver.solve_rows(rows, trajectories)
-    return package_solution(raw, rows, solver.time)
+    return package_solution(raw, rows, solver.time, params.model)
 
 
 def optimise(params: Optional[AscentParams] = None, mesh: Optional[Mesh] = None,

@@ -40,6 +40,9 @@ void set_err(const char* fmt, const char* a = "", const char* b = "") {
   } while (0)
 
 // One CTA of 256 threads (8 warps) per SM: 255 registers x 256 threads fills the register file.
+#ifndef LMATO_SYNC_PERIOD
+#define LMATO_SYNC_PERIOD 1
+#endif
 constexpr int kBlock = 256;
 constexpr int kBlocksPerSM = 1;
 
@@ -58,10 +61,11 @@ struct KArgs {
   const double* h;
   const double* tau;
   int* counter;
+  int model;             // lmato_model_t
   Options O;
 };
 
-__device__ __forceinline__ Params derive_params(const double* __restrict__ p, long B, long b) {
+__device__ __forceinline__ Params derive_params(const double* __restrict__ p, long B, long b, int model) {
   // LO:50-75, 107-109
   Params P;
   const double G = p[LMATO_P_G * B + b], Mm = p[LMATO_P_M * B + b];
@@ -86,6 +90,13 @@ __device__ __forceinline__ Params derive_params(const double* __restrict__ p, lo
   P.tf_ub = fmin(1.0, 1.0 / (P.mflow * P.T));
   P.fuel = fuel;
   P.Sinv = 1.0 / P.S;
+  P.coup5 = 1.0;
+  if (model == LMATO_MODEL_CIRCULAR) {
+    // PDF p.27 src 69-73: the MV is the pitch angle itself; no rate or acceleration limit exists
+    P.coup5 = 0.0;
+    P.asc = 1.0;
+    P.u_ub = 1e20;
+  }
   return P;
 }
 
@@ -116,6 +127,7 @@ __global__ void __launch_bounds__(kBlock, kBlocksPerSM) ascent_ipm_kernel(KArgs 
   bool first = true;
   long b = -1;
   const int warps_per_block = kBlock / 32;
+  unsigned round = 0;
   while (true) {
     // ---- a warp whose 32 problems are all finished claims the next 32 (warp-uniform branch) ----
     if (!exhausted && !__any_sync(0xffffffffu, active)) {
@@ -134,7 +146,7 @@ __global__ void __launch_bounds__(kBlock, kBlocksPerSM) ascent_ipm_kernel(KArgs 
       } else {
         b = (long)chunk * 32 + lane;
         if (b < a.B) {
-          P = derive_params(a.params, a.B, b);
+          P = derive_params(a.params, a.B, b, a.model);
           init_guess(P, M, O, W, S.cur);
           ipm_begin(O, S);
           active = true;
@@ -143,7 +155,10 @@ __global__ void __launch_bounds__(kBlock, kBlocksPerSM) ascent_ipm_kernel(KArgs 
     }
     // ---- all eight warps of the SM start each iteration together: they then run the same sweep
     //      (same code) at the same time, which keeps the 32 KB instruction cache effective ----
-    if (!__syncthreads_or(active ? 1 : 0)) break;
+    // (every LMATO_SYNC_PERIOD-th round: a barrier per iteration costs more in waiting than it
+    //  gains, because line-search retries differ between warps; the imbalance averages out over
+    //  a few iterations while the warps stay close enough to share the instruction cache)
+    if ((round++ % LMATO_SYNC_PERIOD) == 0 && !__syncthreads_or((active || !exhausted) ? 1 : 0)) break;
     if (active && ipm_iterate(P, M, O, W, S)) {
       active = false;
       SolveOut out;
@@ -265,9 +280,9 @@ lmato_status_t lmato_create(lmato_handle** out, int32_t device, int32_t nt, cons
             nodes == 3 ? "3" : "n");
     return LMATO_ERR_UNSUPPORTED;
   }
-  if (model != LMATO_MODEL_ELLIPTICAL) {
-    set_err("lmato_create: only the elliptical model (Launch_Optimiser.py) is implemented on the device");
-    return LMATO_ERR_UNSUPPORTED;
+  if (model != LMATO_MODEL_ELLIPTICAL && model != LMATO_MODEL_CIRCULAR) {
+    set_err("lmato_create: unknown model");
+    return LMATO_ERR_INVALID;
   }
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -373,6 +388,7 @@ lmato_status_t lmato_solve_batch(lmato_handle* h, const double* params, int64_t 
   a.status = out_status; a.iters = out_iters; a.kkt = out_kkt;
   a.ws = h->d_ws; a.slots = slots; a.N = h->nt - 1; a.h = h->d_h; a.tau = h->d_tau;
   a.counter = h->d_counter;
+  a.model = h->model;
   a.O.tol = h->opt.tol; a.O.mu_init = h->opt.mu_init; a.O.obj_scale = h->opt.obj_scale;
   a.O.kappa_eps = 10.0; a.O.kappa_mu = 0.2; a.O.theta_mu = 1.5; a.O.tau_min = 0.99;
   a.O.delta_c = h->opt.delta_c; a.O.tf_guess = h->opt.tf_guess;

@@ -289,9 +289,17 @@ LM_NOINLINE void init_guess(const Params& P, const Mesh& M, const Options& O, co
     const double t = M.tau[k] * tf0 * P.T;
     const double dt = t - t_prev;
     const double tm = 0.5 * (t + t_prev);
-    const double u = tm < g.t1 ? g.ulev : (tm < g.t1 + g.t2 ? -g.ulev : 0.0);
-    w += dt * P.asc * u;
-    a += dt * w;
+    double u = tm < g.t1 ? g.ulev : (tm < g.t1 + g.t2 ? -g.ulev : 0.0);
+    if (P.coup5 != 0.0) {
+      w += dt * P.asc * u;
+      a += dt * w;
+    } else {
+      // circular model: pitch ramps linearly from ~34 deg (PDF p.21 Fig 9); angledot and u follow
+      const double a_new = 0.2 + 0.45 * M.tau[k];
+      w = (a_new - a) / dt;
+      u = w / (dt * P.asc);
+      a = a_new;
+    }
     const double ac = dmin(dmax(a, a_lo), a_hi);
     const double m = P.mflow * P.T * M.tau[k] * tf0;
     // backward-Euler step for (y, vy, x, vx): three fixed-point sweeps
@@ -311,7 +319,9 @@ LM_NOINLINE void init_guess(const Params& P, const Mesh& M, const Options& O, co
 #pragma unroll
     for (int i = 0; i < 6; ++i) WS_AT(sp, F_LAM + i) = 0.0;
     WS_AT(sp, F_ZLA) = 1.0; WS_AT(sp, F_ZUA) = 1.0;
-    WS_AT(sp, F_ZLU) = 1.0; WS_AT(sp, F_ZUU) = 1.0;
+    // an unbounded control (circular model) starts exactly on the central path of its vacuous bounds
+    WS_AT(sp, F_ZLU) = P.coup5 != 0.0 ? 1.0 : O.mu_init / (u + P.u_ub);
+    WS_AT(sp, F_ZUU) = P.coup5 != 0.0 ? 1.0 : O.mu_init / (P.u_ub - u);
 #pragma unroll
     for (int i = 0; i < N_STEP; ++i) WS_AT(sp, R_STEP + i) = 0.0;
     t_prev = t;
@@ -532,7 +542,7 @@ LM_NOINLINE void eval_pass(const Params& P, const Mesh& M, const Options& O, con
       g[2] = pi_next[2] - (q.q02 * ds[0] + q.q22 * ds[2] + q.q24 * ds[4] + q.q26 * dtf);
       g[3] = pi_next[3] - (q.d * ds[3] + q.q36 * dtf);
       g[4] = pi_next[4] - (q.q04 * ds[0] + q.q24 * ds[2] + q.q44 * ds[4] + q.q46 * dtf + q.q4);
-      g[5] = pi_next[5] - (q.d * ds[5] + q.q56 * dtf);
+      g[5] = P.coup5 * pi_next[5] - (q.d * ds[5] + q.q56 * dtf);
       g[6] = 0.0;
       if (k == N) {
         TermQP tq;
@@ -590,7 +600,7 @@ LM_NOINLINE void eval_pass(const Params& P, const Mesh& M, const Options& O, con
     c[2] = z[2] - zp[2] - al * z[3];
     c[3] = z[3] - zp[3] - al * f.ax;
     c[4] = z[4] - zp[4] - al * z[5];
-    c[5] = z[5] - zp[5] - J.beta * u;
+    c[5] = z[5] - P.coup5 * zp[5] - J.beta * u;
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
       const double ac = fabs(c[i]);
@@ -616,7 +626,8 @@ LM_NOINLINE void eval_pass(const Params& P, const Mesh& M, const Options& O, con
       res[3] += -t.zs2 * 2.0 * z[3] + t.nu3 * z[2];
     } else {
 #pragma unroll
-      for (int i = 0; i < 6; ++i) res[i] -= lam_next[i];
+      for (int i = 0; i < 5; ++i) res[i] -= lam_next[i];
+      res[5] -= P.coup5 * lam_next[5];
     }
 #pragma unroll
     for (int i = 0; i < 6; ++i) dual = dmax(dual, fabs(res[i]));
@@ -731,7 +742,7 @@ LM_NOINLINE bool riccati_backward(const Params& P, const Mesh& M, const Options&
       c[2] = zn[2] - zm[2] - al * zn[3];
       c[3] = zn[3] - zm[3] - al * f.ax;
       c[4] = zn[4] - zm[4] - al * zn[5];
-      c[5] = zn[5] - zm[5] - J.beta * u;
+      c[5] = zn[5] - P.coup5 * zm[5] - J.beta * u;
     } else {
 #pragma unroll
       for (int i = 0; i < 6; ++i) c[i] = 0.0;
@@ -802,6 +813,13 @@ LM_NOINLINE bool riccati_backward(const Params& P, const Mesh& M, const Options&
     rx[5] = pv[5] - (Bm[0][1] * c[0] + Bm[1][1] * c[1] + Bm[2][1] * c[2] + Bm[3][1] * c[3] + C01 * c[4] + C11 * c[5]);
     rx[6] = pv[6] - (Bm[0][2] * c[0] + Bm[1][2] * c[1] + Bm[2][2] * c[2] + Bm[3][2] * c[3] + C02 * c[4] + C12 * c[5]);
     const double ru = q.r + beta * rx[5];
+    // d defect_k / d s_{k-1} = -D with D = diag(1,1,1,1,1,coup5,1): the previous node sees the
+    // angledot column scaled by coup5 (0 in the circular model)
+    const double cp = P.coup5;
+    Rux[5] *= cp; rx[5] *= cp;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) Bm[i][1] *= cp;
+    C01 *= cp; C11 *= cp * cp; C12 *= cp;
     if (!(Ruu > 0.0) || !(Ruu < 1e300)) ok = false;
     const double Rinv = lm_rcp(Ruu);
     double RuxS[7];
@@ -887,7 +905,7 @@ LM_NOINLINE void riccati_forward(const Params& P, const Mesh& M, const Options& 
     xi[2] = ds[2] - cw * (zn[2] - zm[2] - al * zn[3]);
     xi[3] = ds[3] - cw * (zn[3] - zm[3] - al * f.ax);
     xi[4] = ds[4] - cw * (zn[4] - zm[4] - al * zn[5]);
-    xi[5] = ds[5] - cw * (zn[5] - zm[5] - J.beta * u) + J.beta * du;
+    xi[5] = P.coup5 * ds[5] - cw * (zn[5] - P.coup5 * zm[5] - J.beta * u) + J.beta * du;
     xi[6] = dtf;
     solveE(J, xi);
 #pragma unroll

@@ -50,6 +50,11 @@ struct Params {
   double tf_ub;   // min(1, 1/(mflow*T)): tf<=1 (LO:39) and mass<=1 (LO:83) at the last node
   double fuel;    // fuel_mass (for final-mass output)
   double Sinv;    // 1 / S
+  // Model switch.  coup5 = 1: Launch_Optimiser.py (angledot_k - angledot_{k-1} = beta*u_k, LO:121).
+  // coup5 = 0: the circular "IB-document" model (PDF p.27 src 69-73), where the pitch angle itself
+  // is the MV: the angledot row loses its link to the previous node (angledot_k = beta*u_k with u
+  // unbounded), which makes angle_k = angle_{k-1} + alpha*angledot_k a free variable per step.
+  double coup5;
 };
 
 // ---------------------------------------------------------------------------------------

@@ -63,7 +63,7 @@ class AscentParams:
     mass_scalar: Optional[float] = None  # LO:108 = fuel_mass; PDF p.27 src 67 = 2576
     angle_ub: float = math.pi / 3   # LO:94
     u_bound: float = 1.0            # LO:96
-    dcost: float = 0.0              # LO:99 is 1e-5; see README in oracle/ for why 0 here
+    dcost: float = 0.0              # LO:99 is 1e-5; 0 = without the move-suppression term
 
     @staticmethod
     def circular() -> "AscentParams":
@@ -268,7 +268,8 @@ class AscentNLP:
     """
 
     def __init__(self, params: AscentParams, nt: int = 200, nodes: int = 2,
-                 time: Optional[Sequence[float]] = None, obj_scale: float = 1.0):
+                 time: Optional[Sequence[float]] = None, obj_scale: float = 1.0,
+                 objective_nodes: Optional[int] = None):
         self.p = params
         self.nm = _build_node_model(params.model)
         self.time = np.linspace(0.0, 1.0, nt) if time is None else np.asarray(time, float)  # LO:20-21
@@ -287,13 +288,24 @@ class AscentNLP:
         self.i_s1 = self.i_tf + 1
         self.i_s2 = self.i_tf + 2
         self.n = self.i_tf + 3
+        # DCOST (LO:99): l1 penalty dcost*|MV_k - MV_{k-1}| per step, written with non-negative
+        # slack pairs  MV_k - MV_{k-1} = p_k - n_k  (SURVEY B.3).  APMonitor sums the objective over
+        # the horizon (`objective_nodes` copies of tf, default nt-1), so relative to obj_scale*tf
+        # the weight per unit of move is obj_scale*dcost/objective_nodes.
+        self.dcost = float(params.dcost) if nodes == 2 else 0.0
+        self.objective_nodes = (self.nt - 1) if objective_nodes is None else objective_nodes
+        self.w_dcost = obj_scale * self.dcost / self.objective_nodes
+        self.i_p = self.n
+        self.i_n = self.n + (self.K if self.dcost > 0 else 0)
+        if self.dcost > 0:
+            self.n += 2 * self.K
         self.is_mv = np.zeros(self.nv, bool)
         self.mv_name = "angledoubledot" if params.model == "elliptical" else "angle"
         self.i_mv = nm.names.index(self.mv_name)
         # constraints: per point ndiff + nalg; MV hold rows for NODES>2; 3 terminal
         self.rows_per_pt = nm.ndiff + nm.nalg
         self.m_hold = self.nsteps * (self.npts - 1)
-        self.m = self.K * self.rows_per_pt + self.m_hold + 3
+        self.m = self.K * self.rows_per_pt + self.m_hold + 3 + (self.K if self.dcost > 0 else 0)
         # bounds
         lb = np.tile(nm.lb, self.K)
         ub = np.tile(nm.ub, self.K)
@@ -305,6 +317,9 @@ class AscentNLP:
             ub[self.i_mv::self.nv] = params.u_bound
         self.lb = np.concatenate([lb, [0.0, 0.0, 0.0]])                    # tf LO:39; slacks >= 0
         self.ub = np.concatenate([ub, [1.0, np.inf, np.inf]])
+        if self.dcost > 0:
+            self.lb = np.concatenate([self.lb, np.zeros(2 * self.K)])
+            self.ub = np.concatenate([self.ub, np.full(2 * self.K, np.inf)])
         # step widths per collocation point
         self.h = np.repeat(np.diff(self.time), self.npts)                  # [K]
         self._build_structure()
@@ -335,11 +350,16 @@ class AscentNLP:
 
     # -- objective ----------------------------------------------------------------------
     def f(self, x):
-        return self.obj_scale * x[self.i_tf]                                # LO:176
+        f = self.obj_scale * x[self.i_tf]                                   # LO:176
+        if self.dcost > 0:
+            f += self.w_dcost * x[self.i_p:].sum()                          # LO:99
+        return f
 
     def grad(self, x):
         g = np.zeros(self.n)
         g[self.i_tf] = self.obj_scale
+        if self.dcost > 0:
+            g[self.i_p:] = self.w_dcost
         return g
 
     # -- constraints --------------------------------------------------------------------
@@ -375,6 +395,10 @@ class AscentNLP:
         t2 = xd ** 2 + yd ** 2 - (p.v_target / S) ** 2 - s2                # LO:169
         t3 = (y + R0 / S) * yd + xx * xd                                   # LO:173 divided by S^2
         out.append(np.array([t1, t2, t3]))
+        if self.dcost > 0:
+            mv = v[self.i_mv]
+            dmv = np.diff(np.concatenate([[0.0], mv]))                     # MV(0) = 0 (pinned)
+            out.append(dmv - x[self.i_p:self.i_p + K] + x[self.i_n:self.i_n + K])
         return np.concatenate(out)
 
     def jac(self, x) -> sp.csr_matrix:
@@ -437,6 +461,11 @@ class AscentNLP:
             rows.append(np.array([r_]))
             cols.append(np.array([c_]))
             vals.append(np.array([v_]))
+        if self.dcost > 0:
+            rd = r0 + 3 + k
+            rows += [rd, rd[1:], rd, rd]
+            cols += [k * nv + self.i_mv, k[:-1] * nv + self.i_mv, self.i_p + k, self.i_n + k]
+            vals += [np.ones(K), -np.ones(K - 1), -np.ones(K), np.ones(K)]
         R = np.concatenate([np.asarray(a).ravel() for a in rows])
         C = np.concatenate([np.asarray(a).ravel() for a in cols])
         Vv = np.concatenate([np.asarray(a, float).ravel() for a in vals])
@@ -553,6 +582,11 @@ class AscentNLP:
         x[self.i_tf] = tf0
         x[self.i_s1] = 1e-2
         x[self.i_s2] = 1e-2
+        if self.dcost > 0:
+            mv = v[self.i_mv]
+            dmv = np.diff(np.concatenate([[0.0], mv]))
+            x[self.i_p:self.i_p + K] = np.maximum(dmv, 0.0) + 1e-2
+            x[self.i_n:self.i_n + K] = np.maximum(-dmv, 0.0) + 1e-2
         return x
 
 

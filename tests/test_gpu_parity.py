@@ -202,3 +202,28 @@ def test_branch_free_math_matches_cuda_library(lm):
     assert e["rcp"] < 5e-16 and e["rsqrt"] < 5e-16, e
     assert e["log"] < 1e-15, e
     assert e["sin"] < 5e-16 and e["cos"] < 5e-16, e
+
+
+def test_circular_model_matches_golden_and_pdf(lm, golden_dir):
+    """Config 2: the 'original IB-document' model (reference PDF p.26-28): pitch angle is the MV,
+    circular target orbit at 53 108.4 m, mass scale 2576.  Published output (PDF p.30):
+    tf = 0.92616537474 (435.2977 s)."""
+    g = np.load(os.path.join(golden_dir, "circular_nominal_nt200.npz"))
+    names = list(g["names"])
+    sol = lm.optimise(lm.AscentParams.circular(), lm.Mesh(nt=200))
+    assert sol.status == 0
+    assert abs(sol.tf - float(g["tf"])) / float(g["tf"]) < 1e-9
+    assert abs(sol.tf - 0.92616537474) / 0.92616537474 < 1e-5          # the reference's own run
+    assert set(sol.states) == {"y", "ydot", "ydoubledot", "x", "xdot", "xdoubledot", "mass"}
+    for n in sol.states:
+        ref = g["traj"][names.index(n)]
+        assert np.abs(sol.states[n].numpy() - ref).max() / np.abs(ref).max() < STATE_RTOL, n
+    ref = g["traj"][names.index("angle")]
+    assert np.abs(sol.control.numpy() - ref).max() / np.abs(ref).max() < STATE_RTOL
+    # published final state (PDF p.30; x-quantities sign-flipped there), SI units via pos_factor
+    S = 53108.4
+    assert abs(float(sol.states["y"][-1]) * S - 28716.160349635127) / 28716.16 < 1e-4
+    assert abs(-float(sol.states["x"][-1]) * S - 294598.36483519967) / 294598.36 < 1e-4
+    assert abs(float(sol.states["ydot"][-1]) * S - (-272.0993356840796)) / 272.1 < 1e-4
+    # final model mass: M0 - fuel_mass*mass = 4821 - 5.053*tf_s
+    assert abs(sol.final_mass - (4821.0 - 5.053 * sol.tf_seconds)) < 1e-9

@@ -24,3 +24,17 @@ for b in range(8):
     print(b, "status", st, "iters", it.value, "kkt %.1e" % kkt.value, "tf rel %.1e" % (abs(tf.value - g["tf"][b]) / g["tf"][b]),
           "angledot %.1e control %.1e others %.1e" % (err[7], err[9], np.delete(err, [7, 9]).max()))
 print("worst per row:", " ".join("%.1e" % e for e in worst))
+
+# circular model (config 2): same sweeps, coup5 = 0
+os.environ["CIRCULAR"] = "1"
+g = np.load(os.path.join(ROOT, "tests", "golden", "circular_nominal_nt200.npz"))
+raw = np.array([6.674e-11, 7.346e22, 1738100.0, 15346.0, 4821.0, 5.053, 2376.0, 5e-4, 53108.4, 53108.4, 470.0, 2576.0,
+                np.pi / 3, 1.0])
+traj = np.empty((10, nt)); tf = C.c_double(); it = C.c_int(); kkt = C.c_double()
+st = L.hostsim_solve(raw.ctypes.data_as(C.c_void_p), nt, None, C.c_double(tol), C.c_double(10.0), C.c_double(mmf),
+                     traj.ctypes.data_as(C.c_void_p), C.byref(tf), C.byref(it), C.byref(kkt))
+names = list(g["names"])
+rows = {"y": 0, "ydot": 1, "ydoubledot": 2, "x": 3, "xdot": 4, "xdoubledot": 5, "angle": 6, "mass": 8}
+err = {n: np.abs(traj[rows[n]] - g["traj"][names.index(n)]).max() / np.abs(g["traj"][names.index(n)]).max() for n in rows}
+print("circular: status", st, "iters", it.value, "kkt %.1e" % kkt.value, "tf_s %.8f (golden %.8f)" % (tf.value * 470, float(g["tf"]) * 470))
+print("circular rel err:", {k: "%.1e" % v for k, v in err.items()})

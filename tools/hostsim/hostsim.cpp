@@ -27,7 +27,7 @@ static Params make_params(double Ft, double M0, double Mdot, double addm, double
   P.vt2 = (vt / P.S) * (vt / P.S);
   P.rt = (R0 + P.S) / P.S; P.R0S = R0 / P.S;
   P.tf_ub = std::fmin(1.0, 1.0 / (P.mflow * T));
-  P.fuel = fuel; P.Sinv = 1.0 / P.S;
+  P.fuel = fuel; P.Sinv = 1.0 / P.S; P.coup5 = 1.0;
   return P;
 }
 
@@ -103,7 +103,8 @@ extern "C" int hostsim_solve(const double* raw14, int nt, const double* time, do
   P.asc = r[7] / 3.0; P.T = r[10]; P.a_ub = r[12]; P.u_ub = r[13];
   const double vt = std::sqrt(P.GM / (P.R0 + 0.5 * (r[8] + r[9])));
   P.vt2 = (vt / P.S) * (vt / P.S); P.rt = (P.R0 + P.S) / P.S; P.R0S = P.R0 / P.S;
-  P.tf_ub = std::fmin(1.0, 1.0 / (P.mflow * P.T)); P.fuel = r[6]; P.Sinv = 1.0 / P.S;
+  P.tf_ub = std::fmin(1.0, 1.0 / (P.mflow * P.T)); P.fuel = r[6]; P.Sinv = 1.0 / P.S; P.coup5 = 1.0;
+  if (getenv("CIRCULAR")) { P.coup5 = 0.0; P.asc = 1.0; P.u_ub = 1e20; }
   std::vector<double> ws((size_t)N_FIELDS * LANES * (N + 1), 0.0);
   Ws W{ws.data(), (long)N_FIELDS * LANES};
   SolveOut out;
