@@ -74,6 +74,13 @@ class ClockSampler:
             self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
             self.nv = pynvml
             self.mode = "nvml"
+            # prime every query once (the first NVML call of each kind is slow)
+            pynvml.nvmlDeviceGetClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            try:
+                pynvml.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            except Exception:
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
             self.thread = threading.Thread(target=self._poll, daemon=True)
             self.thread.start()
             return
@@ -102,7 +109,7 @@ class ClockSampler:
                 self.samples.append((float(sm), float(mx), int(rs)))
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(float(os.environ.get("LMATO_CLOCK_PERIOD_S", "0.2")))
 
     def _read(self):
         for line in self.proc.stdout:
@@ -234,11 +241,15 @@ def main():
 
     fp64_peak = solver.measure_fp64_peak()
     for _ in range(args.warmup):
+        # identical to a timed step, including the host-side bookkeeping: the first use of each torch
+        # reduction kernel costs ~0.3 s of lazy module loading that must not land in the timed region
         raw = step_device()
+        solver.last_kernel_ms()
+        int((raw["status"] == 0).sum()); int(raw["iterations"].sum())
     torch.cuda.synchronize()
     launches0 = solver.kernel_launches()
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and os.environ.get("LMATO_NO_CLOCKS") != "1":
         sampler.start()
     if world > 1:
         dist.barrier()
