@@ -32,7 +32,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 class LmatoOptions(C.Structure):
     _fields_ = [("tol", C.c_double), ("mu_init", C.c_double), ("obj_scale", C.c_double),
                 ("tf_guess", C.c_double), ("delta_c", C.c_double), ("mu_min_factor", C.c_double),
-                ("max_iter", C.c_int32), ("max_ls", C.c_int32), ("n_polish", C.c_int32)]
+                ("max_iter", C.c_int32), ("max_ls", C.c_int32), ("n_polish", C.c_int32),
+                ("warm_start", C.c_int32), ("mu_ref", C.c_double)]
 
 
 class LmatoError(RuntimeError):

@@ -133,7 +133,9 @@ class SolverOptions:
     delta_c: float = 1e-8
     max_ls: int = 40
     mu_min_factor: float = 1e-3    # barrier floor = mu_min_factor * tol
-    n_polish: int = 2              # Newton iterations after tol is first met
+    n_polish: int = 4              # Newton iterations after tol is first met
+    warm_start: bool = True        # batches >= 256: start from the batch-mean problem's central path
+    mu_ref: float = 1e-3           # barrier parameter at which that reference solve stops
 
 
 @dataclasses.dataclass
@@ -198,7 +200,8 @@ class AscentSolver:
     def set_options(self, o: SolverOptions) -> None:
         co = _cabi.LmatoOptions(tol=o.tol, mu_init=o.mu_init, obj_scale=o.obj_scale, tf_guess=o.tf_guess,
                                 delta_c=o.delta_c, mu_min_factor=o.mu_min_factor, max_iter=int(o.max_iter),
-                                max_ls=int(o.max_ls), n_polish=int(o.n_polish))
+                                max_ls=int(o.max_ls), n_polish=int(o.n_polish),
+                                warm_start=int(bool(o.warm_start)), mu_ref=o.mu_ref)
         _cabi.check(_cabi.lib().lmato_set_options(self._h, C.byref(co)), "lmato_set_options")
         self.options = o
 

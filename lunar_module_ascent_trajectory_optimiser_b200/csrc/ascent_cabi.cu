@@ -62,8 +62,25 @@ struct KArgs {
   const double* tau;
   int* counter;
   int model;             // lmato_model_t
+  double* ref;           // reference column (warm start), or null
+  int ref_mode;          // 0 cold start; 1 solve and store the reference; 2 start from the reference
   Options O;
 };
+
+// Mean of every parameter row over the batch: the reference problem of the warm start.
+__global__ void __launch_bounds__(256) mean_params_kernel(const double* __restrict__ p, long B, double* out) {
+  __shared__ double red[256];
+  const int row = blockIdx.x;
+  double acc = 0.0;
+  for (long i = threadIdx.x; i < B; i += blockDim.x) acc += p[row * B + i];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[row] = red[0] / (double)B;
+}
 
 __device__ __forceinline__ Params derive_params(const double* __restrict__ p, long B, long b, int model) {
   // LO:50-75, 107-109
@@ -147,8 +164,15 @@ __global__ void __launch_bounds__(kBlock, kBlocksPerSM) ascent_ipm_kernel(KArgs 
         b = (long)chunk * 32 + lane;
         if (b < a.B) {
           P = derive_params(a.params, a.B, b, a.model);
-          init_guess(P, M, O, W, S.cur);
           ipm_begin(O, S);
+          double mu0 = 0.0;
+          if (a.ref_mode == 2 && init_from_ref(P, M, W, a.ref, S.cur, &mu0)) {
+            S.warm = true;
+            S.ctl.mu = mu0;
+            S.ctl.tau = dmax(O.tau_min, 1.0 - mu0);
+          } else {
+            init_guess(P, M, O, W, S.cur);
+          }
           active = true;
         }
       }
@@ -160,9 +184,19 @@ __global__ void __launch_bounds__(kBlock, kBlocksPerSM) ascent_ipm_kernel(KArgs 
     //  a few iterations while the warps stay close enough to share the instruction cache)
     if ((round++ % LMATO_SYNC_PERIOD) == 0 && !__syncthreads_or((active || !exhausted) ? 1 : 0)) break;
     if (active && ipm_iterate(P, M, O, W, S)) {
+      if (S.warm && S.ctl.status != ST_CONVERGED) {
+        // a warm start that did not work out: this lane restarts the same problem from the cold start
+        ipm_begin(O, S);
+        init_guess(P, M, O, W, S.cur);
+        continue;
+      }
       active = false;
       SolveOut out;
       ipm_result(S, out);
+      if (a.ref_mode == 1) {
+        ref_store(P, M, W, out.cur, S.cur, S.ctl.mu, out.status == ST_CONVERGED, a.ref);
+        continue;
+      }
       a.tf[b] = out.tf;
       a.fmass[b] = P.M0 - P.fuel * (P.mflow * P.T * out.tf);   // mass(nt-1) = mflow*T*tf (LO:123)
       a.status[b] = out.status;
@@ -245,6 +279,8 @@ struct lmato_handle {
   // staging for the host-buffer entry point
   double* d_params = nullptr; size_t params_bytes = 0;
   double* d_out = nullptr; size_t out_bytes = 0;
+  double* d_ref = nullptr;        // reference column of the warm start: [REF_ROWS][nt]
+  double* d_refparams = nullptr;  // [NPARAM] batch-mean parameters + scratch outputs of the reference solve
   lmato_options opt;
   int64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -265,7 +301,9 @@ void lmato_default_options(lmato_options* o) {
   o->tf_guess = 0.9;
   o->delta_c = 1e-8;
   o->mu_min_factor = 1e-3;
-  o->n_polish = 2;
+  o->n_polish = 4;
+  o->warm_start = 1;
+  o->mu_ref = 1e-3;
   o->max_iter = 20000;   // LO:28
   o->max_ls = 40;
 }
@@ -313,6 +351,8 @@ lmato_status_t lmato_create(lmato_handle** out, int32_t device, int32_t nt, cons
   CUDA_TRY(cudaMemcpy(H->d_h, h.data(), sizeof(double) * nt, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(H->d_tau, tau.data(), sizeof(double) * nt, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMalloc(&H->d_counter, sizeof(int)));
+  CUDA_TRY(cudaMalloc(&H->d_ref, sizeof(double) * REF_ROWS * nt));
+  CUDA_TRY(cudaMalloc(&H->d_refparams, sizeof(double) * (LMATO_NPARAM + 8)));
   CUDA_TRY(cudaEventCreate(&H->ev0));
   CUDA_TRY(cudaEventCreate(&H->ev1));
   *out = H;
@@ -323,7 +363,7 @@ lmato_status_t lmato_destroy(lmato_handle* h) {
   if (!h) return LMATO_OK;
   cudaSetDevice(h->device);
   cudaFree(h->d_h); cudaFree(h->d_tau); cudaFree(h->d_ws); cudaFree(h->d_counter);
-  cudaFree(h->d_params); cudaFree(h->d_out);
+  cudaFree(h->d_params); cudaFree(h->d_out); cudaFree(h->d_ref); cudaFree(h->d_refparams);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   delete h;
@@ -334,7 +374,8 @@ lmato_status_t lmato_set_options(lmato_handle* h, const lmato_options* o) {
   if (!h || !o) { set_err("lmato_set_options: NULL argument"); return LMATO_ERR_INVALID; }
   if (!(o->tol > 0) || !(o->mu_init > 0) || !(o->obj_scale > 0) || !(o->delta_c > 0) ||
       !(o->tf_guess > 0 && o->tf_guess < 1) || o->max_iter < 0 || o->max_ls < 1 ||
-      !(o->mu_min_factor > 0 && o->mu_min_factor <= 1) || o->n_polish < 0) {
+      !(o->mu_min_factor > 0 && o->mu_min_factor <= 1) || o->n_polish < 0 ||
+      (o->warm_start != 0 && o->warm_start != 1) || !(o->mu_ref > 0 && o->mu_ref <= o->mu_init)) {
     set_err("lmato_set_options: option out of range");
     return LMATO_ERR_INVALID;
   }
@@ -394,8 +435,25 @@ lmato_status_t lmato_solve_batch(lmato_handle* h, const double* params, int64_t 
   a.O.delta_c = h->opt.delta_c; a.O.tf_guess = h->opt.tf_guess;
   a.O.max_iter = h->opt.max_iter; a.O.max_ls = h->opt.max_ls;
   a.O.mu_min_factor = h->opt.mu_min_factor; a.O.n_polish = h->opt.n_polish;
+  a.ref = nullptr; a.ref_mode = 0;
   const int grid = (int)(slots / kBlock);
   CUDA_TRY(cudaEventRecord(h->ev0, st));
+  if (h->opt.warm_start && B >= 256) {
+    // reference problem = batch mean, solved down to mu_ref only (one thread, ~8 iterations)
+    mean_params_kernel<<<LMATO_NPARAM, 256, 0, st>>>(params, B, h->d_refparams);
+    CUDA_TRY(cudaGetLastError());
+    KArgs r = a;
+    double* scratch = h->d_refparams + LMATO_NPARAM;
+    r.params = h->d_refparams; r.B = 1; r.traj = nullptr; r.tf = scratch; r.fmass = scratch + 1;
+    r.status = (int*)(scratch + 2); r.iters = (int*)(scratch + 3); r.kkt = scratch + 4;
+    r.ref = h->d_ref; r.ref_mode = 1;
+    r.O.tol = 10.0 * h->opt.mu_ref; r.O.mu_min_factor = 0.1; r.O.n_polish = 0;
+    ascent_ipm_kernel<<<1, kBlock, 0, st>>>(r);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemsetAsync(h->d_counter, 0, sizeof(int), st));
+    a.ref = h->d_ref; a.ref_mode = 2;
+    h->launches += 2;
+  }
   ascent_ipm_kernel<<<grid, kBlock, 0, st>>>(a);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaEventRecord(h->ev1, st));

@@ -431,6 +431,63 @@ LM_HD void stage_hessian(const Params& P, const Accel1& f, const StageJac& J, do
 }
 
 // ---------------------------------------------------------------------------------------
+// Warm start: every problem of a batch may start from one reference central-path point (the
+// batch-mean problem solved down to mu_ref ~ 1e-3) instead of the generic roll-out.  That skips
+// the globalisation phase (about 7 of 27 iterations); at smaller mu_ref the iterate sits too close
+// to the reference's active bounds and the method jams, so 1e-3 it is.  The reference column is
+// REF_ROWS x (N+1) doubles: the 17 iterate rows followed by one row of scalars (node 0..).
+// ---------------------------------------------------------------------------------------
+enum : int { REF_ROWS = N_ITER + 1, REF_OK = 0, REF_MU = 1, REF_S = 2, REF_TF = 3, REF_ZLT = 4, REF_ZUT = 5,
+             REF_SG1 = 6, REF_SG2 = 7, REF_ZS1 = 8, REF_ZS2 = 9, REF_NU3 = 10, REF_NSCAL = 11 };
+
+// ref[(row * (N+1)) + k]
+LM_NOINLINE void ref_store(const Params& P, const Mesh& M, const Ws& W, int src, const Scal& c, double mu,
+                           bool ok, double* ref) {
+  const int N1 = M.N + 1;
+  for (int k = 1; k <= M.N; ++k) {
+    const double* sp = W.stage(k);
+#pragma unroll
+    for (int f = 0; f < N_ITER; ++f) ref[f * N1 + k] = WS_AT(sp, src * N_ITER + f);
+  }
+  double* sc = ref + N_ITER * N1;
+  sc[REF_OK] = ok ? 1.0 : 0.0; sc[REF_MU] = mu; sc[REF_S] = P.S; sc[REF_TF] = c.tf;
+  sc[REF_ZLT] = c.zLt; sc[REF_ZUT] = c.zUt; sc[REF_SG1] = c.sg1; sc[REF_SG2] = c.sg2;
+  sc[REF_ZS1] = c.zs1; sc[REF_ZS2] = c.zs2; sc[REF_NU3] = c.nu3;
+}
+
+// Start point of one problem from the reference column (lengths are stored divided by the
+// reference's distance scale S_ref = r_periapsis, LO:107, so they are rescaled to this problem's).
+LM_NOINLINE bool init_from_ref(const Params& P, const Mesh& M, const Ws& W, const double* ref, Scal& s,
+                               double* mu_out) {
+  const int N1 = M.N + 1;
+  const double* sc = ref + N_ITER * N1;
+  if (!(sc[REF_OK] > 0.5)) return false;
+  const double r = sc[REF_S] * P.Sinv, ri = P.S / sc[REF_S];
+  {
+    double* s0 = W.stage(0);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { WS_AT(s0, F_Z + i) = 0.0; WS_AT(s0, N_ITER + F_Z + i) = 0.0; WS_AT(s0, F_DS + i) = 0.0; }
+  }
+  for (int k = 1; k <= M.N; ++k) {
+    double* sp = W.stage(k);
+#pragma unroll
+    for (int f = 0; f < N_ITER; ++f) {
+      double v = ref[f * N1 + k];
+      if (f < 4) v *= r;                               // y, vy, x, vx
+      else if (f >= F_LAM && f < F_LAM + 4) v *= ri;   // multipliers of those rows
+      WS_AT(sp, f) = v;
+    }
+#pragma unroll
+    for (int i = 0; i < N_STEP; ++i) WS_AT(sp, R_STEP + i) = 0.0;
+  }
+  s.tf = dmin(sc[REF_TF], 0.99 * P.tf_ub);
+  s.zLt = sc[REF_ZLT]; s.zUt = sc[REF_ZUT];
+  s.sg1 = sc[REF_SG1]; s.sg2 = sc[REF_SG2]; s.zs1 = sc[REF_ZS1]; s.zs2 = sc[REF_ZS2]; s.nu3 = sc[REF_NU3];
+  *mu_out = sc[REF_MU];
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------
 // evaluation pass: trial point  x + alpha*dx  (alpha=0: the current point), swept from the
 // last node to the first.  Writes the trial iterate into buffer `dst` and returns its merit /
 // KKT-error ingredients.
@@ -1002,6 +1059,7 @@ LM_HD void filter_add(Ctl& c, double th, double ph) {
 enum : int { PH_LSQ = 0, PH_NEWTON = 1 };
 
 struct IpmState {
+  bool warm;        // start point carries its own multipliers (skip the least-squares estimate)
   Scal cur;
   Ctl ctl;
   TermStep ts;
@@ -1025,6 +1083,7 @@ LM_HD void ipm_begin(const Options& O, IpmState& S) {
   S.phase = PH_LSQ;
   S.polish_left = -1;
   S.polishing = false;
+  S.warm = false;
 }
 
 LM_HD bool ipm_iterate(const Params& P, const Mesh& M, const Options& O, const Ws& W, IpmState& S) {
@@ -1066,6 +1125,7 @@ LM_HD bool ipm_iterate(const Params& P, const Mesh& M, const Options& O, const W
   double dw = 0.0, dtf = 0.0;
   bool fact_ok = false;
   for (int attempt = 0; attempt < 40; ++attempt) {
+    if (ls && S.warm) break;
     if (riccati_backward(P, M, O, W, S.src, cur, ctl.mu, dw, ls, &dtf)) { fact_ok = true; break; }
     if (ls) break;
     if (dw == 0.0) dw = (ctl.dw_last == 0.0) ? 1e-4 : dmax(1e-20, ctl.dw_last / 3.0);

@@ -227,3 +227,25 @@ def test_circular_model_matches_golden_and_pdf(lm, golden_dir):
     assert abs(float(sol.states["ydot"][-1]) * S - (-272.0993356840796)) / 272.1 < 1e-4
     # final model mass: M0 - fuel_mass*mass = 4821 - 5.053*tf_s
     assert abs(sol.final_mass - (4821.0 - 5.053 * sol.tf_seconds)) < 1e-9
+
+
+def test_warm_start_is_reproducible_and_faster(lm):
+    """The batch warm start (reference central-path point of the batch-mean problem) must not change
+    the answers: two solves of the same 4096 problems from different start points agree on tf to
+    rounding and on every state to well inside north_star's 1e-4, and the warm one needs fewer
+    iterations."""
+    B = 4096
+    rows = lm.dispersed_params(B, seed=11).rows(B).cuda()
+    res = {}
+    for warm in (False, True):
+        solver = lm.AscentSolver(lm.Mesh(), lm.SolverOptions(warm_start=warm), device=0)
+        raw = solver.solve_rows(rows)
+        torch.cuda.synchronize()
+        res[warm] = {k: v.clone() for k, v in raw.items()}
+        assert int((raw["status"] != 0).sum()) == 0
+    assert float((res[True]["tf"] - res[False]["tf"]).abs().max()) < 1e-11
+    a, b = res[True]["traj"], res[False]["traj"]
+    rel = ((a - b).abs() / b.abs().amax(dim=1, keepdim=True)).amax(dim=(1, 2))
+    assert float(rel[:9].max()) < STATE_RTOL, rel
+    assert float(rel[9]) < 5e-3, rel           # the MV on the singular arc, see CONTROL_RTOL above
+    assert float(res[True]["iterations"].double().mean()) < float(res[False]["iterations"].double().mean()) - 4

@@ -42,7 +42,7 @@ int main(int argc, char** argv) {
   Mesh M{N, h.data(), tau.data()};
   Options O;
   O.tol = 1e-10; O.mu_init = 0.1; O.obj_scale = 10.0; O.kappa_eps = 10.0; O.kappa_mu = 0.2; O.theta_mu = 1.5;
-  O.tau_min = 0.99; O.delta_c = 1e-8; O.tf_guess = 0.9; O.max_iter = 500; O.max_ls = 40; O.mu_min_factor = 1e-3; O.n_polish = 2;
+  O.tau_min = 0.99; O.delta_c = 1e-8; O.tf_guess = 0.9; O.max_iter = 500; O.max_ls = 40; O.mu_min_factor = 1e-3; O.n_polish = 4;
   if (getenv("MMF")) O.mu_min_factor = atof(getenv("MMF"));
   if (getenv("NPOL")) O.n_polish = atoi(getenv("NPOL"));
   if (getenv("OBJ")) O.obj_scale = atof(getenv("OBJ"));
@@ -96,7 +96,7 @@ extern "C" int hostsim_solve(const double* raw14, int nt, const double* time, do
   Mesh M{N, h.data(), tau.data()};
   Options O;
   O.tol = tol; O.mu_init = 0.1; O.obj_scale = obj_scale; O.kappa_eps = 10.0; O.kappa_mu = 0.2; O.theta_mu = 1.5;
-  O.tau_min = 0.99; O.delta_c = 1e-8; O.tf_guess = 0.9; O.max_iter = 500; O.max_ls = 40; O.mu_min_factor = mu_min_factor; O.n_polish = getenv("NPOL") ? atoi(getenv("NPOL")) : 2;
+  O.tau_min = 0.99; O.delta_c = 1e-8; O.tf_guess = 0.9; O.max_iter = 500; O.max_ls = 40; O.mu_min_factor = mu_min_factor; O.n_polish = getenv("NPOL") ? atoi(getenv("NPOL")) : 4;
   Params P;
   const double* r = raw14;
   P.GM = r[0] * r[1]; P.R0 = r[2]; P.Ft = r[3]; P.M0 = r[4]; P.S = r[8]; P.ms = r[11]; P.mflow = r[5] / r[6];
