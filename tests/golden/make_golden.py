@@ -69,5 +69,20 @@ def main():
              final_mass=np.array(fms), traj=np.stack(trajs), names=np.array(VAR_ROWS))
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--dense" not in sys.argv:
     main()
+
+
+def dense_mesh():
+    """Dense-mesh case (the direction of config 5): nt = 801, nominal parameters; every 10th node is
+    kept.  (The general sparse LU of the oracle fills in badly because of the dense tf column; nt =
+    2001 does not finish in reasonable time here, the structured device solver has no such issue.)"""
+    s = solve(AscentParams(), nt=801, tol=2e-7)   # the general sparse LU stalls near 5e-8 on this mesh
+    keep = np.arange(0, 801, 10)
+    np.savez(os.path.join(HERE, "elliptical_nominal_nt801_every10.npz"), tf=s["tf"], final_mass=s["final_mass"],
+             traj=s["traj"][:, keep], names=s["names"], nodes=keep, iters=s["iters"], kkt=s["kkt"])
+    print("dense mesh tf_s", s["tf"] * 470, "iters", s["iters"], "kkt", s["kkt"])
+
+
+if __name__ == "__main__" and "--dense" in sys.argv:
+    dense_mesh()

@@ -249,3 +249,37 @@ def test_warm_start_is_reproducible_and_faster(lm):
     assert float(rel[:9].max()) < STATE_RTOL, rel
     assert float(rel[9]) < 5e-3, rel           # the MV on the singular arc, see CONTROL_RTOL above
     assert float(res[True]["iterations"].double().mean()) < float(res[False]["iterations"].double().mean()) - 4
+
+
+def test_dense_mesh_matches_golden(lm, golden_dir):
+    """nt = 801 against the oracle.  The oracle's general sparse LU stalls at a scaled KKT error of
+    5e-8 on this mesh (fill-in from the dense tf column), so its own barrier bias is ~5e-7 in tf;
+    the comparison is held to north_star's tolerances, not tighter."""
+    g = np.load(os.path.join(golden_dir, "elliptical_nominal_nt801_every10.npz"))
+    names = list(g["names"])
+    sol = lm.optimise(lm.AscentParams(), lm.Mesh(nt=801))
+    assert sol.status == 0
+    assert abs(sol.tf - float(g["tf"])) / float(g["tf"]) < 2e-6
+    assert abs(sol.final_mass - float(g["final_mass"])) / float(g["final_mass"]) < MASS_RTOL
+    keep = g["nodes"]
+    for n in ("y", "ydot", "x", "xdot", "mass", "angle"):
+        ref = g["traj"][names.index(n)]
+        mine = sol.states[n].numpy()[keep]
+        assert np.abs(mine - ref).max() / np.abs(ref).max() < (STATE_RTOL if n != "angle" else 2e-3), n
+    # backward Euler approaches the continuous-time optimum (~435.1 s) from below as the mesh is refined
+    assert 434.5 < sol.tf_seconds < 435.2
+
+
+def test_config5_dense_mesh_batch_properties(lm):
+    """Config 5 (nt = 2001, all six parameters dispersed), a 64-problem slice: every problem converges
+    and satisfies the transcribed equations; the working set per problem no longer fits on chip."""
+    B, nt = 64, 2001
+    p = lm.dispersed_params(B, seed=11)
+    sol = lm.optimise_batch(p, lm.Mesh(nt=nt))
+    assert int((sol.status != 0).sum()) == 0, sol.status.tolist()
+    defect, radius, speed, ortho = _defects(lm, p, sol, nt)
+    assert float(defect.max()) < 1e-9
+    assert float(radius.min()) > -1e-8 and float(radius.max()) < 1e-6
+    assert float(speed.min()) > -1e-8 and float(speed.max()) < 1e-6
+    assert float(ortho.abs().max()) < 1e-7
+    assert abs(float(sol.tf_seconds[0]) - 435.1038) < 1e-3      # nominal on this mesh
