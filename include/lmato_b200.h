@@ -92,6 +92,10 @@ typedef struct {
                          mu_ref and start every problem from that central-path point; a problem that fails
                          from there is restarted from the generic cold start.  0: always cold start. */
   double mu_ref;     /* barrier parameter at which the reference solve stops; default 1e-3 */
+  double dcost;      /* LO:99 angledoubledot.DCOST: l1 move suppression dcost*sum|MV_k - MV_{k-1}|; default
+                        1e-5 (the reference's value); 0 switches the term off (7-state fast path) */
+  int32_t objective_nodes; /* APMonitor sums the objective over the horizon: minimise objective_nodes*tf +
+                        dcost*sum|dMV|; 0 (default) = nt-1.  Only the ratio dcost/objective_nodes matters. */
 } lmato_options;
 
 /* Fill `o` with the defaults above. */

@@ -33,7 +33,8 @@ class LmatoOptions(C.Structure):
     _fields_ = [("tol", C.c_double), ("mu_init", C.c_double), ("obj_scale", C.c_double),
                 ("tf_guess", C.c_double), ("delta_c", C.c_double), ("mu_min_factor", C.c_double),
                 ("max_iter", C.c_int32), ("max_ls", C.c_int32), ("n_polish", C.c_int32),
-                ("warm_start", C.c_int32), ("mu_ref", C.c_double)]
+                ("warm_start", C.c_int32), ("mu_ref", C.c_double), ("dcost", C.c_double),
+                ("objective_nodes", C.c_int32)]
 
 
 class LmatoError(RuntimeError):

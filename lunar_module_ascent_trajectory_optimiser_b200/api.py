@@ -60,7 +60,7 @@ class AscentParams:
     mass_scalar: Optional[Scalar] = None  # LO:108 (= fuel_mass); 2576 in the PDF original
     angle_ub: Scalar = math.pi / 3        # LO:94
     u_bound: Scalar = 1.0                 # LO:96
-    dcost: float = 1e-5                   # LO:99 (accepted; see DESIGN.md "DCOST")
+    dcost: float = 1e-5                   # LO:99 angledoubledot.DCOST (0 = off)
 
     @staticmethod
     def circular() -> "AscentParams":
@@ -136,6 +136,8 @@ class SolverOptions:
     n_polish: int = 4              # Newton iterations after tol is first met
     warm_start: bool = True        # batches >= 256: start from the batch-mean problem's central path
     mu_ref: float = 1e-3           # barrier parameter at which that reference solve stops
+    dcost: Optional[float] = None  # LO:99; None = take AscentParams.dcost (1e-5 in the reference)
+    objective_nodes: int = 0       # APMonitor sums the objective over the horizon; 0 = nt-1
 
 
 @dataclasses.dataclass
@@ -201,7 +203,9 @@ class AscentSolver:
         co = _cabi.LmatoOptions(tol=o.tol, mu_init=o.mu_init, obj_scale=o.obj_scale, tf_guess=o.tf_guess,
                                 delta_c=o.delta_c, mu_min_factor=o.mu_min_factor, max_iter=int(o.max_iter),
                                 max_ls=int(o.max_ls), n_polish=int(o.n_polish),
-                                warm_start=int(bool(o.warm_start)), mu_ref=o.mu_ref)
+                                warm_start=int(bool(o.warm_start)), mu_ref=o.mu_ref,
+                                dcost=float(1e-5 if o.dcost is None else o.dcost),
+                                objective_nodes=int(o.objective_nodes))
         _cabi.check(_cabi.lib().lmato_set_options(self._h, C.byref(co)), "lmato_set_options")
         self.options = o
 
@@ -418,6 +422,8 @@ def optimise_batch(params: AscentParams, mesh: Optional[Mesh] = None,
     """
     mesh = mesh or Mesh()
     options = options or SolverOptions()
+    if options.dcost is None:          # the move-suppression weight travels with the model parameters
+        options = dataclasses.replace(options, dcost=float(params.dcost))
     on_dev = any(isinstance(getattr(params, f.name), torch.Tensor) and getattr(params, f.name).is_cuda
                  for f in dataclasses.fields(params))
     solver = _get_solver(mesh, options, device, params.model)

@@ -18,7 +18,7 @@
 #include <vector>
 
 #include "../../include/lmato_b200.h"
-#include "ascent_ipm.cuh"
+#include "ascent_ipm_dc.cuh"
 
 using namespace lmato;
 
@@ -121,6 +121,8 @@ __device__ __forceinline__ Params derive_params(const double* __restrict__ p, lo
 // shared memory are bank-conflict free (stride 19 doubles = 38 words; 38 mod 32 = 6).
 struct alignas(8) ParamsSlot { Params p; double pad[(sizeof(Params) / 8) % 2 == 0 ? 1 : 2]; };
 
+// SW = Sweeps7 (dcost = 0) or Sweeps8 (with the reference's move-suppression term, LO:99)
+template <class SW>
 __global__ void __launch_bounds__(kBlock, kBlocksPerSM) ascent_ipm_kernel(KArgs a) {
   // The sweeps are separate (noinline) functions taking `const Params&`: keeping the per-problem
   // constants in shared memory instead of the thread's local-memory stack removes a dozen
@@ -136,7 +138,7 @@ __global__ void __launch_bounds__(kBlock, kBlocksPerSM) ascent_ipm_kernel(KArgs 
   const long slot = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   const long nwarps = a.slots / LANES;
-  const Ws W{a.ws + ((slot / LANES) * N_FIELDS) * LANES + lane, nwarps * N_FIELDS * LANES};
+  const Ws W{a.ws + ((slot / LANES) * SW::NFIELDS) * LANES + lane, nwarps * SW::NFIELDS * LANES};
   const int nt = a.N + 1;
   IpmState S;
   bool active = false;        // this lane holds an unfinished problem
@@ -166,12 +168,12 @@ __global__ void __launch_bounds__(kBlock, kBlocksPerSM) ascent_ipm_kernel(KArgs 
           P = derive_params(a.params, a.B, b, a.model);
           ipm_begin(O, S);
           double mu0 = 0.0;
-          if (a.ref_mode == 2 && init_from_ref(P, M, W, a.ref, S.cur, &mu0)) {
+          if (a.ref_mode == 2 && SW::load_ref(P, M, W, a.ref, S.cur, &mu0)) {
             S.warm = true;
             S.ctl.mu = mu0;
             S.ctl.tau = dmax(O.tau_min, 1.0 - mu0);
           } else {
-            init_guess(P, M, O, W, S.cur);
+            SW::guess(P, M, O, W, S.cur);
           }
           active = true;
         }
@@ -183,18 +185,18 @@ __global__ void __launch_bounds__(kBlock, kBlocksPerSM) ascent_ipm_kernel(KArgs 
     //  gains, because line-search retries differ between warps; the imbalance averages out over
     //  a few iterations while the warps stay close enough to share the instruction cache)
     if ((round++ % LMATO_SYNC_PERIOD) == 0 && !__syncthreads_or((active || !exhausted) ? 1 : 0)) break;
-    if (active && ipm_iterate(P, M, O, W, S)) {
+    if (active && ipm_iterate_t<SW>(P, M, O, W, S)) {
       if (S.warm && S.ctl.status != ST_CONVERGED) {
         // a warm start that did not work out: this lane restarts the same problem from the cold start
         ipm_begin(O, S);
-        init_guess(P, M, O, W, S.cur);
+        SW::guess(P, M, O, W, S.cur);
         continue;
       }
       active = false;
       SolveOut out;
       ipm_result(S, out);
       if (a.ref_mode == 1) {
-        ref_store(P, M, W, out.cur, S.cur, S.ctl.mu, out.status == ST_CONVERGED, a.ref);
+        SW::store_ref(P, M, W, out.cur, S.cur, S.ctl.mu, out.status == ST_CONVERGED, a.ref);
         continue;
       }
       a.tf[b] = out.tf;
@@ -211,8 +213,8 @@ __global__ void __launch_bounds__(kBlock, kBlocksPerSM) ascent_ipm_kernel(KArgs 
           const double* sp = W.stage(k);
           double z[6];
 #pragma unroll
-          for (int i = 0; i < 6; ++i) z[i] = WS_AT(sp, out.cur * N_ITER + F_Z + i);
-          const double u = WS_AT(sp, out.cur * N_ITER + F_U);
+          for (int i = 0; i < 6; ++i) z[i] = WS_AT(sp, out.cur * SW::NITER + SW::FZ + i);
+          const double u = WS_AT(sp, out.cur * SW::NITER + SW::FU);
           const double m = P.mflow * P.T * a.tau[k] * out.tf;
           double ay, ax;
           accel_value(P, z[0], z[2], z[4], m, ay, ax);
@@ -304,6 +306,8 @@ void lmato_default_options(lmato_options* o) {
   o->n_polish = 4;
   o->warm_start = 1;
   o->mu_ref = 1e-3;
+  o->dcost = 1e-5;            // LO:99
+  o->objective_nodes = 0;     // 0 = nt - 1
   o->max_iter = 20000;   // LO:28
   o->max_ls = 40;
 }
@@ -351,7 +355,7 @@ lmato_status_t lmato_create(lmato_handle** out, int32_t device, int32_t nt, cons
   CUDA_TRY(cudaMemcpy(H->d_h, h.data(), sizeof(double) * nt, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(H->d_tau, tau.data(), sizeof(double) * nt, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMalloc(&H->d_counter, sizeof(int)));
-  CUDA_TRY(cudaMalloc(&H->d_ref, sizeof(double) * REF_ROWS * nt));
+  CUDA_TRY(cudaMalloc(&H->d_ref, sizeof(double) * (size_t)dc::REF_ROWS * nt));   // dc:: is the larger layout
   CUDA_TRY(cudaMalloc(&H->d_refparams, sizeof(double) * (LMATO_NPARAM + 8)));
   CUDA_TRY(cudaEventCreate(&H->ev0));
   CUDA_TRY(cudaEventCreate(&H->ev1));
@@ -375,13 +379,19 @@ lmato_status_t lmato_set_options(lmato_handle* h, const lmato_options* o) {
   if (!(o->tol > 0) || !(o->mu_init > 0) || !(o->obj_scale > 0) || !(o->delta_c > 0) ||
       !(o->tf_guess > 0 && o->tf_guess < 1) || o->max_iter < 0 || o->max_ls < 1 ||
       !(o->mu_min_factor > 0 && o->mu_min_factor <= 1) || o->n_polish < 0 ||
-      (o->warm_start != 0 && o->warm_start != 1) || !(o->mu_ref > 0 && o->mu_ref <= o->mu_init)) {
+      (o->warm_start != 0 && o->warm_start != 1) || !(o->mu_ref > 0 && o->mu_ref <= o->mu_init) ||
+      !(o->dcost >= 0) || o->objective_nodes < 0) {
     set_err("lmato_set_options: option out of range");
     return LMATO_ERR_INVALID;
   }
   h->opt = *o;
   return LMATO_OK;
 }
+
+// The move-suppression term (LO:99) applies to the MV angledoubledot of the elliptical model; the
+// circular model's MV is the angle itself and runs without it.
+static bool dcost_active(const lmato_handle* h) { return h->opt.dcost > 0.0 && h->model == LMATO_MODEL_ELLIPTICAL; }
+static int fields_for(const lmato_handle* h) { return dcost_active(h) ? (int)dc::N_FIELDS : (int)N_FIELDS; }
 
 static long slots_for(const lmato_handle* h, int64_t B) {
   // one CTA per SM, but never more CTAs than 32-problem chunks
@@ -392,7 +402,7 @@ static long slots_for(const lmato_handle* h, int64_t B) {
 
 lmato_status_t lmato_workspace_bytes(lmato_handle* h, int64_t B, int64_t* bytes) {
   if (!h || !bytes || B < 0) { set_err("lmato_workspace_bytes: bad argument"); return LMATO_ERR_INVALID; }
-  *bytes = (int64_t)sizeof(double) * N_FIELDS * h->nt * slots_for(h, B);
+  *bytes = (int64_t)sizeof(double) * fields_for(h) * h->nt * slots_for(h, B);
   return LMATO_OK;
 }
 
@@ -416,7 +426,8 @@ lmato_status_t lmato_solve_batch(lmato_handle* h, const double* params, int64_t 
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
   const long slots = slots_for(h, B);
-  const size_t need = sizeof(double) * (size_t)N_FIELDS * (size_t)h->nt * (size_t)slots;
+  const bool use_dc = dcost_active(h);
+  const size_t need = sizeof(double) * (size_t)fields_for(h) * (size_t)h->nt * (size_t)slots;
   if (need > h->ws_bytes) {
     if (h->d_ws) { CUDA_TRY(cudaStreamSynchronize(st)); CUDA_TRY(cudaFree(h->d_ws)); h->d_ws = nullptr; h->ws_bytes = 0; }
     CUDA_TRY(cudaMalloc(&h->d_ws, need));
@@ -435,6 +446,10 @@ lmato_status_t lmato_solve_batch(lmato_handle* h, const double* params, int64_t 
   a.O.delta_c = h->opt.delta_c; a.O.tf_guess = h->opt.tf_guess;
   a.O.max_iter = h->opt.max_iter; a.O.max_ls = h->opt.max_ls;
   a.O.mu_min_factor = h->opt.mu_min_factor; a.O.n_polish = h->opt.n_polish;
+  {
+    const int on = h->opt.objective_nodes > 0 ? h->opt.objective_nodes : h->nt - 1;
+    a.O.w_dcost = use_dc ? h->opt.obj_scale * h->opt.dcost / (double)on : 0.0;
+  }
   a.ref = nullptr; a.ref_mode = 0;
   const int grid = (int)(slots / kBlock);
   CUDA_TRY(cudaEventRecord(h->ev0, st));
@@ -448,13 +463,15 @@ lmato_status_t lmato_solve_batch(lmato_handle* h, const double* params, int64_t 
     r.status = (int*)(scratch + 2); r.iters = (int*)(scratch + 3); r.kkt = scratch + 4;
     r.ref = h->d_ref; r.ref_mode = 1;
     r.O.tol = 10.0 * h->opt.mu_ref; r.O.mu_min_factor = 0.1; r.O.n_polish = 0;
-    ascent_ipm_kernel<<<1, kBlock, 0, st>>>(r);
+    if (use_dc) ascent_ipm_kernel<Sweeps8><<<1, kBlock, 0, st>>>(r);
+    else ascent_ipm_kernel<Sweeps7><<<1, kBlock, 0, st>>>(r);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemsetAsync(h->d_counter, 0, sizeof(int), st));
     a.ref = h->d_ref; a.ref_mode = 2;
     h->launches += 2;
   }
-  ascent_ipm_kernel<<<grid, kBlock, 0, st>>>(a);
+  if (use_dc) ascent_ipm_kernel<Sweeps8><<<grid, kBlock, 0, st>>>(a);
+  else ascent_ipm_kernel<Sweeps7><<<grid, kBlock, 0, st>>>(a);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaEventRecord(h->ev1, st));
   h->last_stream = st; h->timed = true;

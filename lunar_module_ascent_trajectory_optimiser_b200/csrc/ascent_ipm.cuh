@@ -33,6 +33,7 @@ struct Options {
   double delta_c;        // dual regularisation of the terminal equality row
   double tf_guess;       // initial tf (scaled, 0..1)
   double mu_min_factor;  // smallest barrier parameter = mu_min_factor * tol (IPOPT: 0.1)
+  double w_dcost;        // weight of the move-suppression term (LO:99) relative to obj_scale*tf; 0 = off
   int max_iter;          // LO:28 MAX_ITER
   int max_ls;            // max backtracking steps
   int n_polish;          // extra Newton iterations after the tolerance is first met
@@ -1086,12 +1087,40 @@ LM_HD void ipm_begin(const Options& O, IpmState& S) {
   S.warm = false;
 }
 
-LM_HD bool ipm_iterate(const Params& P, const Mesh& M, const Options& O, const Ws& W, IpmState& S) {
+// Sweeps policy of the 7-state formulation (dcost = 0); ascent_ipm_dc.cuh provides the 8-state one.
+struct Sweeps7 {
+  enum : int { NFIELDS = N_FIELDS, NITER = N_ITER, FZ = F_Z, FU = F_U, REFROWS = REF_ROWS };
+  LM_HD static int n_eq(int N) { return 6 * N + 3; }
+  LM_HD static int n_bd(int N) { return 4 * N + 4; }
+  LM_HD static bool backward(const Params& P, const Mesh& M, const Options& O, const Ws& W, int src, const Scal& c0,
+                             double mu, double dw, bool ls, double* dtf) {
+    return riccati_backward(P, M, O, W, src, c0, mu, dw, ls, dtf);
+  }
+  LM_HD static void forward(const Params& P, const Mesh& M, const Options& O, const Ws& W, int src, const Scal& c0,
+                            double mu, double tau, double dtf, bool ls, TermStep& ts, StepInfo& si) {
+    riccati_forward(P, M, O, W, src, c0, mu, tau, dtf, ls, ts, si);
+  }
+  LM_HD static void eval(const Params& P, const Mesh& M, const Options& O, const Ws& W, int src, int dst,
+                         const Scal& c0, const TermStep& ts, double mu, double dw, double alpha, double alpha_z,
+                         double alpha_lam, int mode, Scal& t, double* pimax) {
+    eval_pass(P, M, O, W, src, dst, c0, ts, mu, dw, alpha, alpha_z, alpha_lam, mode, t, pimax);
+  }
+  LM_HD static void guess(const Params& P, const Mesh& M, const Options& O, const Ws& W, Scal& s) { init_guess(P, M, O, W, s); }
+  LM_HD static void store_ref(const Params& P, const Mesh& M, const Ws& W, int src, const Scal& c, double mu, bool ok,
+                              double* ref) { ref_store(P, M, W, src, c, mu, ok, ref); }
+  LM_HD static bool load_ref(const Params& P, const Mesh& M, const Ws& W, const double* ref, Scal& s, double* mu) {
+    return init_from_ref(P, M, W, ref, s, mu);
+  }
+  LM_HD static void remerit(const Mesh&, const Options&, const Ws&, int, double, Scal&) {}
+};
+
+template <class SW>
+LM_HD bool ipm_iterate_t(const Params& P, const Mesh& M, const Options& O, const Ws& W, IpmState& S) {
   Ctl& ctl = S.ctl;
   Scal& cur = S.cur;
   const int N = M.N;
-  const int n_eq = 6 * N + 3;
-  const int n_bd = 4 * N + 4;
+  const int n_eq = SW::n_eq(N);
+  const int n_bd = SW::n_bd(N);
   const bool ls = (S.phase == PH_LSQ);
   if (!ls) {
     S.err0 = kkt_error(cur, 0.0, n_eq, n_bd);
@@ -1099,11 +1128,14 @@ LM_HD bool ipm_iterate(const Params& P, const Mesh& M, const Options& O, const W
     const double mu_min = O.tol * O.mu_min_factor;
     // (the sub-problem tolerance kappa_eps*mu is floored at tol: below that it would ask for more
     //  than the final test does, and more than FP64 can deliver for the dual residual)
+    bool mu_changed = false;
     while (kkt_error(cur, ctl.mu, n_eq, n_bd) <= dmax(O.kappa_eps * ctl.mu, O.tol) && ctl.mu > mu_min * (1.0 + 1e-12)) {
       ctl.mu = dmax(mu_min, dmin(O.kappa_mu * ctl.mu, ctl.mu * sqrt(ctl.mu)));   // theta_mu = 1.5
       ctl.tau = dmax(O.tau_min, 1.0 - ctl.mu);
       ctl.nf = 0;
+      mu_changed = true;
     }
+    if (mu_changed) SW::remerit(M, O, W, S.src, ctl.mu, cur);
     // Converged = scaled KKT error <= tol with the barrier parameter at its floor.  Requiring the
     // floor pins the final point on the central path: the control on the singular arc is a nearly
     // flat direction of this NLP and moves like O(mu / sigma_min) (DESIGN.md "Tolerance").
@@ -1126,7 +1158,7 @@ LM_HD bool ipm_iterate(const Params& P, const Mesh& M, const Options& O, const W
   bool fact_ok = false;
   for (int attempt = 0; attempt < 40; ++attempt) {
     if (ls && S.warm) break;
-    if (riccati_backward(P, M, O, W, S.src, cur, ctl.mu, dw, ls, &dtf)) { fact_ok = true; break; }
+    if (SW::backward(P, M, O, W, S.src, cur, ctl.mu, dw, ls, &dtf)) { fact_ok = true; break; }
     if (ls) break;
     if (dw == 0.0) dw = (ctl.dw_last == 0.0) ? 1e-4 : dmax(1e-20, ctl.dw_last / 3.0);
     else dw *= (ctl.dw_last == 0.0) ? 100.0 : 8.0;
@@ -1139,14 +1171,14 @@ LM_HD bool ipm_iterate(const Params& P, const Mesh& M, const Options& O, const W
     if (fact_ok) {
       StepInfo s0;
       double pimax = 0.0;
-      riccati_forward(P, M, O, W, S.src, cur, ctl.mu, ctl.tau, dtf, true, S.ts, s0);
-      eval_pass(P, M, O, W, S.src, 1 - S.src, cur, S.ts, ctl.mu, 0.0, 0.0, 0.0, 1.0, EV_LSQ, trial, &pimax);
+      SW::forward(P, M, O, W, S.src, cur, ctl.mu, ctl.tau, dtf, true, S.ts, s0);
+      SW::eval(P, M, O, W, S.src, 1 - S.src, cur, S.ts, ctl.mu, 0.0, 0.0, 0.0, 1.0, EV_LSQ, trial, &pimax);
       have = pimax <= 1e3 * dmax(1.0, O.obj_scale) && fabs(S.ts.dnu3) <= 1e3 * dmax(1.0, O.obj_scale);
 #if defined(LMATO_TRACE) && !defined(__CUDA_ARCH__)
       printf("LS multipliers: pimax %.3e dnu3 %.3e dtf %.3e -> %s\n", pimax, S.ts.dnu3, dtf, have ? "used" : "discarded");
 #endif
     }
-    if (!have) eval_pass(P, M, O, W, S.src, 1 - S.src, cur, S.ts, ctl.mu, 0.0, 0.0, 0.0, 0.0, EV_READ_PI, trial, nullptr);
+    if (!have) SW::eval(P, M, O, W, S.src, 1 - S.src, cur, S.ts, ctl.mu, 0.0, 0.0, 0.0, 0.0, EV_READ_PI, trial, nullptr);
     cur = trial; S.src = 1 - S.src;
     ctl.theta_max = 1e4 * dmax(1.0, cur.theta);
     ctl.theta_min = 1e-4 * dmax(1.0, cur.theta);
@@ -1156,7 +1188,7 @@ LM_HD bool ipm_iterate(const Params& P, const Mesh& M, const Options& O, const W
   if (!fact_ok) { ctl.status = polishing ? ST_CONVERGED : ST_INERTIA_FAIL; return true; }
   if (dw > 0.0) ctl.dw_last = dw;
   StepInfo si;
-  riccati_forward(P, M, O, W, S.src, cur, ctl.mu, ctl.tau, dtf, false, S.ts, si);
+  SW::forward(P, M, O, W, S.src, cur, ctl.mu, ctl.tau, dtf, false, S.ts, si);
   if (!(si.dphi == si.dphi) || !(si.dxmax < 1e300)) { ctl.status = polishing ? ST_CONVERGED : ST_NUMERICAL; return true; }
   // filter line search (IPOPT section 2.3)
   const double theta = cur.theta;
@@ -1171,8 +1203,8 @@ LM_HD bool ipm_iterate(const Params& P, const Mesh& M, const Options& O, const W
   const double sw_lhs = sw_possible ? pow(-dphi, s_ph) : 0.0;
   const double sw_rhs = sw_possible ? delta * pow(theta, s_th) : 0.0;
   for (int lsi = 0; lsi < O.max_ls; ++lsi) {
-    eval_pass(P, M, O, W, S.src, 1 - S.src, cur, S.ts, ctl.mu, dw, alpha, si.a_z, alpha,
-              lsi == 0 ? EV_NEWTON : EV_READ_PI, trial, nullptr);
+    SW::eval(P, M, O, W, S.src, 1 - S.src, cur, S.ts, ctl.mu, dw, alpha, si.a_z, alpha,
+             lsi == 0 ? EV_NEWTON : EV_READ_PI, trial, nullptr);
     const double th_t = trial.theta;
     const double ph_t = trial.fobj - ctl.mu * trial.sumlog;
     bool ok = (th_t <= ctl.theta_max) && (ph_t == ph_t) && (ph_t < 1e299) && filter_ok(ctl, th_t, ph_t);
@@ -1201,6 +1233,10 @@ LM_HD bool ipm_iterate(const Params& P, const Mesh& M, const Options& O, const W
          cur.theta, S.err0, ctl.mu, alpha, si.a_z, dw, dphi, si.dxmax, ctl.nf, ftype ? "f" : "h");
 #endif
   return false;
+}
+
+LM_HD bool ipm_iterate(const Params& P, const Mesh& M, const Options& O, const Ws& W, IpmState& S) {
+  return ipm_iterate_t<Sweeps7>(P, M, O, W, S);
 }
 
 LM_HD void ipm_result(const IpmState& S, SolveOut& out) {

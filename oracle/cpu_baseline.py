@@ -27,17 +27,17 @@ def _init_worker():
 
 
 def solve_one(args) -> Tuple[float, int, int, float]:
-    col, nt, tol, obj_scale = args
+    col, nt, tol, obj_scale, dcost = args
     from oracle.ascent_nlp import AscentNLP, AscentParams
     from oracle.ipm_reference import IPMOptions, solve_ipm
     kw = dict(zip(_ROWS, [float(v) for v in col]))
     p = AscentParams(G=kw["G"], M=kw["M"], R0=kw["R0"], Ft=kw["Ft"], M0=kw["M0"], M_dot=kw["M_dot"],
                      fuel_mass=kw["fuel_mass"], angle_doubledot_max=kw["angle_doubledot_max"],
                      r_periapsis=kw["r_periapsis"], r_apoapsis=kw["r_apoapsis"], final_time=kw["final_time"],
-                     mass_scalar=kw["mass_scalar"], angle_ub=kw["angle_ub"], u_bound=kw["u_bound"])
+                     mass_scalar=kw["mass_scalar"], angle_ub=kw["angle_ub"], u_bound=kw["u_bound"], dcost=dcost)
     t0 = time.perf_counter()
     nlp = AscentNLP(p, nt=nt, obj_scale=obj_scale)
-    r = solve_ipm(nlp, nlp.initial_guess(0.9), IPMOptions(tol=tol))
+    r = solve_ipm(nlp, nlp.initial_guess(0.9), IPMOptions(tol=tol, max_iter=500))
     return float(r.x[nlp.i_tf]), int(r.status), int(r.iterations), time.perf_counter() - t0
 
 
@@ -51,11 +51,11 @@ class OraclePool:
         # make sure every worker has finished building its model before anything is timed
         self.pool.map(_noop, range(self.cores * 2))
 
-    def solve(self, rows: np.ndarray, nt: int, tol: float, obj_scale: float):
+    def solve(self, rows: np.ndarray, nt: int, tol: float, obj_scale: float, dcost: float = 1e-5):
         """rows: [NPARAM, n].  Returns (tf[n], status[n], iters[n], wall seconds)."""
         n = rows.shape[1]
         t0 = time.perf_counter()
-        res = self.pool.map(solve_one, [(rows[:, i].copy(), nt, tol, obj_scale) for i in range(n)], chunksize=1)
+        res = self.pool.map(solve_one, [(rows[:, i].copy(), nt, tol, obj_scale, dcost) for i in range(n)], chunksize=1)
         wall = time.perf_counter() - t0
         tf = np.array([r[0] for r in res])
         st = np.array([r[1] for r in res])

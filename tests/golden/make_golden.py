@@ -69,7 +69,7 @@ def main():
              final_mass=np.array(fms), traj=np.stack(trajs), names=np.array(VAR_ROWS))
 
 
-if __name__ == "__main__" and "--dense" not in sys.argv:
+if __name__ == "__main__" and "--dense" not in sys.argv and "--dcost" not in sys.argv:
     main()
 
 
@@ -86,3 +86,29 @@ def dense_mesh():
 
 if __name__ == "__main__" and "--dense" in sys.argv:
     dense_mesh()
+
+
+def dcost():
+    """The reference's move suppression (angledoubledot.DCOST = 1e-5, LO:99) with the objective summed
+    over the nt-1 steps (APMonitor IMODE 6): nominal case + the first 4 seed-11 dispersions."""
+    import torch  # noqa: F401
+    from lunar_module_ascent_trajectory_optimiser_b200.dispersions import dispersed_params
+    rows = dispersed_params(4, seed=11).rows().numpy()
+    tfs, fms, trajs = [], [], []
+    for b in range(rows.shape[1]):
+        p = AscentParams(Ft=rows[3, b], M0=rows[4, b], M_dot=rows[5, b], angle_doubledot_max=rows[7, b],
+                         r_periapsis=rows[8, b], r_apoapsis=rows[9, b], dcost=1e-5)
+        nlp = AscentNLP(p, nt=200, obj_scale=10.0)
+        r = solve_ipm(nlp, nlp.initial_guess(0.9), IPMOptions(tol=1e-12, max_iter=500))
+        assert r.status == 0, (r.status, r.kkt_error)
+        nv = nlp.node_values(r.x)
+        tfs.append(nv["tf"]); fms.append(p.M0 - p.fuel_mass * nv["mass"][-1])
+        trajs.append(np.stack([nv[n] for n in VAR_ROWS]))
+        print("dcost", b, "tf_s", nv["tf"] * 470, "iters", r.iterations, "kkt", r.kkt_error)
+    np.savez(os.path.join(HERE, "elliptical_dcost1e-5_disp4_seed11_nt200.npz"), rows=rows, tf=np.array(tfs),
+             final_mass=np.array(fms), traj=np.stack(trajs), names=np.array(VAR_ROWS), dcost=1e-5,
+             objective_nodes=199)
+
+
+if __name__ == "__main__" and "--dcost" in sys.argv:
+    dcost()

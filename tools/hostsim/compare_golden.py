@@ -38,3 +38,20 @@ rows = {"y": 0, "ydot": 1, "ydoubledot": 2, "x": 3, "xdot": 4, "xdoubledot": 5, 
 err = {n: np.abs(traj[rows[n]] - g["traj"][names.index(n)]).max() / np.abs(g["traj"][names.index(n)]).max() for n in rows}
 print("circular: status", st, "iters", it.value, "kkt %.1e" % kkt.value, "tf_s %.8f (golden %.8f)" % (tf.value * 470, float(g["tf"]) * 470))
 print("circular rel err:", {k: "%.1e" % v for k, v in err.items()})
+
+# DCOST (8-state path): weight relative to obj_scale*tf = obj_scale*dcost/(nt-1)
+os.environ.pop("CIRCULAR", None)
+os.environ["WDC"] = repr(10.0 * 1e-5 / 199)
+g = np.load(os.path.join(ROOT, "tests", "golden", "elliptical_dcost1e-5_disp4_seed11_nt200.npz"))
+worst = np.zeros(10)
+for b in range(g["rows"].shape[1]):
+    raw = np.ascontiguousarray(g["rows"][:, b])
+    traj = np.empty((10, nt)); tf = C.c_double(); it = C.c_int(); kkt = C.c_double()
+    st = L.hostsim_solve(raw.ctypes.data_as(C.c_void_p), nt, None, C.c_double(tol), C.c_double(10.0), C.c_double(mmf),
+                         traj.ctypes.data_as(C.c_void_p), C.byref(tf), C.byref(it), C.byref(kkt))
+    gt = g["traj"][b]
+    err = (np.abs(traj - gt) / np.abs(gt).max(axis=1, keepdims=True)).max(axis=1)
+    worst = np.maximum(worst, err)
+    print("dcost", b, "status", st, "iters", it.value, "kkt %.1e" % kkt.value, "tf rel %.1e" % (abs(tf.value - g["tf"][b]) / g["tf"][b]),
+          "angledot %.1e control %.1e others %.1e" % (err[7], err[9], np.delete(err, [7, 9]).max()))
+print("dcost worst per row:", " ".join("%.1e" % e for e in worst))

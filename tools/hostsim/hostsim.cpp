@@ -14,7 +14,7 @@
 #include <cmath>
 #include <vector>
 #include <random>
-#include "ascent_ipm.cuh"
+#include "ascent_ipm_dc.cuh"
 
 using namespace lmato;
 
@@ -45,13 +45,15 @@ int main(int argc, char** argv) {
   O.tau_min = 0.99; O.delta_c = 1e-8; O.tf_guess = 0.9; O.max_iter = 500; O.max_ls = 40; O.mu_min_factor = 1e-3; O.n_polish = 4;
   if (getenv("MMF")) O.mu_min_factor = atof(getenv("MMF"));
   if (getenv("NPOL")) O.n_polish = atoi(getenv("NPOL"));
+  O.w_dcost = getenv("WDC") ? atof(getenv("WDC")) : 0.0;
   if (getenv("OBJ")) O.obj_scale = atof(getenv("OBJ"));
   if (getenv("MU0")) O.mu_init = atof(getenv("MU0"));
   if (getenv("TOL")) O.tol = atof(getenv("TOL"));
   if (getenv("TF0")) O.tf_guess = atof(getenv("TF0"));
   if (getenv("DC")) O.delta_c = atof(getenv("DC"));
-  std::vector<double> ws((size_t)N_FIELDS * LANES * (N + 1), 0.0);   // one warp block, lane 0 used
-  Ws W{ws.data(), (long)N_FIELDS * LANES};
+  const int nfields = O.w_dcost > 0 ? (int)dc::N_FIELDS : (int)N_FIELDS;
+  std::vector<double> ws((size_t)nfields * LANES * (N + 1), 0.0);   // one warp block, lane 0 used
+  Ws W{ws.data(), (long)nfields * LANES};
   std::mt19937_64 rng(11);
   std::uniform_real_distribution<double> U(0.0, 1.0);
   int nfail = 0, itsum = 0, itmax = 0;
@@ -69,7 +71,15 @@ int main(int argc, char** argv) {
     Params P = make_params(Ft, M0, Mdot, addm, rp, ra);
     std::fill(ws.begin(), ws.end(), 0.0);
     SolveOut out;
-    ipm_solve(P, M, O, W, false, out);
+    if (O.w_dcost > 0) {
+      IpmState S;
+      dc::init_guess(P, M, O, W, S.cur);
+      ipm_begin(O, S);
+      while (!ipm_iterate_t<Sweeps8>(P, M, O, W, S)) {}
+      ipm_result(S, out);
+    } else {
+      ipm_solve(P, M, O, W, false, out);
+    }
     itsum += out.iters; if (out.iters > itmax) itmax = out.iters;
     if (out.status != 0) ++nfail;
     if (verbose || nprob <= 20 || out.status != 0)
@@ -97,6 +107,7 @@ extern "C" int hostsim_solve(const double* raw14, int nt, const double* time, do
   Options O;
   O.tol = tol; O.mu_init = 0.1; O.obj_scale = obj_scale; O.kappa_eps = 10.0; O.kappa_mu = 0.2; O.theta_mu = 1.5;
   O.tau_min = 0.99; O.delta_c = 1e-8; O.tf_guess = 0.9; O.max_iter = 500; O.max_ls = 40; O.mu_min_factor = mu_min_factor; O.n_polish = getenv("NPOL") ? atoi(getenv("NPOL")) : 4;
+  O.w_dcost = getenv("WDC") ? atof(getenv("WDC")) : 0.0;
   Params P;
   const double* r = raw14;
   P.GM = r[0] * r[1]; P.R0 = r[2]; P.Ft = r[3]; P.M0 = r[4]; P.S = r[8]; P.ms = r[11]; P.mflow = r[5] / r[6];
@@ -105,20 +116,31 @@ extern "C" int hostsim_solve(const double* raw14, int nt, const double* time, do
   P.vt2 = (vt / P.S) * (vt / P.S); P.rt = (P.R0 + P.S) / P.S; P.R0S = P.R0 / P.S;
   P.tf_ub = std::fmin(1.0, 1.0 / (P.mflow * P.T)); P.fuel = r[6]; P.Sinv = 1.0 / P.S; P.coup5 = 1.0;
   if (getenv("CIRCULAR")) { P.coup5 = 0.0; P.asc = 1.0; P.u_ub = 1e20; }
-  std::vector<double> ws((size_t)N_FIELDS * LANES * (N + 1), 0.0);
-  Ws W{ws.data(), (long)N_FIELDS * LANES};
+  const bool DC = O.w_dcost > 0;
+  const int nfields = DC ? (int)dc::N_FIELDS : (int)N_FIELDS;
+  const int niter = DC ? (int)dc::N_ITER : (int)N_ITER;
+  std::vector<double> ws((size_t)nfields * LANES * (N + 1), 0.0);
+  Ws W{ws.data(), (long)nfields * LANES};
   SolveOut out;
-  ipm_solve(P, M, O, W, false, out);
+  if (DC) {
+    IpmState S;
+    dc::init_guess(P, M, O, W, S.cur);
+    ipm_begin(O, S);
+    while (!ipm_iterate_t<Sweeps8>(P, M, O, W, S)) {}
+    ipm_result(S, out);
+  } else {
+    ipm_solve(P, M, O, W, false, out);
+  }
   *tf_out = out.tf; *iters = out.iters; *kkt = out.kkt;
   for (int v = 0; v < 10; ++v) traj[v * nt] = 0.0;
   for (int k = 1; k <= N; ++k) {
     const double* sp = W.stage(k);
     double z[6];
-    for (int i = 0; i < 6; ++i) z[i] = WS_AT(sp, out.cur * N_ITER + F_Z + i);
+    for (int i = 0; i < 6; ++i) z[i] = WS_AT(sp, out.cur * niter + F_Z + i);
     const double m = P.mflow * P.T * tau[k] * out.tf;
     double ay, ax;
     accel_value(P, z[0], z[2], z[4], m, ay, ax);
-    const double vals[10] = {z[0], z[1], ay, z[2], z[3], ax, z[4], z[5], m, WS_AT(sp, out.cur * N_ITER + F_U)};
+    const double vals[10] = {z[0], z[1], ay, z[2], z[3], ax, z[4], z[5], m, WS_AT(sp, out.cur * niter + F_U)};
     for (int v = 0; v < 10; ++v) traj[v * nt + k] = vals[v];
   }
   return out.status;
