@@ -87,7 +87,8 @@ typedef struct {
   double mu_min_factor; /* barrier floor = mu_min_factor * tol; default 1e-3 (IPOPT uses 0.1) */
   int32_t max_iter;  /* LO:28 MAX_ITER; default 20000 (the reference's value) */
   int32_t max_ls;    /* max backtracking steps per iteration; default 40 */
-  int32_t n_polish;  /* Newton iterations taken after tol is first met; default 4 (DESIGN.md "Tolerance") */
+  int32_t n_polish;  /* Newton iterations taken after tol is first met; default -1 = automatic: 2 with the
+                        DCOST term (it regularises the flat control directions), 4 without (DESIGN.md "Tolerance") */
   int32_t warm_start; /* 1 (default): batches of >= 256 problems first solve the batch-mean problem down to
                          mu_ref and start every problem from that central-path point; a problem that fails
                          from there is restarted from the generic cold start.  0: always cold start. */

@@ -133,7 +133,7 @@ class SolverOptions:
     delta_c: float = 1e-8
     max_ls: int = 40
     mu_min_factor: float = 1e-3    # barrier floor = mu_min_factor * tol
-    n_polish: int = 4              # Newton iterations after tol is first met
+    n_polish: int = -1             # Newton iterations after tol is first met; -1 = 2 with DCOST, 4 without
     warm_start: bool = True        # batches >= 256: start from the batch-mean problem's central path
     mu_ref: float = 1e-3           # barrier parameter at which that reference solve stops
     dcost: Optional[float] = None  # LO:99; None = take AscentParams.dcost (1e-5 in the reference)

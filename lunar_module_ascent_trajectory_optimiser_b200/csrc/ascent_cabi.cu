@@ -303,7 +303,7 @@ void lmato_default_options(lmato_options* o) {
   o->tf_guess = 0.9;
   o->delta_c = 1e-8;
   o->mu_min_factor = 1e-3;
-  o->n_polish = 4;
+  o->n_polish = -1;           // automatic: 2 with the DCOST term, 4 without (DESIGN.md "Tolerance")
   o->warm_start = 1;
   o->mu_ref = 1e-3;
   o->dcost = 1e-5;            // LO:99
@@ -378,7 +378,7 @@ lmato_status_t lmato_set_options(lmato_handle* h, const lmato_options* o) {
   if (!h || !o) { set_err("lmato_set_options: NULL argument"); return LMATO_ERR_INVALID; }
   if (!(o->tol > 0) || !(o->mu_init > 0) || !(o->obj_scale > 0) || !(o->delta_c > 0) ||
       !(o->tf_guess > 0 && o->tf_guess < 1) || o->max_iter < 0 || o->max_ls < 1 ||
-      !(o->mu_min_factor > 0 && o->mu_min_factor <= 1) || o->n_polish < 0 ||
+      !(o->mu_min_factor > 0 && o->mu_min_factor <= 1) || o->n_polish < -1 ||
       (o->warm_start != 0 && o->warm_start != 1) || !(o->mu_ref > 0 && o->mu_ref <= o->mu_init) ||
       !(o->dcost >= 0) || o->objective_nodes < 0) {
     set_err("lmato_set_options: option out of range");
@@ -445,7 +445,8 @@ lmato_status_t lmato_solve_batch(lmato_handle* h, const double* params, int64_t 
   a.O.kappa_eps = 10.0; a.O.kappa_mu = 0.2; a.O.theta_mu = 1.5; a.O.tau_min = 0.99;
   a.O.delta_c = h->opt.delta_c; a.O.tf_guess = h->opt.tf_guess;
   a.O.max_iter = h->opt.max_iter; a.O.max_ls = h->opt.max_ls;
-  a.O.mu_min_factor = h->opt.mu_min_factor; a.O.n_polish = h->opt.n_polish;
+  a.O.mu_min_factor = h->opt.mu_min_factor;
+  a.O.n_polish = h->opt.n_polish >= 0 ? h->opt.n_polish : (use_dc ? 2 : 4);
   {
     const int on = h->opt.objective_nodes > 0 ? h->opt.objective_nodes : h->nt - 1;
     a.O.w_dcost = use_dc ? h->opt.obj_scale * h->opt.dcost / (double)on : 0.0;

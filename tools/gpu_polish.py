@@ -3,7 +3,7 @@ sys.path.insert(0, '.')
 import lunar_module_ascent_trajectory_optimiser_b200 as lm
 B = 65536
 rows = lm.dispersed_params(B).rows(B).cuda()
-for npol in (2, 3, 4):
+for npol in (0, 1, 2, 4):
     res = {}
     for warm in (False, True):
         solver = lm.AscentSolver(lm.Mesh(), lm.SolverOptions(warm_start=warm, n_polish=npol), device=0)
