@@ -34,6 +34,10 @@ sys.path.insert(0, ROOT)
 FLOP_PER_STAGE = 2147.0
 BYTE_PER_STAGE = 336.0
 METRIC = "converged ascent-NLP solves/sec at batch 64K"
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE ascent_ipm_kernel launch, from the `ncu --set full`
+# capture summarised in profiles/r01_ncu_ascent_ipm_kernel_metrics.csv; keyed by (dcost on, batch, nt) and
+# only reported when the run matches that workload, otherwise null.
+NCU_TRAFFIC_BYTES = {(True, 65536, 200): 248.946e9 + 139.002e9}
 
 
 def load_peaks():
@@ -334,6 +338,7 @@ def main():
         "config": {"workload": f"cfg4: elliptical ascent (Launch_Optimiser.py defaults), nt={nt}, NODES=2, "
                                f"6-parameter dispersions, seed 11+rank",
                    "batch_per_gpu": B, "global_batch": B * world, "tol": opts.tol, "obj_scale": opts.obj_scale,
+                   "dcost": 1e-5 if opts.dcost is None else opts.dcost, "warm_start": bool(opts.warm_start),
                    "trajectories": traj, "parallelism": f"index-sharded x{world}, one allgather of results" if world > 1 else "single GPU",
                    "l2": f"no flush needed: the kernel streams a {solver.workspace_bytes(B) / 2**30:.1f} GiB workspace (>> 126 MB L2) every sweep"},
         "converged_fraction": conv_all / (B * world * args.steps),
@@ -345,7 +350,10 @@ def main():
         "gpu_launches": launches_all,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": ach_gbs_gpu, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": ach_gbs_gpu / hbm_peak, "traffic": None, "peak_source": peak_src,
+                     "frac": ach_gbs_gpu / hbm_peak,
+                     "traffic": NCU_TRAFFIC_BYTES.get((bool((opts.dcost if opts.dcost is not None else 1e-5) > 0), B, nt)) if traj else None,
+                     "traffic_source": "profiles/r01_ncu_ascent_ipm_kernel_metrics.csv (one launch, bytes)",
+                     "peak_source": peak_src,
                      "kernel": "ascent_ipm_kernel", "algorithmic_bytes_per_stage_iter": BYTE_PER_STAGE,
                      "fp64": {"achieved_gflops": ach_gf_gpu, "peak_gflops": fp64_peak, "frac": ach_gf_gpu / fp64_peak,
                               "algorithmic_flop_per_stage_iter": FLOP_PER_STAGE,
