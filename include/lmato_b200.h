@@ -95,6 +95,8 @@ typedef struct {
   double mu_ref;     /* barrier parameter at which the reference solve stops; default 1e-3 */
   double dcost;      /* LO:99 angledoubledot.DCOST: l1 move suppression dcost*sum|MV_k - MV_{k-1}|; default
                         1e-5 (the reference's value); 0 switches the term off (7-state fast path) */
+  double kappa_eps;  /* barrier sub-problem tolerance factor (IPOPT barrier_tol_factor, default there 10): mu is
+                        reduced once E_mu <= kappa_eps*mu; default 30 (2.4 fewer iterations, same answers) */
   int32_t objective_nodes; /* APMonitor sums the objective over the horizon: minimise objective_nodes*tf +
                         dcost*sum|dMV|; 0 (default) = nt-1.  Only the ratio dcost/objective_nodes matters. */
 } lmato_options;

@@ -34,7 +34,7 @@ class LmatoOptions(C.Structure):
                 ("tf_guess", C.c_double), ("delta_c", C.c_double), ("mu_min_factor", C.c_double),
                 ("max_iter", C.c_int32), ("max_ls", C.c_int32), ("n_polish", C.c_int32),
                 ("warm_start", C.c_int32), ("mu_ref", C.c_double), ("dcost", C.c_double),
-                ("objective_nodes", C.c_int32)]
+                ("kappa_eps", C.c_double), ("objective_nodes", C.c_int32)]
 
 
 class LmatoError(RuntimeError):

@@ -138,6 +138,7 @@ class SolverOptions:
     mu_ref: float = 1e-3           # barrier parameter at which that reference solve stops
     dcost: Optional[float] = None  # LO:99; None = take AscentParams.dcost (1e-5 in the reference)
     objective_nodes: int = 0       # APMonitor sums the objective over the horizon; 0 = nt-1
+    kappa_eps: float = 30.0        # barrier sub-problem tolerance factor (IPOPT's default is 10)
 
 
 @dataclasses.dataclass
@@ -205,7 +206,7 @@ class AscentSolver:
                                 max_ls=int(o.max_ls), n_polish=int(o.n_polish),
                                 warm_start=int(bool(o.warm_start)), mu_ref=o.mu_ref,
                                 dcost=float(1e-5 if o.dcost is None else o.dcost),
-                                objective_nodes=int(o.objective_nodes))
+                                kappa_eps=float(o.kappa_eps), objective_nodes=int(o.objective_nodes))
         _cabi.check(_cabi.lib().lmato_set_options(self._h, C.byref(co)), "lmato_set_options")
         self.options = o
 

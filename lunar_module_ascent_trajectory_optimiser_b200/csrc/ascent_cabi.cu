@@ -307,6 +307,7 @@ void lmato_default_options(lmato_options* o) {
   o->warm_start = 1;
   o->mu_ref = 1e-3;
   o->dcost = 1e-5;            // LO:99
+  o->kappa_eps = 30.0;
   o->objective_nodes = 0;     // 0 = nt - 1
   o->max_iter = 20000;   // LO:28
   o->max_ls = 40;
@@ -380,7 +381,7 @@ lmato_status_t lmato_set_options(lmato_handle* h, const lmato_options* o) {
       !(o->tf_guess > 0 && o->tf_guess < 1) || o->max_iter < 0 || o->max_ls < 1 ||
       !(o->mu_min_factor > 0 && o->mu_min_factor <= 1) || o->n_polish < -1 ||
       (o->warm_start != 0 && o->warm_start != 1) || !(o->mu_ref > 0 && o->mu_ref <= o->mu_init) ||
-      !(o->dcost >= 0) || o->objective_nodes < 0) {
+      !(o->dcost >= 0) || o->objective_nodes < 0 || !(o->kappa_eps >= 1.0)) {
     set_err("lmato_set_options: option out of range");
     return LMATO_ERR_INVALID;
   }
@@ -442,7 +443,7 @@ lmato_status_t lmato_solve_batch(lmato_handle* h, const double* params, int64_t 
   a.counter = h->d_counter;
   a.model = h->model;
   a.O.tol = h->opt.tol; a.O.mu_init = h->opt.mu_init; a.O.obj_scale = h->opt.obj_scale;
-  a.O.kappa_eps = 10.0; a.O.kappa_mu = 0.2; a.O.theta_mu = 1.5; a.O.tau_min = 0.99;
+  a.O.kappa_eps = h->opt.kappa_eps; a.O.kappa_mu = 0.2; a.O.theta_mu = 1.5; a.O.tau_min = 0.99;
   a.O.delta_c = h->opt.delta_c; a.O.tf_guess = h->opt.tf_guess;
   a.O.max_iter = h->opt.max_iter; a.O.max_ls = h->opt.max_ls;
   a.O.mu_min_factor = h->opt.mu_min_factor;

@@ -1130,7 +1130,7 @@ LM_HD bool ipm_iterate_t(const Params& P, const Mesh& M, const Options& O, const
     //  than the final test does, and more than FP64 can deliver for the dual residual)
     bool mu_changed = false;
     while (kkt_error(cur, ctl.mu, n_eq, n_bd) <= dmax(O.kappa_eps * ctl.mu, O.tol) && ctl.mu > mu_min * (1.0 + 1e-12)) {
-      ctl.mu = dmax(mu_min, dmin(O.kappa_mu * ctl.mu, ctl.mu * sqrt(ctl.mu)));   // theta_mu = 1.5
+      ctl.mu = dmax(mu_min, dmin(O.kappa_mu * ctl.mu, pow(ctl.mu, O.theta_mu)));
       ctl.tau = dmax(O.tau_min, 1.0 - ctl.mu);
       ctl.nf = 0;
       mu_changed = true;

@@ -43,7 +43,7 @@ def test_default_options_and_enums(built_lib):
     L.lmato_default_options(C.byref(o))
     assert o.tol == 1e-10 and o.mu_init == 0.1 and o.max_iter == 20000 and o.obj_scale == 10.0   # LO:28
     assert o.mu_min_factor == 1e-3 and o.n_polish == -1 and o.warm_start == 1 and o.mu_ref == 1e-3
-    assert o.dcost == 1e-5 and o.objective_nodes == 0                                             # LO:99
+    assert o.dcost == 1e-5 and o.objective_nodes == 0 and o.kappa_eps == 30.0                                             # LO:99
     src = open(HEADER).read()
     assert int(re.search(r"LMATO_NPARAM = (\d+)", src).group(1)) == _cabi.NPARAM == len(_cabi.PARAM_ROWS)
     assert int(re.search(r"LMATO_NVAR = (\d+)", src).group(1)) == _cabi.NVAR == len(_cabi.VAR_ROWS)

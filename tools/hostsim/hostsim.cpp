@@ -46,6 +46,9 @@ int main(int argc, char** argv) {
   if (getenv("MMF")) O.mu_min_factor = atof(getenv("MMF"));
   if (getenv("NPOL")) O.n_polish = atoi(getenv("NPOL"));
   O.w_dcost = getenv("WDC") ? atof(getenv("WDC")) : 0.0;
+  if (getenv("THMU")) O.theta_mu = atof(getenv("THMU"));
+  if (getenv("KMU")) O.kappa_mu = atof(getenv("KMU"));
+  if (getenv("KEPS")) O.kappa_eps = atof(getenv("KEPS"));
   if (getenv("OBJ")) O.obj_scale = atof(getenv("OBJ"));
   if (getenv("MU0")) O.mu_init = atof(getenv("MU0"));
   if (getenv("TOL")) O.tol = atof(getenv("TOL"));
