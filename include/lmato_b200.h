@@ -149,6 +149,15 @@ lmato_status_t lmato_last_kernel_ms(lmato_handle* h, double* ms);
  * micro-benchmark; used as the roofline denominator, MEASURED_PEAKS.json has no FP64). */
 lmato_status_t lmato_measure_fp64_peak(lmato_handle* h, double* gflops);
 
+/* Post-solve orbit check (reference PDF p.28-29 src 185-237): coast each state around the Moon with the PDF's
+ * explicit Euler scheme (a from the current position; position += old velocity*dt; velocity += a*dt).
+ *   state [4][B]  x, y, vx, vy   SI, Moon-centred (device pointer)
+ *   gm            Gs*m_2 (PDF src 186-188: 6.67e-11 * 7.346e22), dt (PDF: 0.001), nsteps (PDF: 6600/dt)
+ *   out   [6][B]  r_min, r_max over the coast, then the final x, y, vx, vy (device pointer)
+ * Asynchronous on `stream`. */
+lmato_status_t lmato_coast_orbit(lmato_handle* h, const double* state, int64_t B, double gm, double dt,
+                                 int64_t nsteps, double* out, void* stream);
+
 /* Device self-test of the solver's branch-free FP64 math (rcp, rsqrt, log, sin, cos) against the
  * CUDA math library: max_err5 = {rel rcp, rel rsqrt, rel log, abs sin, abs cos}. */
 lmato_status_t lmato_selftest_math(lmato_handle* h, double* max_err5);

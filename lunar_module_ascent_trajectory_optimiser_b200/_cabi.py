@@ -86,9 +86,10 @@ def lib() -> C.CDLL:
     L.lmato_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_double)]
     L.lmato_measure_fp64_peak.argtypes = [vp, C.POINTER(C.c_double)]
     L.lmato_selftest_math.argtypes = [vp, C.POINTER(C.c_double)]
+    L.lmato_coast_orbit.argtypes = [vp, vp, i64, C.c_double, C.c_double, i64, vp, vp]
     for name in ("lmato_create", "lmato_destroy", "lmato_set_options", "lmato_solve_batch",
                  "lmato_solve_batch_host", "lmato_workspace_bytes", "lmato_kernel_launches",
-                 "lmato_last_kernel_ms", "lmato_measure_fp64_peak", "lmato_selftest_math"):
+                 "lmato_last_kernel_ms", "lmato_measure_fp64_peak", "lmato_selftest_math", "lmato_coast_orbit"):
         getattr(L, name).restype = C.c_int
     _lib = L
     return L
@@ -97,7 +98,7 @@ def lib() -> C.CDLL:
 EXPORTED_SYMBOLS = ["lmato_default_options", "lmato_create", "lmato_destroy", "lmato_set_options",
                     "lmato_solve_batch", "lmato_solve_batch_host", "lmato_workspace_bytes",
                     "lmato_kernel_launches", "lmato_last_kernel_ms", "lmato_measure_fp64_peak",
-                    "lmato_selftest_math", "lmato_last_error", "lmato_version"]
+                    "lmato_selftest_math", "lmato_coast_orbit", "lmato_last_error", "lmato_version"]
 
 
 def check(rc: int, what: str) -> None:

@@ -292,6 +292,24 @@ class AscentSolver:
         _cabi.check(_cabi.lib().lmato_measure_fp64_peak(self._h, C.byref(g)), "lmato_measure_fp64_peak")
         return g.value
 
+    def coast_orbit(self, state: torch.Tensor, t_coast: float = 6600.0, dt: float = 1e-3,
+                    gm: float = 6.67e-11 * 7.346e22) -> Dict[str, torch.Tensor]:
+        """The reference PDF's post-solve orbit check (p.28-29 src 185-237), batched: explicit Euler coast of
+        ``state`` ``[4, B]`` = x, y, vx, vy (SI, Moon-centred, CUDA float64) for ``t_coast`` seconds.  Returns the
+        extreme radii seen and the final state."""
+        if not state.is_cuda or state.dtype != torch.float64 or state.dim() != 2 or state.shape[0] != 4:
+            raise ValueError("state must be a CUDA float64 tensor of shape [4, B]")
+        state = state.contiguous()
+        B = int(state.shape[1])
+        out = torch.empty((6, B), dtype=torch.float64, device=self.device)
+        nsteps = int(round(t_coast / dt))
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            _cabi.check(_cabi.lib().lmato_coast_orbit(self._h, C.c_void_p(state.data_ptr()), B, float(gm), float(dt),
+                                                      nsteps, C.c_void_p(out.data_ptr()), C.c_void_p(stream)),
+                        "lmato_coast_orbit")
+        return {"r_min": out[0], "r_max": out[1], "final_state": out[2:6]}
+
     def selftest_math(self):
         e = (C.c_double * 5)()
         _cabi.check(_cabi.lib().lmato_selftest_math(self._h, e), "lmato_selftest_math")
@@ -386,6 +404,15 @@ def sharded_solve(rows: torch.Tensor, solve_fn: Callable[[torch.Tensor], Dict[st
             out[k] = full[:, c].to(v.dtype)
         c += w
     return out
+
+
+def final_state_si(sol: AscentBatchSolution, params: AscentParams) -> torch.Tensor:
+    """Final ascent state in the PDF's plotting frame (src 189-192): ``[4, B]`` = (-x*S, y*S+R0, -xdot*S, ydot*S)."""
+    B = len(sol)
+    rows = params.rows(B, device=sol.tf.device)
+    S, R0 = rows[_cabi.PARAM_ROWS.index("r_periapsis")], rows[_cabi.PARAM_ROWS.index("R0")]
+    st = sol.states
+    return torch.stack([-st["x"][:, -1] * S, st["y"][:, -1] * S + R0, -st["xdot"][:, -1] * S, st["ydot"][:, -1] * S])
 
 
 # ---------------------------------------------------------------------------------------

@@ -246,6 +246,31 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters) 
   out[(long)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
+// Post-solve orbit check of the reference PDF (p.28-29 src 185-237): explicit Euler two-body coast,
+// one problem per thread, everything in registers.  state/out: [4][B] / [6][B], SI, Moon-centred.
+__global__ void __launch_bounds__(128) coast_orbit_kernel(const double* __restrict__ state, long B, double gm,
+                                                          double dt, long nsteps, double* __restrict__ out) {
+  const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double x = state[0 * B + b], y = state[1 * B + b], vx = state[2 * B + b], vy = state[3 * B + b];
+  double r2 = fma(x, x, y * y);
+  double r2min = r2, r2max = r2;
+  for (long i = 0; i < nsteps; ++i) {
+    const double inv = lm_rsqrt(r2);
+    const double k = gm * inv * inv * inv;
+    const double ax = -k * x, ay = -k * y;            // src 207-208
+    x = fma(vx, dt, x);                               // src 231-232 (old velocity)
+    y = fma(vy, dt, y);
+    vx = fma(ax, dt, vx);                             // src 233-234
+    vy = fma(ay, dt, vy);
+    r2 = fma(x, x, y * y);
+    r2min = fmin(r2min, r2);
+    r2max = fmax(r2max, r2);
+  }
+  out[0 * B + b] = sqrt(r2min); out[1 * B + b] = sqrt(r2max);
+  out[2 * B + b] = x; out[3 * B + b] = y; out[4 * B + b] = vx; out[5 * B + b] = vy;
+}
+
 // Self-test of the branch-free math against the CUDA library: max relative errors of
 // rcp, rsqrt, log over [1e-40, 1e3] and max absolute errors of sin, cos over [0, 3.5].
 __global__ void math_selftest_kernel(double* out, int n) {
@@ -536,6 +561,19 @@ lmato_status_t lmato_solve_batch_host(lmato_handle* h, const double* params, int
   CUDA_TRY(cudaMemcpyAsync(out_status, d_st, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaMemcpyAsync(out_iters, d_it, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
+  return LMATO_OK;
+}
+
+lmato_status_t lmato_coast_orbit(lmato_handle* h, const double* state, int64_t B, double gm, double dt,
+                                 int64_t nsteps, double* out, void* stream) {
+  if (!h || B < 0 || nsteps < 0 || !(dt > 0) || !(gm > 0)) { set_err("lmato_coast_orbit: bad argument"); return LMATO_ERR_INVALID; }
+  if (B == 0) return LMATO_OK;
+  if (!state || !out) { set_err("lmato_coast_orbit: NULL buffer"); return LMATO_ERR_INVALID; }
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  coast_orbit_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(state, (long)B, gm, dt, (long)nsteps, out);
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 1;
   return LMATO_OK;
 }
 

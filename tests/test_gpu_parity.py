@@ -303,3 +303,38 @@ def test_dcost_matches_golden(lm, golden_dir):
     w = np.abs(_traj(nod, 0)[7] - g["traj"][0][7]).max() / np.abs(g["traj"][0][7]).max()
     assert w > 1e-3
     assert abs(float(nod.tf[0]) - float(sol.tf[0])) / float(sol.tf[0]) < 1e-7      # ... while tf barely moves
+
+
+def test_coast_orbit_matches_pdf_propagator(lm):
+    """Section 8(f).3: the PDF's explicit-Euler coast (p.28-29 src 185-237), batched.  Parity with the numpy
+    restatement over 20 000 steps, then the full 6600 s / 0.001 s coast checked against the two-body
+    (vis-viva) prediction.  Physics note: the script's speed target is the circular speed at the MEAN radius
+    (LO:75-78), which is below the circular speed at the insertion radius, so the insertion point is the
+    apolune of the coasted orbit and its perilune lies below the surface (~ -48 km for the nominal case);
+    the circular IB-document model coasts on a near-circular orbit instead."""
+    from oracle.coast_reference import coast, GS_PDF, M2_PDF
+    p = lm.dispersed_params(64, seed=11)
+    sol = lm.optimise_batch(p, device=0)
+    assert bool(sol.converged.all())
+    solver = lm.AscentSolver(lm.Mesh(), lm.SolverOptions(), device=0)
+    state = lm.final_state_si(sol, p).cuda()
+    short = solver.coast_orbit(state, t_coast=20.0, dt=1e-3)
+    rmin, rmax, fin = coast(state.cpu().numpy(), 20000, 1e-3)
+    assert np.allclose(short["final_state"].cpu().numpy(), fin, rtol=1e-11, atol=1e-6)
+    assert np.allclose(short["r_min"].cpu().numpy(), rmin, rtol=1e-12) and np.allclose(short["r_max"].cpu().numpy(), rmax, rtol=1e-12)
+    full = solver.coast_orbit(state, t_coast=6600.0, dt=1e-3)
+    torch.cuda.synchronize()
+    st = state.cpu().numpy()
+    gm = GS_PDF * M2_PDF
+    r0 = np.hypot(st[0], st[1])
+    v2 = st[2] ** 2 + st[3] ** 2
+    a = -gm / (2.0 * (0.5 * v2 - gm / r0))                    # vis-viva
+    d = full["r_max"].cpu().numpy() - r0                                     # insertion point = apolune;
+    assert np.all(d >= 0) and np.all(d < 80.0)                               # explicit Euler gains ~20 m per orbit
+    assert np.all(np.abs(full["r_min"].cpu().numpy() - (2.0 * a - r0)) < 300.0)
+    assert abs(float(full["r_min"][0]) - 1738100.0 - (-48.5e3)) < 1.5e3       # nominal: perilune below the surface
+    # circular IB-document model: near-circular orbit at 53.1 km
+    c = lm.optimise_batch(lm.AscentParams.circular(), batch=1, device=0)
+    cst = lm.final_state_si(c, lm.AscentParams.circular()).cuda()
+    cf = solver.coast_orbit(cst, t_coast=6600.0, dt=1e-3)
+    assert abs(float(cf["r_max"][0]) - 1738100.0 - 53108.4) < 5.0e3 and abs(float(cf["r_min"][0]) - 1738100.0 - 53108.4) < 5.0e3
