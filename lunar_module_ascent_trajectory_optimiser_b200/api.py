@@ -134,7 +134,7 @@ class SolverOptions:
     max_ls: int = 40
     mu_min_factor: float = 1e-3    # barrier floor = mu_min_factor * tol
     n_polish: int = -1             # Newton iterations after tol is first met; -1 = 2 with DCOST, 4 without
-    warm_start: bool = True        # batches >= 256: start from the batch-mean problem's central path
+    warm_start: bool = True        # batches >= 16384: start from the batch-mean problem's central path
     mu_ref: float = 1e-3           # barrier parameter at which that reference solve stops
     dcost: Optional[float] = None  # LO:99; None = take AscentParams.dcost (1e-5 in the reference)
     objective_nodes: int = 0       # APMonitor sums the objective over the horizon; 0 = nt-1

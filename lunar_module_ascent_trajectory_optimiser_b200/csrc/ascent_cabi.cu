@@ -45,6 +45,8 @@ void set_err(const char* fmt, const char* a = "", const char* b = "") {
 #endif
 constexpr int kBlock = 256;
 constexpr int kBlocksPerSM = 1;
+// The warm start costs one serial single-problem solve (~13 ms); measured break-even is ~8k problems.
+constexpr long kWarmStartMinBatch = 16384;
 
 struct KArgs {
   const double* params;  // [NPARAM][B]
@@ -480,7 +482,7 @@ lmato_status_t lmato_solve_batch(lmato_handle* h, const double* params, int64_t 
   a.ref = nullptr; a.ref_mode = 0;
   const int grid = (int)(slots / kBlock);
   CUDA_TRY(cudaEventRecord(h->ev0, st));
-  if (h->opt.warm_start && B >= 256) {
+  if (h->opt.warm_start && B >= kWarmStartMinBatch) {
     // reference problem = batch mean, solved down to mu_ref only (one thread, ~8 iterations)
     mean_params_kernel<<<LMATO_NPARAM, 256, 0, st>>>(params, B, h->d_refparams);
     CUDA_TRY(cudaGetLastError());
