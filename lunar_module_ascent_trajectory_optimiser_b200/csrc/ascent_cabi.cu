@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(kBlock, kBlocksPerSM) ascent_ipm_kernel(KArgs 
           P = derive_params(a.params, a.B, b, a.model);
           ipm_begin(O, S);
           double mu0 = 0.0;
-          if (a.ref_mode == 2 && SW::load_ref(P, M, W, a.ref, S.cur, &mu0)) {
+          if (a.ref_mode == 2 && SW::load_ref(P, M, O, W, a.ref, S.cur, &mu0)) {
             S.warm = true;
             S.ctl.mu = mu0;
             S.ctl.tau = dmax(O.tau_min, 1.0 - mu0);
@@ -492,8 +492,8 @@ lmato_status_t lmato_solve_batch(lmato_handle* h, const double* params, int64_t 
     r.status = (int*)(scratch + 2); r.iters = (int*)(scratch + 3); r.kkt = scratch + 4;
     r.ref = h->d_ref; r.ref_mode = 1;
     r.O.tol = 10.0 * h->opt.mu_ref; r.O.mu_min_factor = 0.1; r.O.n_polish = 0;
-    if (use_dc) ascent_ipm_kernel<Sweeps8><<<1, kBlock, 0, st>>>(r);
-    else ascent_ipm_kernel<Sweeps7><<<1, kBlock, 0, st>>>(r);
+    r.O.w_dcost = 0.0;     // always the 7-state solve: cheaper, and at mu_ref >> w the move term is immaterial
+    ascent_ipm_kernel<Sweeps7><<<1, kBlock, 0, st>>>(r);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemsetAsync(h->d_counter, 0, sizeof(int), st));
     a.ref = h->d_ref; a.ref_mode = 2;

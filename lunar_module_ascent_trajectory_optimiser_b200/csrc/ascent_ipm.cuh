@@ -1108,7 +1108,8 @@ struct Sweeps7 {
   LM_HD static void guess(const Params& P, const Mesh& M, const Options& O, const Ws& W, Scal& s) { init_guess(P, M, O, W, s); }
   LM_HD static void store_ref(const Params& P, const Mesh& M, const Ws& W, int src, const Scal& c, double mu, bool ok,
                               double* ref) { ref_store(P, M, W, src, c, mu, ok, ref); }
-  LM_HD static bool load_ref(const Params& P, const Mesh& M, const Ws& W, const double* ref, Scal& s, double* mu) {
+  LM_HD static bool load_ref(const Params& P, const Mesh& M, const Options&, const Ws& W, const double* ref, Scal& s,
+                             double* mu) {
     return init_from_ref(P, M, W, ref, s, mu);
   }
   LM_HD static void remerit(const Mesh&, const Options&, const Ws&, int, double, Scal&) {}

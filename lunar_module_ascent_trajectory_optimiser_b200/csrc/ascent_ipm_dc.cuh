@@ -181,6 +181,51 @@ LM_NOINLINE bool init_from_ref(const Params& P, const Mesh& M, const Ws& W, cons
   return true;
 }
 
+// Start from a reference column produced by the (cheaper) 7-state solve of the batch-mean problem without
+// the move term: at mu_ref ~ 1e-3 >> w the two central paths practically coincide.  The slack pair is put
+// exactly on its own central path for the reference's moves (z_p + z_n = 2w, p z_p = n z_n = mu) and the
+// multiplier of the u row follows from dual feasibility, lam_6 = w - z_p.
+LM_NOINLINE bool init_from_ref7(const Params& P, const Mesh& M, const Options& O, const Ws& W, const double* ref,
+                                Scal& s, double* mu_out) {
+  const int N1 = M.N + 1;
+  const int NI7 = lmato::N_ITER;                       // 17 rows in the 7-state layout
+  const double* sc = ref + NI7 * N1;
+  if (!(sc[REF_OK] > 0.5)) return false;
+  const double r = sc[REF_S] * P.Sinv, ri = P.S / sc[REF_S];
+  const double mu = sc[REF_MU], w = O.w_dcost;
+  {
+    double* s0 = W.stage(0);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { WS_AT(s0, F_Z + i) = 0.0; WS_AT(s0, N_ITER + F_Z + i) = 0.0; WS_AT(s0, F_DS + i) = 0.0; }
+    WS_AT(s0, F_U) = 0.0; WS_AT(s0, N_ITER + F_U) = 0.0; WS_AT(s0, F_DU) = 0.0;
+  }
+  double u_prev = 0.0;
+  for (int k = 1; k <= M.N; ++k) {
+    double* sp = W.stage(k);
+#pragma unroll
+    for (int f = 0; f < 7; ++f) WS_AT(sp, f) = ref[f * N1 + k] * (f < 4 ? r : 1.0);                 // states, u
+#pragma unroll
+    for (int i = 0; i < 6; ++i) WS_AT(sp, F_LAM + i) = ref[(lmato::F_LAM + i) * N1 + k] * (i < 4 ? ri : 1.0);
+    WS_AT(sp, F_ZLA) = ref[lmato::F_ZLA * N1 + k]; WS_AT(sp, F_ZUA) = ref[lmato::F_ZUA * N1 + k];
+    WS_AT(sp, F_ZLU) = ref[lmato::F_ZLU * N1 + k]; WS_AT(sp, F_ZUU) = ref[lmato::F_ZUU * N1 + k];
+    const double u = ref[lmato::F_U * N1 + k];
+    const double v = u - u_prev;
+    const double tt = (mu + sqrt(mu * mu + w * w * v * v)) / w;
+    const double pp = 0.5 * (tt + v), pn = 0.5 * (tt - v);
+    WS_AT(sp, F_PP) = pp; WS_AT(sp, F_PN) = pn;
+    WS_AT(sp, F_ZPP) = mu / pp; WS_AT(sp, F_ZPN) = mu / pn;
+    WS_AT(sp, F_LAM + 6) = w - mu / pp;
+#pragma unroll
+    for (int i = 0; i < N_STEP; ++i) WS_AT(sp, R_STEP + i) = 0.0;
+    u_prev = u;
+  }
+  s.tf = dmin(sc[REF_TF], 0.99 * P.tf_ub);
+  s.zLt = sc[REF_ZLT]; s.zUt = sc[REF_ZUT];
+  s.sg1 = sc[REF_SG1]; s.sg2 = sc[REF_SG2]; s.zs1 = sc[REF_ZS1]; s.zs2 = sc[REF_ZS2]; s.nu3 = sc[REF_NU3];
+  *mu_out = mu;
+  return true;
+}
+
 // ---------------------------------------------------------------------------------------
 // evaluation pass (see ascent_ipm.cuh: eval_pass); differences: u is a state of the node, the u row
 // and its multiplier lam_6, the move slack pair (p, n, z_p, z_n) in the merit and the residuals.
@@ -780,8 +825,9 @@ struct Sweeps8 {
   LM_HD static void guess(const Params& P, const Mesh& M, const Options& O, const Ws& W, Scal& s) { dc::init_guess(P, M, O, W, s); }
   LM_HD static void store_ref(const Params& P, const Mesh& M, const Ws& W, int src, const Scal& c, double mu, bool ok,
                               double* ref) { dc::ref_store(P, M, W, src, c, mu, ok, ref); }
-  LM_HD static bool load_ref(const Params& P, const Mesh& M, const Ws& W, const double* ref, Scal& s, double* mu) {
-    return dc::init_from_ref(P, M, W, ref, s, mu);
+  LM_HD static bool load_ref(const Params& P, const Mesh& M, const Options& O, const Ws& W, const double* ref,
+                             Scal& s, double* mu) {
+    return dc::init_from_ref7(P, M, O, W, ref, s, mu);      // the reference is produced by the 7-state solve
   }
   LM_HD static void remerit(const Mesh&, const Options&, const Ws&, int, double, Scal&) {}
 };
