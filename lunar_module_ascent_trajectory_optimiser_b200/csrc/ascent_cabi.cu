@@ -45,6 +45,7 @@ void set_err(const char* fmt, const char* a = "", const char* b = "") {
 #endif
 constexpr int kBlock = 256;
 constexpr int kBlocksPerSM = 1;
+constexpr size_t kTileSmem = (size_t)(kBlock / 32) * 2 * TILE_ROWS * LANES * sizeof(double);   // 147 456 B
 // The warm start costs one serial single-problem solve (~13 ms); measured break-even is ~8k problems.
 constexpr long kWarmStartMinBatch = 16384;
 
@@ -140,7 +141,15 @@ __global__ void __launch_bounds__(kBlock, kBlocksPerSM) ascent_ipm_kernel(KArgs 
   const long slot = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   const long nwarps = a.slots / LANES;
-  const Ws W{a.ws + ((slot / LANES) * SW::NFIELDS) * LANES + lane, nwarps * SW::NFIELDS * LANES};
+  // staging tiles: [warp][2 buffers][TILE_ROWS][32 lanes] doubles of dynamic shared memory
+  extern __shared__ __align__(16) double sTiles[];
+  const unsigned tile0 = (unsigned)__cvta_generic_to_shared(sTiles) +
+                         (unsigned)(((threadIdx.x / 32) * 2 * TILE_ROWS * LANES + lane) * sizeof(double));
+  // the workspace view is read inside every stage of the noinline sweeps: shared memory, not the
+  // local-memory stack (24-byte stride: conflict-free per half warp)
+  __shared__ Ws sW[kBlock];
+  sW[threadIdx.x] = Ws{a.ws + ((slot / LANES) * SW::NFIELDS) * LANES + lane, nwarps * SW::NFIELDS * LANES, tile0};
+  const Ws& W = sW[threadIdx.x];
   const int nt = a.N + 1;
   IpmState S;
   bool active = false;        // this lane holds an unfinished problem
@@ -378,6 +387,9 @@ lmato_status_t lmato_create(lmato_handle** out, int32_t device, int32_t nt, cons
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   H->sm_count = prop.multiProcessorCount;
+  // the staging tiles need the opt-in shared-memory size (147 KB dynamic + 39 KB static per CTA)
+  CUDA_TRY(cudaFuncSetAttribute(ascent_ipm_kernel<Sweeps7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmem));
+  CUDA_TRY(cudaFuncSetAttribute(ascent_ipm_kernel<Sweeps8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmem));
   CUDA_TRY(cudaMalloc(&H->d_h, sizeof(double) * nt));
   CUDA_TRY(cudaMalloc(&H->d_tau, sizeof(double) * nt));
   CUDA_TRY(cudaMemcpy(H->d_h, h.data(), sizeof(double) * nt, cudaMemcpyHostToDevice));
@@ -493,14 +505,14 @@ lmato_status_t lmato_solve_batch(lmato_handle* h, const double* params, int64_t 
     r.ref = h->d_ref; r.ref_mode = 1;
     r.O.tol = 10.0 * h->opt.mu_ref; r.O.mu_min_factor = 0.1; r.O.n_polish = 0;
     r.O.w_dcost = 0.0;     // always the 7-state solve: cheaper, and at mu_ref >> w the move term is immaterial
-    ascent_ipm_kernel<Sweeps7><<<1, kBlock, 0, st>>>(r);
+    ascent_ipm_kernel<Sweeps7><<<1, kBlock, kTileSmem, st>>>(r);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemsetAsync(h->d_counter, 0, sizeof(int), st));
     a.ref = h->d_ref; a.ref_mode = 2;
     h->launches += 2;
   }
-  if (use_dc) ascent_ipm_kernel<Sweeps8><<<grid, kBlock, 0, st>>>(a);
-  else ascent_ipm_kernel<Sweeps7><<<grid, kBlock, 0, st>>>(a);
+  if (use_dc) ascent_ipm_kernel<Sweeps8><<<grid, kBlock, kTileSmem, st>>>(a);
+  else ascent_ipm_kernel<Sweeps7><<<grid, kBlock, kTileSmem, st>>>(a);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaEventRecord(h->ev1, st));
   h->last_stream = st; h->timed = true;

@@ -80,40 +80,86 @@ struct Mesh {
   const double* tau;     // tau[k] = time[k]
 };
 
+// Staging tiles in shared memory (below): the handle is a shared-space byte address on the device and a
+// plain pointer in the host build of these headers (tools/hostsim).
+constexpr int TILE_DATA = 36;                       // largest set of workspace rows a stage of any sweep reads
+constexpr int TL_H = TILE_DATA, TL_TAU = TILE_DATA + 1;   // + the mesh step h[k] and the node time tau[k]
+constexpr int TILE_ROWS = TILE_DATA + 2;
+#if defined(__CUDA_ARCH__)
+typedef unsigned TileRef;
+#else
+typedef double* TileRef;
+#endif
+
 // View of one thread's column of the workspace.
 struct Ws {
   double* p;             // base + (warp * N_FIELDS) * 32 + lane
   long SS;               // stage stride in doubles = n_warps * N_FIELDS * 32
+  TileRef tl;            // this lane's column of the warp's two staging tiles
   LM_HD double* stage(int k) const { return p + (long)k * SS; }
 };
 #define WS_AT(sp, row) (sp)[(row) * LANES]
 
-// Software prefetch of workspace rows into L1.  The sweeps are latency-bound otherwise: with 255
-// registers per thread only 8 warps are resident per SM, far too few to hide an HBM round trip
-// per stage.  A prefetch costs no registers; issued PF_DIST stages ahead it turns the dependent
-// load at the top of each stage into an L1 hit.
-#ifndef LMATO_PF_DIST
-#define LMATO_PF_DIST 1
-#endif
-#ifndef LMATO_PF_LEVEL
-#define LMATO_PF_LEVEL 1
-#endif
-constexpr int PF_DIST = LMATO_PF_DIST;
-LM_HD void pf_row(const double* sp, int row) {
+// Staging of workspace rows in shared memory.  With 255 registers per thread only 8 warps are
+// resident per SM, far too few to hide a memory round trip per stage, and eight warps' stage
+// footprints thrash L1 (a software prefetch into L1 ended with a 1 % hit rate).  Instead every lane
+// copies the rows of its own column that the NEXT stage reads into a per-warp double buffer with
+// cp.async (LDGSTS: no registers, and no warp-level synchronisation, because a lane only ever reads
+// what it copied itself), commits one group per stage and waits for all but the newest group before
+// it consumes a tile.  The loads of the stage body are then shared-memory loads.
+// Tile of stage k lives in buffer k & 1.
+LM_HD TileRef tl_buf(const Ws& W, int k) {
 #if defined(__CUDA_ARCH__)
-#if LMATO_PF_LEVEL == 1
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(sp + row * LANES));
-#elif LMATO_PF_LEVEL == 2
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(sp + row * LANES));
-#endif
+  return W.tl + (unsigned)(k & 1) * (unsigned)(TILE_ROWS * LANES * 8);
 #else
-  (void)sp; (void)row;
+  return W.tl + (k & 1) * TILE_ROWS;
 #endif
 }
-template <int R0, int R1>
-LM_HD void pf_rows(const double* sp, int base) {
+LM_HD void tl_copy(TileRef tb, int slot, const double* src) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(tb + (unsigned)(slot * LANES * 8)), "l"(src) : "memory");
+#else
+  tb[slot] = *src;
+#endif
+}
+// rows [row0, row0 + NROWS) of the stage column sp -> slots [SLOT0, SLOT0 + NROWS)
+template <int SLOT0, int NROWS>
+LM_HD void tl_copy_rows(TileRef tb, const double* sp, int row0) {
 #pragma unroll
-  for (int r = R0; r < R1; ++r) pf_row(sp, base + r);
+  for (int r = 0; r < NROWS; ++r) tl_copy(tb, SLOT0 + r, sp + (row0 + r) * LANES);
+}
+// h[k], tau[k]: every lane stages its own copy (same address across the warp: one sector)
+LM_HD void tl_copy_mesh(TileRef tb, const Mesh& M, int k) {
+  tl_copy(tb, TL_H, M.h + k);
+  tl_copy(tb, TL_TAU, M.tau + k);
+}
+LM_HD void tl_commit() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+// all groups but the newest have landed
+LM_HD void tl_wait_prev() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.wait_group 1;" ::: "memory");
+#endif
+}
+// start of a sweep: the rows about to be copied were written by this thread's own stores
+LM_HD void tl_begin() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __threadfence_block();
+#endif
+}
+LM_HD double tl_ld(TileRef tb, int slot) {
+#if defined(__CUDA_ARCH__)
+  double v;
+  // volatile keeps it after the wait (volatile asms are not reordered among themselves)
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(tb + (unsigned)(slot * LANES * 8)));
+  return v;
+#else
+  return tb[slot];
+#endif
 }
 
 constexpr int NFILT = 12;
@@ -501,16 +547,58 @@ LM_NOINLINE bool init_from_ref(const Params& P, const Mesh& M, const Ws& W, cons
 //                   per stage never travel through HBM.
 // mode EV_LSQ     : same recursion for the least-squares multiplier estimate (Q = I).
 // ---------------------------------------------------------------------------------------
+// Staging tiles of the 7-state sweeps (tl_* above): "CUR" = rows F_U .. N_ITER-1 of the source iterate at
+// stage k (control, multipliers), "PZ"/"PDS" = state and its step at stage k-1.
+enum : int {
+  N_CUR = N_ITER - F_U,                            // 11
+  EV_CUR = 0, EV_DU = EV_CUR + N_CUR, EV_PI = EV_DU + 1, EV_PZ = EV_PI + 6, EV_PDS = EV_PZ + 6, EV_ROWS = EV_PDS + 6,
+  BK_CUR = 0, BK_PZ = BK_CUR + N_CUR, BK_ROWS = BK_PZ + 6,
+  FW_Z = 0, FW_ZB = FW_Z + 7, FW_K = FW_ZB + (N_ITER - F_ZLA), FW_ROWS = FW_K + N_FACT
+};
+static_assert(EV_ROWS <= TILE_DATA && BK_ROWS <= TILE_DATA && FW_ROWS <= TILE_DATA, "tile too small");
+#define TL7_CUR(tb, base, f) tl_ld(tb, (base) + (f) - F_U)      // row f (>= F_U) of the source iterate
+
+LM_HD void ev7_stage_copy(const Mesh& M, const Ws& W, int k, int so, bool read_pi) {
+  const TileRef tb = tl_buf(W, k);
+  tl_copy_mesh(tb, M, k);
+  const double* sp = W.stage(k);
+  const double* sm = W.stage(k - 1);
+  tl_copy_rows<EV_CUR, N_CUR>(tb, sp, so + F_U);
+  tl_copy(tb, EV_DU, sp + F_DU * LANES);
+  if (read_pi) tl_copy_rows<EV_PI, 6>(tb, sp, F_PI);
+  tl_copy_rows<EV_PZ, 6>(tb, sm, so + F_Z);
+  tl_copy_rows<EV_PDS, 6>(tb, sm, F_DS);
+  tl_commit();
+}
+LM_HD void bk7_stage_copy(const Mesh& M, const Ws& W, int k, int so) {
+  const TileRef tb = tl_buf(W, k);
+  tl_copy_mesh(tb, M, k);
+  tl_copy_rows<BK_CUR, N_CUR>(tb, W.stage(k), so + F_U);
+  tl_copy_rows<BK_PZ, 6>(tb, W.stage(k - 1), so + F_Z);
+  tl_commit();
+}
+LM_HD void fw7_stage_copy(const Mesh& M, const Ws& W, int k, int so) {
+  const TileRef tb = tl_buf(W, k);
+  tl_copy_mesh(tb, M, k);
+  const double* sp = W.stage(k);
+  tl_copy_rows<FW_Z, 7>(tb, sp, so + F_Z);
+  tl_copy_rows<FW_ZB, N_ITER - F_ZLA>(tb, sp, so + F_ZLA);
+  tl_copy_rows<FW_K, N_FACT>(tb, sp, F_K);
+  tl_commit();
+}
+
 enum : int { EV_READ_PI = 0, EV_NEWTON = 1, EV_LSQ = 2 };
 
 LM_NOINLINE void eval_pass(const Params& P, const Mesh& M, const Options& O, const Ws& W, int src, int dst,
                            const Scal& c0, const TermStep& ts, double mu, double dw, double alpha,
                            double alpha_z, double alpha_lam, int mode, Scal& t, double* pimax_out) {
   const int N = M.N;
+  const int so = src * N_ITER, dd = dst * N_ITER;
+  tl_begin();
+  ev7_stage_copy(M, W, N, so, mode == EV_READ_PI);
   const double tf0 = c0.tf, dtf = ts.dtf;
   t.tf = tf0 + alpha * dtf;
   const double tf = t.tf;
-  const int so = src * N_ITER, dd = dst * N_ITER;
   const double mT = P.mflow * P.T;
   const bool ls = (mode == EV_LSQ);
   double theta = 0, prim = 0, dual = 0, sumlog = 0, cmin = 1e300, cmax = 0, slam = 0, sz = 0;
@@ -552,38 +640,28 @@ LM_NOINLINE void eval_pass(const Params& P, const Mesh& M, const Options& O, con
   double pi_next[6] = {0, 0, 0, 0, 0, 0};    // adjoint of node k+1
   for (int k = N; k >= 1; --k) {
     double* sp = W.stage(k);
-    if (k - PF_DIST >= 1) {            // rows this sweep will read PF_DIST stages from now
-      const double* pp = W.stage(k - PF_DIST);
-      pf_rows<F_U, N_ITER>(pp, so);                       // u, lam, bound multipliers
-      pf_row(pp, F_DU);
-      if (mode == EV_READ_PI) pf_rows<0, 6>(pp, F_PI);
-      if (k - PF_DIST - 1 >= 1) {
-        const double* pq = W.stage(k - PF_DIST - 1);
-        pf_rows<0, 6>(pq, so + F_Z);
-        pf_rows<0, 6>(pq, F_DS);
-      }
-    }
+    // stage the rows of the next stage, then wait for this stage's tile
+    if (k > 1) ev7_stage_copy(M, W, k - 1, so, mode == EV_READ_PI); else tl_commit();
+    tl_wait_prev();
+    const TileRef tb = tl_buf(W, k);
     double z[6], zpo[6], dsp[6], zp[6], lam[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i) z[i] = fma(alpha, ds[i], zo[i]);
-    {
-      const double* sm = W.stage(k - 1);          // node 0 rows are zeros
 #pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        zpo[i] = WS_AT(sm, so + F_Z + i); dsp[i] = WS_AT(sm, F_DS + i);
-        zp[i] = fma(alpha, dsp[i], zpo[i]);
-      }
+    for (int i = 0; i < 6; ++i) {                 // node k-1 (node 0 rows are zeros)
+      zpo[i] = tl_ld(tb, EV_PZ + i); dsp[i] = tl_ld(tb, EV_PDS + i);
+      zp[i] = fma(alpha, dsp[i], zpo[i]);
     }
-    const double u_old = WS_AT(sp, so + F_U);
-    const double du = WS_AT(sp, F_DU);
+    const double u_old = TL7_CUR(tb, EV_CUR, F_U);
+    const double du = tl_ld(tb, EV_DU);
     const double u = fma(alpha, du, u_old);
     double lam_old[6];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) lam_old[i] = WS_AT(sp, so + F_LAM + i);
-    double zla = WS_AT(sp, so + F_ZLA), zua = WS_AT(sp, so + F_ZUA);
-    double zlu = WS_AT(sp, so + F_ZLU), zuu = WS_AT(sp, so + F_ZUU);
-    const double kap = M.h[k] * P.T;
-    const double taum = mT * M.tau[k];
+    for (int i = 0; i < 6; ++i) lam_old[i] = TL7_CUR(tb, EV_CUR, F_LAM + i);
+    double zla = TL7_CUR(tb, EV_CUR, F_ZLA), zua = TL7_CUR(tb, EV_CUR, F_ZUA);
+    double zlu = TL7_CUR(tb, EV_CUR, F_ZLU), zuu = TL7_CUR(tb, EV_CUR, F_ZUU);
+    const double kap = tl_ld(tb, TL_H) * P.T;
+    const double taum = mT * tl_ld(tb, TL_TAU);
     // ---- new multipliers pi_k ----
     double pi[6];
     if (mode != EV_READ_PI) {
@@ -614,7 +692,7 @@ LM_NOINLINE void eval_pass(const Params& P, const Mesh& M, const Options& O, con
       for (int i = 0; i < 6; ++i) { pi[i] = g[i]; WS_AT(sp, F_PI + i) = g[i]; pimax = dmax(pimax, fabs(g[i])); }
     } else {
 #pragma unroll
-      for (int i = 0; i < 6; ++i) pi[i] = WS_AT(sp, F_PI + i);
+      for (int i = 0; i < 6; ++i) pi[i] = tl_ld(tb, EV_PI + i);
     }
 #pragma unroll
     for (int i = 0; i < 6; ++i) lam[i] = fma(alpha_lam, pi[i] - lam_old[i], lam_old[i]);
@@ -728,6 +806,8 @@ LM_NOINLINE bool riccati_backward(const Params& P, const Mesh& M, const Options&
   const int N = M.N;
   const double tf = c0.tf;
   const int so = src * N_ITER;
+  tl_begin();
+  bk7_stage_copy(M, W, N, so);
   const double mT = P.mflow * P.T;
   // cost-to-go Hessian in blocks: A = (p,p) 4x4 symmetric (full storage), B = (p,q) 4x3,
   // Cq = (q,q) 3x3 symmetric (upper triangle used); p = (y,vy,x,vx), q = (angle, angledot, tf)
@@ -757,23 +837,19 @@ LM_NOINLINE bool riccati_backward(const Params& P, const Mesh& M, const Options&
   bool ok = true;
   for (int k = N; k >= 1; --k) {
     double* sp = W.stage(k);
-    if (k - PF_DIST >= 1) {
-      pf_rows<F_U, N_ITER>(W.stage(k - PF_DIST), so);
-      if (k - PF_DIST - 1 >= 1) pf_rows<0, 6>(W.stage(k - PF_DIST - 1), so + F_Z);
-    }
+    if (k > 1) bk7_stage_copy(M, W, k - 1, so); else tl_commit();
+    tl_wait_prev();
+    const TileRef tb = tl_buf(W, k);
     double lam[6], zm[6];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) lam[i] = WS_AT(sp, so + F_LAM + i);
-    {
-      const double* sm = W.stage(k - 1);          // node 0 rows are zeros
+    for (int i = 0; i < 6; ++i) lam[i] = TL7_CUR(tb, BK_CUR, F_LAM + i);
 #pragma unroll
-      for (int i = 0; i < 6; ++i) zm[i] = WS_AT(sm, so + F_Z + i);
-    }
-    const double u = WS_AT(sp, so + F_U);
-    const double zla = WS_AT(sp, so + F_ZLA), zua = WS_AT(sp, so + F_ZUA);
-    const double zlu = WS_AT(sp, so + F_ZLU), zuu = WS_AT(sp, so + F_ZUU);
-    const double kap = M.h[k] * P.T;
-    const double taum = mT * M.tau[k];
+    for (int i = 0; i < 6; ++i) zm[i] = tl_ld(tb, BK_PZ + i);       // node k-1 (node 0 rows are zeros)
+    const double u = TL7_CUR(tb, BK_CUR, F_U);
+    const double zla = TL7_CUR(tb, BK_CUR, F_ZLA), zua = TL7_CUR(tb, BK_CUR, F_ZUA);
+    const double zlu = TL7_CUR(tb, BK_CUR, F_ZLU), zuu = TL7_CUR(tb, BK_CUR, F_ZUU);
+    const double kap = tl_ld(tb, TL_H) * P.T;
+    const double taum = mT * tl_ld(tb, TL_TAU);
     Accel1 f;
     accel_first(P, zn[0], zn[2], zn[4], taum * tf, f);
     StageJac J;
@@ -928,6 +1004,8 @@ LM_NOINLINE void riccati_forward(const Params& P, const Mesh& M, const Options& 
   const double tf = c0.tf;
   const int so = src * N_ITER;
   const double mT = P.mflow * P.T;
+  tl_begin();
+  fw7_stage_copy(M, W, 1, so);
   double ds[7] = {0, 0, 0, 0, 0, 0, dtf};
   double zm[6] = {0, 0, 0, 0, 0, 0};
   double dphi = 0.0, dxmax = fabs(dtf);
@@ -936,27 +1014,24 @@ LM_NOINLINE void riccati_forward(const Params& P, const Mesh& M, const Options& 
   const double cw = ls ? 0.0 : 1.0;   // defects are dropped in the least-squares mode
   for (int k = 1; k <= N; ++k) {
     double* sp = W.stage(k);
-    if (k + PF_DIST <= N) {
-      const double* pp = W.stage(k + PF_DIST);
-      pf_rows<F_Z, F_U + 1>(pp, so);
-      pf_rows<F_ZLA, N_ITER>(pp, so);
-      pf_rows<0, 8>(pp, F_K);
-    }
+    if (k < N) fw7_stage_copy(M, W, k + 1, so); else tl_commit();
+    tl_wait_prev();
+    const TileRef tb = tl_buf(W, k);
     double zn[6];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) zn[i] = WS_AT(sp, so + F_Z + i);
-    const double u = WS_AT(sp, so + F_U);
-    const double kap = M.h[k] * P.T;
-    const double taum = mT * M.tau[k];
+    for (int i = 0; i < 6; ++i) zn[i] = tl_ld(tb, FW_Z + i);
+    const double u = tl_ld(tb, FW_Z + 6);
+    const double kap = tl_ld(tb, TL_H) * P.T;
+    const double taum = mT * tl_ld(tb, TL_TAU);
     Accel1 f;
     accel_first(P, zn[0], zn[2], zn[4], taum * tf, f);
     StageJac J;
     stagejac_build(P, kap, tf, taum, f, zn[1], zn[3], zn[5], u, J);
     stagejac_invert(J);
     const double al = J.al;
-    double du = WS_AT(sp, F_KFF);
+    double du = tl_ld(tb, FW_K + 7);
 #pragma unroll
-    for (int i = 0; i < 7; ++i) du = fma(WS_AT(sp, F_K + i), ds[i], du);
+    for (int i = 0; i < 7; ++i) du = fma(tl_ld(tb, FW_K + i), ds[i], du);
     double xi[7];
     xi[0] = ds[0] - cw * (zn[0] - zm[0] - al * zn[1]);
     xi[1] = ds[1] - cw * (zn[1] - zm[1] - al * f.ay);
@@ -974,8 +1049,8 @@ LM_NOINLINE void riccati_forward(const Params& P, const Mesh& M, const Options& 
     const double da = ds[4];
     const double dLa = zn[4], dUa = P.a_ub - zn[4], dLu = u + P.u_ub, dUu = P.u_ub - u;
     rp.push(-da, dLa); rp.push(da, dUa); rp.push(-du, dLu); rp.push(du, dUu);
-    const double zla = WS_AT(sp, so + F_ZLA), zua = WS_AT(sp, so + F_ZUA);
-    const double zlu = WS_AT(sp, so + F_ZLU), zuu = WS_AT(sp, so + F_ZUU);
+    const double zla = tl_ld(tb, FW_ZB + 0), zua = tl_ld(tb, FW_ZB + 1);
+    const double zlu = tl_ld(tb, FW_ZB + 2), zuu = tl_ld(tb, FW_ZB + 3);
     double rLa, rUa, rLu, rUu;
     recip4(dLa, dUa, dLu, dUu, rLa, rUa, rLu, rUu);
     const double d1 = (mu - zla * da) * rLa - zla;

@@ -227,6 +227,48 @@ LM_NOINLINE bool init_from_ref7(const Params& P, const Mesh& M, const Options& O
 }
 
 // ---------------------------------------------------------------------------------------
+// Staging tiles (see ascent_ipm.cuh: tl_*): which rows each sweep reads per stage and where they sit
+// in the tile.  "CUR" = rows F_LAM .. N_ITER-1 of the source iterate at stage k (multipliers and the
+// slack pair), "PZ"/"PDS" = (s, u) and their steps at stage k-1.
+// ---------------------------------------------------------------------------------------
+enum : int {
+  N_CUR = N_ITER - F_LAM,                          // 15
+  EV_CUR = 0, EV_PI = EV_CUR + N_CUR, EV_PZ = EV_PI + 7, EV_PDS = EV_PZ + 7, EV_ROWS = EV_PDS + 7,
+  BK_CUR = 0, BK_PZ = BK_CUR + N_CUR, BK_ROWS = BK_PZ + 7,
+  FW_Z = 0, FW_ZB = FW_Z + 7, FW_K = FW_ZB + (N_ITER - F_ZLA), FW_ROWS = FW_K + N_FACT
+};
+static_assert(EV_ROWS <= TILE_DATA && BK_ROWS <= TILE_DATA && FW_ROWS <= TILE_DATA, "tile too small");
+#define TL_CUR(tb, base, f) tl_ld(tb, (base) + (f) - F_LAM)      // row f (>= F_LAM) of the source iterate
+
+LM_HD void ev_stage_copy(const Mesh& M, const Ws& W, int k, int so, bool read_pi) {
+  const TileRef tb = tl_buf(W, k);
+  tl_copy_mesh(tb, M, k);
+  const double* sp = W.stage(k);
+  const double* sm = W.stage(k - 1);
+  tl_copy_rows<EV_CUR, N_CUR>(tb, sp, so + F_LAM);
+  if (read_pi) tl_copy_rows<EV_PI, 7>(tb, sp, F_PI);
+  tl_copy_rows<EV_PZ, 7>(tb, sm, so + F_Z);
+  tl_copy_rows<EV_PDS, 7>(tb, sm, F_DS);
+  tl_commit();
+}
+LM_HD void bk_stage_copy(const Mesh& M, const Ws& W, int k, int so) {
+  const TileRef tb = tl_buf(W, k);
+  tl_copy_mesh(tb, M, k);
+  tl_copy_rows<BK_CUR, N_CUR>(tb, W.stage(k), so + F_LAM);
+  tl_copy_rows<BK_PZ, 7>(tb, W.stage(k - 1), so + F_Z);
+  tl_commit();
+}
+LM_HD void fw_stage_copy(const Mesh& M, const Ws& W, int k, int so) {
+  const TileRef tb = tl_buf(W, k);
+  tl_copy_mesh(tb, M, k);
+  const double* sp = W.stage(k);
+  tl_copy_rows<FW_Z, 7>(tb, sp, so + F_Z);
+  tl_copy_rows<FW_ZB, N_ITER - F_ZLA>(tb, sp, so + F_ZLA);
+  tl_copy_rows<FW_K, N_FACT>(tb, sp, F_K);
+  tl_commit();
+}
+
+// ---------------------------------------------------------------------------------------
 // evaluation pass (see ascent_ipm.cuh: eval_pass); differences: u is a state of the node, the u row
 // and its multiplier lam_6, the move slack pair (p, n, z_p, z_n) in the merit and the residuals.
 // ---------------------------------------------------------------------------------------
@@ -234,10 +276,12 @@ LM_NOINLINE void eval_pass(const Params& P, const Mesh& M, const Options& O, con
                            const Scal& c0, const TermStep& ts, double mu, double dw, double alpha,
                            double alpha_z, double alpha_lam, int mode, Scal& t, double* pimax_out) {
   const int N = M.N;
+  const int so = src * N_ITER, dd = dst * N_ITER;
+  tl_begin();
+  ev_stage_copy(M, W, N, so, mode == EV_READ_PI);
   const double tf0 = c0.tf, dtf = ts.dtf;
   t.tf = tf0 + alpha * dtf;
   const double tf = t.tf;
-  const int so = src * N_ITER, dd = dst * N_ITER;
   const double mT = P.mflow * P.T;
   const bool ls = (mode == EV_LSQ);
   const double wdc = O.w_dcost;
@@ -278,35 +322,25 @@ LM_NOINLINE void eval_pass(const Params& P, const Mesh& M, const Options& O, con
   double pi_next[7] = {0, 0, 0, 0, 0, 0, 0};
   for (int k = N; k >= 1; --k) {
     double* sp = W.stage(k);
-    if (k - PF_DIST >= 1) {
-      const double* pp = W.stage(k - PF_DIST);
-      pf_rows<F_LAM, N_ITER>(pp, so);
-      if (mode == EV_READ_PI) pf_rows<0, 7>(pp, F_PI);
-      if (k - PF_DIST - 1 >= 1) {
-        const double* pq = W.stage(k - PF_DIST - 1);
-        pf_rows<0, 7>(pq, so + F_Z);
-        pf_rows<0, 7>(pq, F_DS);
-      }
-    }
+    if (k > 1) ev_stage_copy(M, W, k - 1, so, mode == EV_READ_PI); else tl_commit();
+    tl_wait_prev();
+    const TileRef tb = tl_buf(W, k);
     double z[7], zpo[7], dsp[7], zp[7], lam[7];
 #pragma unroll
     for (int i = 0; i < 7; ++i) z[i] = fma(alpha, ds[i], zo[i]);
-    {
-      const double* sm = W.stage(k - 1);          // node 0 rows are zeros
 #pragma unroll
-      for (int i = 0; i < 6; ++i) { zpo[i] = WS_AT(sm, so + F_Z + i); dsp[i] = WS_AT(sm, F_DS + i); }
-      zpo[6] = WS_AT(sm, so + F_U); dsp[6] = WS_AT(sm, F_DU);
-#pragma unroll
-      for (int i = 0; i < 7; ++i) zp[i] = fma(alpha, dsp[i], zpo[i]);
+    for (int i = 0; i < 7; ++i) {                 // node k-1 (node 0 rows are zeros)
+      zpo[i] = tl_ld(tb, EV_PZ + i); dsp[i] = tl_ld(tb, EV_PDS + i);
+      zp[i] = fma(alpha, dsp[i], zpo[i]);
     }
     const double u_old = zo[6], du = ds[6], u = z[6];
     double lam_old[7];
 #pragma unroll
-    for (int i = 0; i < 7; ++i) lam_old[i] = WS_AT(sp, so + F_LAM + i);
-    double zla = WS_AT(sp, so + F_ZLA), zua = WS_AT(sp, so + F_ZUA);
-    double zlu = WS_AT(sp, so + F_ZLU), zuu = WS_AT(sp, so + F_ZUU);
-    const double kap = M.h[k] * P.T;
-    const double taum = mT * M.tau[k];
+    for (int i = 0; i < 7; ++i) lam_old[i] = TL_CUR(tb, EV_CUR, F_LAM + i);
+    double zla = TL_CUR(tb, EV_CUR, F_ZLA), zua = TL_CUR(tb, EV_CUR, F_ZUA);
+    double zlu = TL_CUR(tb, EV_CUR, F_ZLU), zuu = TL_CUR(tb, EV_CUR, F_ZUU);
+    const double kap = tl_ld(tb, TL_H) * P.T;
+    const double taum = mT * tl_ld(tb, TL_TAU);
     // ---- new multipliers pi_k ----
     double pi[7];
     if (mode != EV_READ_PI) {
@@ -342,7 +376,7 @@ LM_NOINLINE void eval_pass(const Params& P, const Mesh& M, const Options& O, con
       for (int i = 0; i < 7; ++i) { pi[i] = g[i]; WS_AT(sp, F_PI + i) = g[i]; pimax = dmax(pimax, fabs(g[i])); }
     } else {
 #pragma unroll
-      for (int i = 0; i < 7; ++i) pi[i] = WS_AT(sp, F_PI + i);
+      for (int i = 0; i < 7; ++i) pi[i] = tl_ld(tb, EV_PI + i);
     }
 #pragma unroll
     for (int i = 0; i < 7; ++i) lam[i] = fma(alpha_lam, pi[i] - lam_old[i], lam_old[i]);
@@ -374,8 +408,8 @@ LM_NOINLINE void eval_pass(const Params& P, const Mesh& M, const Options& O, con
     }
     sz += (zla + zua) + (zlu + zuu);
     // ---- move slack pair: p, n follow the move step, their multipliers the dual step ----
-    double pp = WS_AT(sp, so + F_PP), pn = WS_AT(sp, so + F_PN);
-    double zpp = WS_AT(sp, so + F_ZPP), zpn = WS_AT(sp, so + F_ZPN);
+    double pp = TL_CUR(tb, EV_CUR, F_PP), pn = TL_CUR(tb, EV_CUR, F_PN);
+    double zpp = TL_CUR(tb, EV_CUR, F_ZPP), zpn = TL_CUR(tb, EV_CUR, F_ZPN);
     {
       Move mv;
       mv.build(pp, pn, zpp, zpn, u_old - zpo[6], wdc, mu, false);
@@ -486,6 +520,8 @@ LM_NOINLINE bool riccati_backward(const Params& P, const Mesh& M, const Options&
   const int N = M.N;
   const double tf = c0.tf;
   const int so = src * N_ITER;
+  tl_begin();
+  bk_stage_copy(M, W, N, so);
   const double mT = P.mflow * P.T;
   const double wdc = O.w_dcost;
   double A[4][4], Bm[4][4], C[4][4];     // C: q x q, full storage (kept symmetric)
@@ -512,24 +548,19 @@ LM_NOINLINE bool riccati_backward(const Params& P, const Mesh& M, const Options&
   bool ok = true;
   for (int k = N; k >= 1; --k) {
     double* sp = W.stage(k);
-    if (k - PF_DIST >= 1) {
-      pf_rows<F_LAM, N_ITER>(W.stage(k - PF_DIST), so);
-      if (k - PF_DIST - 1 >= 1) pf_rows<0, 7>(W.stage(k - PF_DIST - 1), so + F_Z);
-    }
+    if (k > 1) bk_stage_copy(M, W, k - 1, so); else tl_commit();
+    tl_wait_prev();
+    const TileRef tb = tl_buf(W, k);
     double lam[6], zm[7];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) lam[i] = WS_AT(sp, so + F_LAM + i);
-    {
-      const double* sm = W.stage(k - 1);
+    for (int i = 0; i < 6; ++i) lam[i] = TL_CUR(tb, BK_CUR, F_LAM + i);
 #pragma unroll
-      for (int i = 0; i < 6; ++i) zm[i] = WS_AT(sm, so + F_Z + i);
-      zm[6] = WS_AT(sm, so + F_U);
-    }
+    for (int i = 0; i < 7; ++i) zm[i] = tl_ld(tb, BK_PZ + i);
     const double u = zn[6];
-    const double zla = WS_AT(sp, so + F_ZLA), zua = WS_AT(sp, so + F_ZUA);
-    const double zlu = WS_AT(sp, so + F_ZLU), zuu = WS_AT(sp, so + F_ZUU);
-    const double kap = M.h[k] * P.T;
-    const double taum = mT * M.tau[k];
+    const double zla = TL_CUR(tb, BK_CUR, F_ZLA), zua = TL_CUR(tb, BK_CUR, F_ZUA);
+    const double zlu = TL_CUR(tb, BK_CUR, F_ZLU), zuu = TL_CUR(tb, BK_CUR, F_ZUU);
+    const double kap = tl_ld(tb, TL_H) * P.T;
+    const double taum = mT * tl_ld(tb, TL_TAU);
     Accel1 f;
     accel_first(P, zn[0], zn[2], zn[4], taum * tf, f);
     StageJac J;
@@ -554,7 +585,7 @@ LM_NOINLINE bool riccati_backward(const Params& P, const Mesh& M, const Options&
     pv[4] += q.q4;
     pv[6] += q.r;
     Move mv;
-    mv.build(WS_AT(sp, so + F_PP), WS_AT(sp, so + F_PN), WS_AT(sp, so + F_ZPP), WS_AT(sp, so + F_ZPN),
+    mv.build(TL_CUR(tb, BK_CUR, F_PP), TL_CUR(tb, BK_CUR, F_PN), TL_CUR(tb, BK_CUR, F_ZPP), TL_CUR(tb, BK_CUR, F_ZPN),
              u - zm[6], wdc, mu, ls);
     const double R = mv.R + (ls ? 0.0 : dw);
     const double r = mv.r;
@@ -693,6 +724,8 @@ LM_NOINLINE void riccati_forward(const Params& P, const Mesh& M, const Options& 
   const int so = src * N_ITER;
   const double mT = P.mflow * P.T;
   const double wdc = O.w_dcost;
+  tl_begin();
+  fw_stage_copy(M, W, 1, so);
   double ds[8] = {0, 0, 0, 0, 0, 0, 0, dtf};      // (y,vy,x,vx,a,w,u,tf) of the previous node
   double zm[7] = {0, 0, 0, 0, 0, 0, 0};
   double dphi = 0.0, dxmax = fabs(dtf);
@@ -701,28 +734,24 @@ LM_NOINLINE void riccati_forward(const Params& P, const Mesh& M, const Options& 
   const double cw = ls ? 0.0 : 1.0;
   for (int k = 1; k <= N; ++k) {
     double* sp = W.stage(k);
-    if (k + PF_DIST <= N) {
-      const double* pp = W.stage(k + PF_DIST);
-      pf_rows<F_Z, F_U + 1>(pp, so);
-      pf_rows<F_ZLA, N_ITER>(pp, so);
-      pf_rows<0, 9>(pp, F_K);
-    }
+    if (k < N) fw_stage_copy(M, W, k + 1, so); else tl_commit();
+    tl_wait_prev();
+    const TileRef tb = tl_buf(W, k);
     double zn[7];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) zn[i] = WS_AT(sp, so + F_Z + i);
-    zn[6] = WS_AT(sp, so + F_U);
+    for (int i = 0; i < 7; ++i) zn[i] = tl_ld(tb, FW_Z + i);
     const double u = zn[6];
-    const double kap = M.h[k] * P.T;
-    const double taum = mT * M.tau[k];
+    const double kap = tl_ld(tb, TL_H) * P.T;
+    const double taum = mT * tl_ld(tb, TL_TAU);
     Accel1 f;
     accel_first(P, zn[0], zn[2], zn[4], taum * tf, f);
     StageJac J;
     stagejac_build(P, kap, tf, taum, f, zn[1], zn[3], zn[5], u, J);
     stagejac_invert(J);
     const double al = J.al;
-    double dv = WS_AT(sp, F_KFF);
+    double dv = tl_ld(tb, FW_K + 8);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) dv = fma(WS_AT(sp, F_K + i), ds[i], dv);
+    for (int i = 0; i < 8; ++i) dv = fma(tl_ld(tb, FW_K + i), ds[i], dv);
     double xi[8];
     xi[0] = ds[0] - cw * (zn[0] - zm[0] - al * zn[1]);
     xi[1] = ds[1] - cw * (zn[1] - zm[1] - al * f.ay);
@@ -735,8 +764,8 @@ LM_NOINLINE void riccati_forward(const Params& P, const Mesh& M, const Options& 
     solveE8(J, xi);
     {
       // slack pair: primal and dual steps, fraction to the boundary, merit slope
-      const double pp = WS_AT(sp, so + F_PP), pn = WS_AT(sp, so + F_PN);
-      const double zpp = WS_AT(sp, so + F_ZPP), zpn = WS_AT(sp, so + F_ZPN);
+      const double pp = tl_ld(tb, FW_ZB + F_PP - F_ZLA), pn = tl_ld(tb, FW_ZB + F_PN - F_ZLA);
+      const double zpp = tl_ld(tb, FW_ZB + F_ZPP - F_ZLA), zpn = tl_ld(tb, FW_ZB + F_ZPN - F_ZLA);
       Move mv;
       mv.build(pp, pn, zpp, zpn, u - zm[6], wdc, mu, ls);
       double dp, dn;
@@ -761,8 +790,8 @@ LM_NOINLINE void riccati_forward(const Params& P, const Mesh& M, const Options& 
     const double da = ds[4];
     const double dLa = zn[4], dUa = P.a_ub - zn[4], dLu = u + P.u_ub, dUu = P.u_ub - u;
     rp.push(-da, dLa); rp.push(da, dUa); rp.push(-du, dLu); rp.push(du, dUu);
-    const double zla = WS_AT(sp, so + F_ZLA), zua = WS_AT(sp, so + F_ZUA);
-    const double zlu = WS_AT(sp, so + F_ZLU), zuu = WS_AT(sp, so + F_ZUU);
+    const double zla = tl_ld(tb, FW_ZB + 0), zua = tl_ld(tb, FW_ZB + 1);
+    const double zlu = tl_ld(tb, FW_ZB + 2), zuu = tl_ld(tb, FW_ZB + 3);
     double rLa, rUa, rLu, rUu;
     recip4(dLa, dUa, dLu, dUu, rLa, rUa, rLu, rUu);
     const double d1 = (mu - zla * da) * rLa - zla;

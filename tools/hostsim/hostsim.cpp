@@ -56,7 +56,8 @@ int main(int argc, char** argv) {
   if (getenv("DC")) O.delta_c = atof(getenv("DC"));
   const int nfields = O.w_dcost > 0 ? (int)dc::N_FIELDS : (int)N_FIELDS;
   std::vector<double> ws((size_t)nfields * LANES * (N + 1), 0.0);   // one warp block, lane 0 used
-  Ws W{ws.data(), (long)nfields * LANES};
+  std::vector<double> tile(2 * TILE_ROWS, 0.0);
+  Ws W{ws.data(), (long)nfields * LANES, tile.data()};
   std::mt19937_64 rng(11);
   std::uniform_real_distribution<double> U(0.0, 1.0);
   int nfail = 0, itsum = 0, itmax = 0;
@@ -123,7 +124,8 @@ extern "C" int hostsim_solve(const double* raw14, int nt, const double* time, do
   const int nfields = DC ? (int)dc::N_FIELDS : (int)N_FIELDS;
   const int niter = DC ? (int)dc::N_ITER : (int)N_ITER;
   std::vector<double> ws((size_t)nfields * LANES * (N + 1), 0.0);
-  Ws W{ws.data(), (long)nfields * LANES};
+  std::vector<double> tile(2 * TILE_ROWS, 0.0);
+  Ws W{ws.data(), (long)nfields * LANES, tile.data()};
   SolveOut out;
   if (DC) {
     IpmState S;
