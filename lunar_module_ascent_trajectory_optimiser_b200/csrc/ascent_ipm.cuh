@@ -91,12 +91,24 @@ typedef unsigned TileRef;
 typedef double* TileRef;
 #endif
 
+// Hides how a workspace pointer was computed from the optimiser.  Without it the loop-strength
+// reduction turns every row address of a stage loop into its own 64-bit induction variable (two
+// integer adds per row and stage, and a register pair each); with it a stage has one base pointer and
+// the rows are immediate offsets.
+template <class T>
+LM_HD T* ws_opaque(T* q) {
+#if defined(__CUDA_ARCH__)
+  asm("" : "+l"(q));
+#endif
+  return q;
+}
+
 // View of one thread's column of the workspace.
 struct Ws {
   double* p;             // base + (warp * N_FIELDS) * 32 + lane
   long SS;               // stage stride in doubles = n_warps * N_FIELDS * 32
   TileRef tl;            // this lane's column of the warp's two staging tiles
-  LM_HD double* stage(int k) const { return p + (long)k * SS; }
+  LM_HD double* stage(int k) const { return ws_opaque(p + (long)k * SS); }
 };
 #define WS_AT(sp, row) (sp)[(row) * LANES]
 
@@ -562,27 +574,31 @@ LM_HD void ev7_stage_copy(const Mesh& M, const Ws& W, int k, int so, bool read_p
   const TileRef tb = tl_buf(W, k);
   tl_copy_mesh(tb, M, k);
   const double* sp = W.stage(k);
-  const double* sm = W.stage(k - 1);
-  tl_copy_rows<EV_CUR, N_CUR>(tb, sp, so + F_U);
+  const double* sm = ws_opaque(sp - W.SS);
+  const double* spo = ws_opaque(sp + so * LANES);
+  const double* smo = ws_opaque(sm + so * LANES);
+  tl_copy_rows<EV_CUR, N_CUR>(tb, spo, F_U);
   tl_copy(tb, EV_DU, sp + F_DU * LANES);
   if (read_pi) tl_copy_rows<EV_PI, 6>(tb, sp, F_PI);
-  tl_copy_rows<EV_PZ, 6>(tb, sm, so + F_Z);
+  tl_copy_rows<EV_PZ, 6>(tb, smo, F_Z);
   tl_copy_rows<EV_PDS, 6>(tb, sm, F_DS);
   tl_commit();
 }
 LM_HD void bk7_stage_copy(const Mesh& M, const Ws& W, int k, int so) {
   const TileRef tb = tl_buf(W, k);
   tl_copy_mesh(tb, M, k);
-  tl_copy_rows<BK_CUR, N_CUR>(tb, W.stage(k), so + F_U);
-  tl_copy_rows<BK_PZ, 6>(tb, W.stage(k - 1), so + F_Z);
+  const double* spo = ws_opaque(W.stage(k) + so * LANES);
+  tl_copy_rows<BK_CUR, N_CUR>(tb, spo, F_U);
+  tl_copy_rows<BK_PZ, 6>(tb, ws_opaque(spo - W.SS), F_Z);
   tl_commit();
 }
 LM_HD void fw7_stage_copy(const Mesh& M, const Ws& W, int k, int so) {
   const TileRef tb = tl_buf(W, k);
   tl_copy_mesh(tb, M, k);
   const double* sp = W.stage(k);
-  tl_copy_rows<FW_Z, 7>(tb, sp, so + F_Z);
-  tl_copy_rows<FW_ZB, N_ITER - F_ZLA>(tb, sp, so + F_ZLA);
+  const double* spo = ws_opaque(sp + so * LANES);
+  tl_copy_rows<FW_Z, 7>(tb, spo, F_Z);
+  tl_copy_rows<FW_ZB, N_ITER - F_ZLA>(tb, spo, F_ZLA);
   tl_copy_rows<FW_K, N_FACT>(tb, sp, F_K);
   tl_commit();
 }
@@ -770,14 +786,15 @@ LM_NOINLINE void eval_pass(const Params& P, const Mesh& M, const Options& O, con
     dual = dmax(dual, fabs(-J.beta * lam[5] - zlu + zuu));     // d L / d u_k
     gtf -= J.e0 * lam[0] + J.e1 * lam[1] + J.e2 * lam[2] + J.e3 * lam[3] + J.e4 * lam[4] + J.e5 * lam[5];
     // ---- write the trial iterate, shift the pipeline ----
+double* spd = ws_opaque(sp + dd * LANES);
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
-      WS_AT(sp, dd + F_Z + i) = z[i]; WS_AT(sp, dd + F_LAM + i) = lam[i];
+      WS_AT(spd, F_Z + i) = z[i]; WS_AT(spd, F_LAM + i) = lam[i];
       lam_next[i] = lam[i]; pi_next[i] = pi[i]; zo[i] = zpo[i]; ds[i] = dsp[i];
     }
-    WS_AT(sp, dd + F_U) = u;
-    WS_AT(sp, dd + F_ZLA) = zla; WS_AT(sp, dd + F_ZUA) = zua;
-    WS_AT(sp, dd + F_ZLU) = zlu; WS_AT(sp, dd + F_ZUU) = zuu;
+    WS_AT(spd, F_U) = u;
+    WS_AT(spd, F_ZLA) = zla; WS_AT(spd, F_ZUA) = zua;
+    WS_AT(spd, F_ZLU) = zlu; WS_AT(spd, F_ZUU) = zuu;
   }
   dual = dmax(dual, fabs(gtf));
   t.theta = theta;

@@ -244,26 +244,30 @@ LM_HD void ev_stage_copy(const Mesh& M, const Ws& W, int k, int so, bool read_pi
   const TileRef tb = tl_buf(W, k);
   tl_copy_mesh(tb, M, k);
   const double* sp = W.stage(k);
-  const double* sm = W.stage(k - 1);
-  tl_copy_rows<EV_CUR, N_CUR>(tb, sp, so + F_LAM);
+  const double* sm = ws_opaque(sp - W.SS);
+  const double* spo = ws_opaque(sp + so * LANES);
+  const double* smo = ws_opaque(sm + so * LANES);
+  tl_copy_rows<EV_CUR, N_CUR>(tb, spo, F_LAM);
   if (read_pi) tl_copy_rows<EV_PI, 7>(tb, sp, F_PI);
-  tl_copy_rows<EV_PZ, 7>(tb, sm, so + F_Z);
+  tl_copy_rows<EV_PZ, 7>(tb, smo, F_Z);
   tl_copy_rows<EV_PDS, 7>(tb, sm, F_DS);
   tl_commit();
 }
 LM_HD void bk_stage_copy(const Mesh& M, const Ws& W, int k, int so) {
   const TileRef tb = tl_buf(W, k);
   tl_copy_mesh(tb, M, k);
-  tl_copy_rows<BK_CUR, N_CUR>(tb, W.stage(k), so + F_LAM);
-  tl_copy_rows<BK_PZ, 7>(tb, W.stage(k - 1), so + F_Z);
+  const double* spo = ws_opaque(W.stage(k) + so * LANES);
+  tl_copy_rows<BK_CUR, N_CUR>(tb, spo, F_LAM);
+  tl_copy_rows<BK_PZ, 7>(tb, ws_opaque(spo - W.SS), F_Z);
   tl_commit();
 }
 LM_HD void fw_stage_copy(const Mesh& M, const Ws& W, int k, int so) {
   const TileRef tb = tl_buf(W, k);
   tl_copy_mesh(tb, M, k);
   const double* sp = W.stage(k);
-  tl_copy_rows<FW_Z, 7>(tb, sp, so + F_Z);
-  tl_copy_rows<FW_ZB, N_ITER - F_ZLA>(tb, sp, so + F_ZLA);
+  const double* spo = ws_opaque(sp + so * LANES);
+  tl_copy_rows<FW_Z, 7>(tb, spo, F_Z);
+  tl_copy_rows<FW_ZB, N_ITER - F_ZLA>(tb, spo, F_ZLA);
   tl_copy_rows<FW_K, N_FACT>(tb, sp, F_K);
   tl_commit();
 }
@@ -489,18 +493,19 @@ LM_NOINLINE void eval_pass(const Params& P, const Mesh& M, const Options& O, con
     dual = dmax(dual, dmax(fabs(wdc - lam[6] - zpp), fabs(wdc + lam[6] - zpn)));   // d L / d p_k, d L / d n_k
     gtf -= J.e0 * lam[0] + J.e1 * lam[1] + J.e2 * lam[2] + J.e3 * lam[3] + J.e4 * lam[4] + J.e5 * lam[5];
     // ---- write the trial iterate, shift the pipeline ----
+double* spd = ws_opaque(sp + dd * LANES);
 #pragma unroll
-    for (int i = 0; i < 6; ++i) WS_AT(sp, dd + F_Z + i) = z[i];
+    for (int i = 0; i < 6; ++i) WS_AT(spd, F_Z + i) = z[i];
 #pragma unroll
     for (int i = 0; i < 7; ++i) {
-      WS_AT(sp, dd + F_LAM + i) = lam[i];
+      WS_AT(spd, F_LAM + i) = lam[i];
       lam_next[i] = lam[i]; pi_next[i] = pi[i]; zo[i] = zpo[i]; ds[i] = dsp[i];
     }
-    WS_AT(sp, dd + F_U) = u;
-    WS_AT(sp, dd + F_ZLA) = zla; WS_AT(sp, dd + F_ZUA) = zua;
-    WS_AT(sp, dd + F_ZLU) = zlu; WS_AT(sp, dd + F_ZUU) = zuu;
-    WS_AT(sp, dd + F_PP) = pp; WS_AT(sp, dd + F_PN) = pn;
-    WS_AT(sp, dd + F_ZPP) = zpp; WS_AT(sp, dd + F_ZPN) = zpn;
+    WS_AT(spd, F_U) = u;
+    WS_AT(spd, F_ZLA) = zla; WS_AT(spd, F_ZUA) = zua;
+    WS_AT(spd, F_ZLU) = zlu; WS_AT(spd, F_ZUU) = zuu;
+    WS_AT(spd, F_PP) = pp; WS_AT(spd, F_PN) = pn;
+    WS_AT(spd, F_ZPP) = zpp; WS_AT(spd, F_ZPN) = zpn;
   }
   dual = dmax(dual, fabs(gtf));
   t.theta = theta;
