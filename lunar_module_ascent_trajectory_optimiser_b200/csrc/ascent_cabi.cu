@@ -45,7 +45,8 @@ void set_err(const char* fmt, const char* a = "", const char* b = "") {
 #endif
 constexpr int kBlock = 256;
 constexpr int kBlocksPerSM = 1;
-constexpr size_t kTileSmem = (size_t)(kBlock / 32) * 2 * TILE_ROWS * LANES * sizeof(double);   // 147 456 B
+// dynamic shared memory: the staging tiles, then one workspace view per thread
+constexpr size_t kTileSmem = (size_t)(kBlock / 32) * 2 * TILE_ROWS * LANES * sizeof(double) + kBlock * sizeof(Ws);
 // The warm start costs one serial single-problem solve (~13 ms); measured break-even is ~8k problems.
 constexpr long kWarmStartMinBatch = 16384;
 
@@ -111,6 +112,7 @@ __device__ __forceinline__ Params derive_params(const double* __restrict__ p, lo
   P.fuel = fuel;
   P.Sinv = 1.0 / P.S;
   P.coup5 = 1.0;
+  P.mT = P.mflow * P.T;
   if (model == LMATO_MODEL_CIRCULAR) {
     // PDF p.27 src 69-73: the MV is the pitch angle itself; no rate or acceleration limit exists
     P.coup5 = 0.0;
@@ -147,7 +149,7 @@ __global__ void __launch_bounds__(kBlock, kBlocksPerSM) ascent_ipm_kernel(KArgs 
                          (unsigned)(((threadIdx.x / 32) * 2 * TILE_ROWS * LANES + lane) * sizeof(double));
   // the workspace view is read inside every stage of the noinline sweeps: shared memory, not the
   // local-memory stack (24-byte stride: conflict-free per half warp)
-  __shared__ Ws sW[kBlock];
+  Ws* sW = reinterpret_cast<Ws*>(sTiles + (size_t)(kBlock / 32) * 2 * TILE_ROWS * LANES);   // after the tiles
   sW[threadIdx.x] = Ws{a.ws + ((slot / LANES) * SW::NFIELDS) * LANES + lane, nwarps * SW::NFIELDS * LANES, tile0};
   const Ws& W = sW[threadIdx.x];
   const int nt = a.N + 1;
@@ -387,7 +389,7 @@ lmato_status_t lmato_create(lmato_handle** out, int32_t device, int32_t nt, cons
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   H->sm_count = prop.multiProcessorCount;
-  // the staging tiles need the opt-in shared-memory size (147 KB dynamic + 39 KB static per CTA)
+  // the staging tiles need the opt-in shared-memory size (158 KB dynamic + 42 KB static per CTA)
   CUDA_TRY(cudaFuncSetAttribute(ascent_ipm_kernel<Sweeps7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmem));
   CUDA_TRY(cudaFuncSetAttribute(ascent_ipm_kernel<Sweeps8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmem));
   CUDA_TRY(cudaMalloc(&H->d_h, sizeof(double) * nt));

@@ -615,7 +615,6 @@ LM_NOINLINE void eval_pass(const Params& P, const Mesh& M, const Options& O, con
   const double tf0 = c0.tf, dtf = ts.dtf;
   t.tf = tf0 + alpha * dtf;
   const double tf = t.tf;
-  const double mT = P.mflow * P.T;
   const bool ls = (mode == EV_LSQ);
   double theta = 0, prim = 0, dual = 0, sumlog = 0, cmin = 1e300, cmax = 0, slam = 0, sz = 0;
   double gtf = 0;                          // d Lagrangian / d tf accumulated over stages
@@ -677,7 +676,7 @@ LM_NOINLINE void eval_pass(const Params& P, const Mesh& M, const Options& O, con
     double zla = TL7_CUR(tb, EV_CUR, F_ZLA), zua = TL7_CUR(tb, EV_CUR, F_ZUA);
     double zlu = TL7_CUR(tb, EV_CUR, F_ZLU), zuu = TL7_CUR(tb, EV_CUR, F_ZUU);
     const double kap = tl_ld(tb, TL_H) * P.T;
-    const double taum = mT * tl_ld(tb, TL_TAU);
+    const double taum = P.mT * tl_ld(tb, TL_TAU);
     // ---- new multipliers pi_k ----
     double pi[6];
     if (mode != EV_READ_PI) {
@@ -825,7 +824,6 @@ LM_NOINLINE bool riccati_backward(const Params& P, const Mesh& M, const Options&
   const int so = src * N_ITER;
   tl_begin();
   bk7_stage_copy(M, W, N, so);
-  const double mT = P.mflow * P.T;
   // cost-to-go Hessian in blocks: A = (p,p) 4x4 symmetric (full storage), B = (p,q) 4x3,
   // Cq = (q,q) 3x3 symmetric (upper triangle used); p = (y,vy,x,vx), q = (angle, angledot, tf)
   double A[4][4], Bm[4][3], C00, C01, C02, C11, C12, C22;
@@ -866,7 +864,7 @@ LM_NOINLINE bool riccati_backward(const Params& P, const Mesh& M, const Options&
     const double zla = TL7_CUR(tb, BK_CUR, F_ZLA), zua = TL7_CUR(tb, BK_CUR, F_ZUA);
     const double zlu = TL7_CUR(tb, BK_CUR, F_ZLU), zuu = TL7_CUR(tb, BK_CUR, F_ZUU);
     const double kap = tl_ld(tb, TL_H) * P.T;
-    const double taum = mT * tl_ld(tb, TL_TAU);
+    const double taum = P.mT * tl_ld(tb, TL_TAU);
     Accel1 f;
     accel_first(P, zn[0], zn[2], zn[4], taum * tf, f);
     StageJac J;
@@ -1020,7 +1018,6 @@ LM_NOINLINE void riccati_forward(const Params& P, const Mesh& M, const Options& 
   const int N = M.N;
   const double tf = c0.tf;
   const int so = src * N_ITER;
-  const double mT = P.mflow * P.T;
   tl_begin();
   fw7_stage_copy(M, W, 1, so);
   double ds[7] = {0, 0, 0, 0, 0, 0, dtf};
@@ -1039,7 +1036,7 @@ LM_NOINLINE void riccati_forward(const Params& P, const Mesh& M, const Options& 
     for (int i = 0; i < 6; ++i) zn[i] = tl_ld(tb, FW_Z + i);
     const double u = tl_ld(tb, FW_Z + 6);
     const double kap = tl_ld(tb, TL_H) * P.T;
-    const double taum = mT * tl_ld(tb, TL_TAU);
+    const double taum = P.mT * tl_ld(tb, TL_TAU);
     Accel1 f;
     accel_first(P, zn[0], zn[2], zn[4], taum * tf, f);
     StageJac J;

@@ -286,7 +286,6 @@ LM_NOINLINE void eval_pass(const Params& P, const Mesh& M, const Options& O, con
   const double tf0 = c0.tf, dtf = ts.dtf;
   t.tf = tf0 + alpha * dtf;
   const double tf = t.tf;
-  const double mT = P.mflow * P.T;
   const bool ls = (mode == EV_LSQ);
   const double wdc = O.w_dcost;
   double theta = 0, prim = 0, dual = 0, sumlog = 0, cmin = 1e300, cmax = 0, slam = 0, sz = 0;
@@ -344,7 +343,7 @@ LM_NOINLINE void eval_pass(const Params& P, const Mesh& M, const Options& O, con
     double zla = TL_CUR(tb, EV_CUR, F_ZLA), zua = TL_CUR(tb, EV_CUR, F_ZUA);
     double zlu = TL_CUR(tb, EV_CUR, F_ZLU), zuu = TL_CUR(tb, EV_CUR, F_ZUU);
     const double kap = tl_ld(tb, TL_H) * P.T;
-    const double taum = mT * tl_ld(tb, TL_TAU);
+    const double taum = P.mT * tl_ld(tb, TL_TAU);
     // ---- new multipliers pi_k ----
     double pi[7];
     if (mode != EV_READ_PI) {
@@ -527,7 +526,6 @@ LM_NOINLINE bool riccati_backward(const Params& P, const Mesh& M, const Options&
   const int so = src * N_ITER;
   tl_begin();
   bk_stage_copy(M, W, N, so);
-  const double mT = P.mflow * P.T;
   const double wdc = O.w_dcost;
   double A[4][4], Bm[4][4], C[4][4];     // C: q x q, full storage (kept symmetric)
   double pv[8];
@@ -565,7 +563,7 @@ LM_NOINLINE bool riccati_backward(const Params& P, const Mesh& M, const Options&
     const double zla = TL_CUR(tb, BK_CUR, F_ZLA), zua = TL_CUR(tb, BK_CUR, F_ZUA);
     const double zlu = TL_CUR(tb, BK_CUR, F_ZLU), zuu = TL_CUR(tb, BK_CUR, F_ZUU);
     const double kap = tl_ld(tb, TL_H) * P.T;
-    const double taum = mT * tl_ld(tb, TL_TAU);
+    const double taum = P.mT * tl_ld(tb, TL_TAU);
     Accel1 f;
     accel_first(P, zn[0], zn[2], zn[4], taum * tf, f);
     StageJac J;
@@ -727,7 +725,6 @@ LM_NOINLINE void riccati_forward(const Params& P, const Mesh& M, const Options& 
   const int N = M.N;
   const double tf = c0.tf;
   const int so = src * N_ITER;
-  const double mT = P.mflow * P.T;
   const double wdc = O.w_dcost;
   tl_begin();
   fw_stage_copy(M, W, 1, so);
@@ -747,7 +744,7 @@ LM_NOINLINE void riccati_forward(const Params& P, const Mesh& M, const Options& 
     for (int i = 0; i < 7; ++i) zn[i] = tl_ld(tb, FW_Z + i);
     const double u = zn[6];
     const double kap = tl_ld(tb, TL_H) * P.T;
-    const double taum = mT * tl_ld(tb, TL_TAU);
+    const double taum = P.mT * tl_ld(tb, TL_TAU);
     Accel1 f;
     accel_first(P, zn[0], zn[2], zn[4], taum * tf, f);
     StageJac J;

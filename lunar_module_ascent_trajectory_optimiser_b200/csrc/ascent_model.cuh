@@ -55,6 +55,8 @@ struct Params {
   // is the MV: the angledot row loses its link to the previous node (angledot_k = beta*u_k with u
   // unbounded), which makes angle_k = angle_{k-1} + alpha*angledot_k a free variable per step.
   double coup5;
+  double mT;      // mflow * T: mass(tau) = mT * tau * tf (LO:123); read per stage, kept here so that it is a
+                  // shared-memory load and not a spilled register
 };
 
 // ---------------------------------------------------------------------------------------

@@ -27,7 +27,7 @@ static Params make_params(double Ft, double M0, double Mdot, double addm, double
   P.vt2 = (vt / P.S) * (vt / P.S);
   P.rt = (R0 + P.S) / P.S; P.R0S = R0 / P.S;
   P.tf_ub = std::fmin(1.0, 1.0 / (P.mflow * T));
-  P.fuel = fuel; P.Sinv = 1.0 / P.S; P.coup5 = 1.0;
+  P.fuel = fuel; P.Sinv = 1.0 / P.S; P.coup5 = 1.0; P.mT = P.mflow * P.T;
   return P;
 }
 
@@ -118,7 +118,7 @@ extern "C" int hostsim_solve(const double* raw14, int nt, const double* time, do
   P.asc = r[7] / 3.0; P.T = r[10]; P.a_ub = r[12]; P.u_ub = r[13];
   const double vt = std::sqrt(P.GM / (P.R0 + 0.5 * (r[8] + r[9])));
   P.vt2 = (vt / P.S) * (vt / P.S); P.rt = (P.R0 + P.S) / P.S; P.R0S = P.R0 / P.S;
-  P.tf_ub = std::fmin(1.0, 1.0 / (P.mflow * P.T)); P.fuel = r[6]; P.Sinv = 1.0 / P.S; P.coup5 = 1.0;
+  P.tf_ub = std::fmin(1.0, 1.0 / (P.mflow * P.T)); P.fuel = r[6]; P.Sinv = 1.0 / P.S; P.coup5 = 1.0; P.mT = P.mflow * P.T;
   if (getenv("CIRCULAR")) { P.coup5 = 0.0; P.asc = 1.0; P.u_ub = 1e20; }
   const bool DC = O.w_dcost > 0;
   const int nfields = DC ? (int)dc::N_FIELDS : (int)N_FIELDS;
