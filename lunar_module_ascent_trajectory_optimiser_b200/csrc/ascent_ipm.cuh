@@ -605,7 +605,7 @@ LM_HD void fw7_stage_copy(const Mesh& M, const Ws& W, int k, int so) {
 
 enum : int { EV_READ_PI = 0, EV_NEWTON = 1, EV_LSQ = 2 };
 
-LM_NOINLINE void eval_pass(const Params& P, const Mesh& M, const Options& O, const Ws& W, int src, int dst,
+LM_SWEEP void eval_pass(const Params& P, const Mesh& M, const Options& O, const Ws& W, int src, int dst,
                            const Scal& c0, const TermStep& ts, double mu, double dw, double alpha,
                            double alpha_z, double alpha_lam, int mode, Scal& t, double* pimax_out) {
   const int N = M.N;
@@ -815,7 +815,7 @@ double* spd = ws_opaque(sp + dd * LANES);
 // then the control is condensed (it enters through the angledot row only).  Only the feedback
 // gains K_k, k_k leave the SM; the cost-to-go P, p lives in registers.
 // ---------------------------------------------------------------------------------------
-LM_NOINLINE bool riccati_backward(const Params& P, const Mesh& M, const Options& O, const Ws& W, int src,
+LM_SWEEP bool riccati_backward(const Params& P, const Mesh& M, const Options& O, const Ws& W, int src,
                                   const Scal& c0, double mu, double dw, bool ls, double* dtf_out) {
   // ls == true: least-squares multiplier estimate (IPOPT section 3.6): Hessian := I, defects := 0,
   // gradient := grad f - zL + zU.
@@ -1012,7 +1012,7 @@ struct RatioMax {
   LM_HD void push(double num, double den) { if (num * d > n * den) { n = num; d = den; } }
 };
 
-LM_NOINLINE void riccati_forward(const Params& P, const Mesh& M, const Options& O, const Ws& W, int src,
+LM_SWEEP void riccati_forward(const Params& P, const Mesh& M, const Options& O, const Ws& W, int src,
                                  const Scal& c0, double mu, double tau, double dtf, bool ls, TermStep& ts,
                                  StepInfo& si) {
   const int N = M.N;
@@ -1254,47 +1254,49 @@ LM_HD bool ipm_iterate_t(const Params& P, const Mesh& M, const Options& O, const
     else dw *= (ctl.dw_last == 0.0) ? 100.0 : 8.0;
     if (dw > 1e40) break;
   }
-  Scal trial;
-  if (ls) {
-    // least-squares multipliers for the defect rows; discarded if the solve failed or they are huge
-    bool have = false;
-    if (fact_ok) {
-      StepInfo s0;
-      double pimax = 0.0;
-      SW::forward(P, M, O, W, S.src, cur, ctl.mu, ctl.tau, dtf, true, S.ts, s0);
-      SW::eval(P, M, O, W, S.src, 1 - S.src, cur, S.ts, ctl.mu, 0.0, 0.0, 0.0, 1.0, EV_LSQ, trial, &pimax);
-      have = pimax <= 1e3 * dmax(1.0, O.obj_scale) && fabs(S.ts.dnu3) <= 1e3 * dmax(1.0, O.obj_scale);
-#if defined(LMATO_TRACE) && !defined(__CUDA_ARCH__)
-      printf("LS multipliers: pimax %.3e dnu3 %.3e dtf %.3e -> %s\n", pimax, S.ts.dnu3, dtf, have ? "used" : "discarded");
-#endif
-    }
-    if (!have) SW::eval(P, M, O, W, S.src, 1 - S.src, cur, S.ts, ctl.mu, 0.0, 0.0, 0.0, 0.0, EV_READ_PI, trial, nullptr);
-    cur = trial; S.src = 1 - S.src;
-    ctl.theta_max = 1e4 * dmax(1.0, cur.theta);
-    ctl.theta_min = 1e-4 * dmax(1.0, cur.theta);
-    S.phase = PH_NEWTON;
-    return false;
-  }
-  if (!fact_ok) { ctl.status = polishing ? ST_CONVERGED : ST_INERTIA_FAIL; return true; }
+  // The three sweeps are inlined into the kernel, so each has exactly one call site: the
+  // least-squares multiplier estimate ("iteration 0") runs through the same forward sweep and the
+  // same trial loop as a Newton iteration, with its own modes.
+  if (!ls && !fact_ok) { ctl.status = polishing ? ST_CONVERGED : ST_INERTIA_FAIL; return true; }
   if (dw > 0.0) ctl.dw_last = dw;
   StepInfo si;
-  SW::forward(P, M, O, W, S.src, cur, ctl.mu, ctl.tau, dtf, false, S.ts, si);
-  if (!(si.dphi == si.dphi) || !(si.dxmax < 1e300)) { ctl.status = polishing ? ST_CONVERGED : ST_NUMERICAL; return true; }
+  si.a_max = 0.0; si.a_z = 0.0; si.dphi = 0.0; si.dxmax = 0.0;
+  if (fact_ok) SW::forward(P, M, O, W, S.src, cur, ctl.mu, ctl.tau, dtf, ls, S.ts, si);
+  if (!ls && (!(si.dphi == si.dphi) || !(si.dxmax < 1e300))) { ctl.status = polishing ? ST_CONVERGED : ST_NUMERICAL; return true; }
   // filter line search (IPOPT section 2.3)
   const double theta = cur.theta;
   const double phi = cur.fobj - ctl.mu * cur.sumlog;
   const double dphi = si.dphi;
   const double g_th = 1e-5, g_ph = 1e-8, s_th = 1.1, s_ph = 2.3, eta = 1e-8, delta = 1.0;
-  double alpha = si.a_max;
   bool accepted = false, ftype = false;
   // switching condition (IPOPT eq. 19): alpha * (-dphi)^s_ph > delta * theta^s_th.  The two powers
   // do not depend on alpha, so they are evaluated once per iteration.
-  const bool sw_possible = (theta <= ctl.theta_min) && (dphi < 0.0);
+  const bool sw_possible = !ls && (theta <= ctl.theta_min) && (dphi < 0.0);
   const double sw_lhs = sw_possible ? pow(-dphi, s_ph) : 0.0;
   const double sw_rhs = sw_possible ? delta * pow(theta, s_th) : 0.0;
+  // trial parameters.  Least-squares phase: the point does not move; the first pass takes the
+  // least-squares multipliers of the defect rows (alpha_lam = 1), and if the solve failed or they
+  // are huge a second pass (alpha_lam = 0) keeps the old ones.
+  Scal trial;
+  double alpha = ls ? 0.0 : si.a_max;
+  const double a_z = ls ? 0.0 : si.a_z;
+  const double dw_eval = ls ? 0.0 : dw;
+  double a_lam = ls ? (fact_ok ? 1.0 : 0.0) : alpha;
+  int mode = ls ? (fact_ok ? EV_LSQ : EV_READ_PI) : EV_NEWTON;
   for (int lsi = 0; lsi < O.max_ls; ++lsi) {
-    SW::eval(P, M, O, W, S.src, 1 - S.src, cur, S.ts, ctl.mu, dw, alpha, si.a_z, alpha,
-             lsi == 0 ? EV_NEWTON : EV_READ_PI, trial, nullptr);
+    double pimax = 0.0;
+    SW::eval(P, M, O, W, S.src, 1 - S.src, cur, S.ts, ctl.mu, dw_eval, alpha, a_z, a_lam, mode, trial, &pimax);
+    if (ls) {
+      if (mode == EV_LSQ) {
+        const bool have = pimax <= 1e3 * dmax(1.0, O.obj_scale) && fabs(S.ts.dnu3) <= 1e3 * dmax(1.0, O.obj_scale);
+#if defined(LMATO_TRACE) && !defined(__CUDA_ARCH__)
+        printf("LS multipliers: pimax %.3e dnu3 %.3e dtf %.3e -> %s\n", pimax, S.ts.dnu3, dtf, have ? "used" : "discarded");
+#endif
+        if (!have) { mode = EV_READ_PI; a_lam = 0.0; continue; }
+      }
+      accepted = true;
+      break;
+    }
     const double th_t = trial.theta;
     const double ph_t = trial.fobj - ctl.mu * trial.sumlog;
     bool ok = (th_t <= ctl.theta_max) && (ph_t == ph_t) && (ph_t < 1e299) && filter_ok(ctl, th_t, ph_t);
@@ -1310,6 +1312,15 @@ LM_HD bool ipm_iterate_t(const Params& P, const Mesh& M, const Options& O, const
         fabs(ph_t - phi) <= O.tol * dmax(1.0, fabs(phi))) { ok = true; ftype = true; }
     if (ok) { accepted = true; break; }
     alpha *= 0.5;
+    a_lam = alpha;
+    mode = EV_READ_PI;
+  }
+  if (ls) {
+    cur = trial; S.src = 1 - S.src;
+    ctl.theta_max = 1e4 * dmax(1.0, cur.theta);
+    ctl.theta_min = 1e-4 * dmax(1.0, cur.theta);
+    S.phase = PH_NEWTON;
+    return false;
   }
 #if defined(LMATO_TRACE) && !defined(__CUDA_ARCH__)
   if (!accepted) printf("LS FAIL theta %.3e phi %.6e dphi %.3e amax %.3e dx %.2e th_t %.3e ph_t %.6e\n", theta, phi, dphi, si.a_max, si.dxmax, trial.theta, trial.fobj - ctl.mu * trial.sumlog);

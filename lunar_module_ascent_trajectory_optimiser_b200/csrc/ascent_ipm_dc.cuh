@@ -276,7 +276,7 @@ LM_HD void fw_stage_copy(const Mesh& M, const Ws& W, int k, int so) {
 // evaluation pass (see ascent_ipm.cuh: eval_pass); differences: u is a state of the node, the u row
 // and its multiplier lam_6, the move slack pair (p, n, z_p, z_n) in the merit and the residuals.
 // ---------------------------------------------------------------------------------------
-LM_NOINLINE void eval_pass(const Params& P, const Mesh& M, const Options& O, const Ws& W, int src, int dst,
+LM_SWEEP void eval_pass(const Params& P, const Mesh& M, const Options& O, const Ws& W, int src, int dst,
                            const Scal& c0, const TermStep& ts, double mu, double dw, double alpha,
                            double alpha_z, double alpha_lam, int mode, Scal& t, double* pimax_out) {
   const int N = M.N;
@@ -519,7 +519,7 @@ double* spd = ws_opaque(sp + dd * LANES);
 // backward Riccati sweep, 8 states: p = (y,vy,x,vx), q = (angle, angledot, u, tf); the control is the
 // move v (enters the u row with coefficient 1; its cost is the condensed slack pair, struct Move).
 // ---------------------------------------------------------------------------------------
-LM_NOINLINE bool riccati_backward(const Params& P, const Mesh& M, const Options& O, const Ws& W, int src,
+LM_SWEEP bool riccati_backward(const Params& P, const Mesh& M, const Options& O, const Ws& W, int src,
                                   const Scal& c0, double mu, double dw, bool ls, double* dtf_out) {
   const int N = M.N;
   const double tf = c0.tf;
@@ -719,7 +719,7 @@ LM_NOINLINE bool riccati_backward(const Params& P, const Mesh& M, const Options&
 // ---------------------------------------------------------------------------------------
 // forward sweep, 8 states
 // ---------------------------------------------------------------------------------------
-LM_NOINLINE void riccati_forward(const Params& P, const Mesh& M, const Options& O, const Ws& W, int src,
+LM_SWEEP void riccati_forward(const Params& P, const Mesh& M, const Options& O, const Ws& W, int src,
                                  const Scal& c0, double mu, double tau, double dtf, bool ls, TermStep& ts,
                                  StepInfo& si) {
   const int N = M.N;

@@ -23,10 +23,17 @@
 #define LM_HD __host__ __device__ __forceinline__
 #define LM_D __device__ __forceinline__
 #define LM_NOINLINE __host__ __device__ __noinline__
+// The three sweeps have one call site each and are inlined into the kernel: as ABI functions every
+// global access paid two R2UR moves for its memory descriptor and scalar arguments travelled through
+// the local-memory stack.
+#ifndef LM_SWEEP
+#define LM_SWEEP __host__ __device__ __forceinline__
+#endif
 #else
 #define LM_HD inline
 #define LM_D inline
 #define LM_NOINLINE
+#define LM_SWEEP inline
 #endif
 
 namespace lmato {
