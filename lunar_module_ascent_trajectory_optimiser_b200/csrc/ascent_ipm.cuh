@@ -108,6 +108,8 @@ struct Ws {
   double* p;             // base + (warp * N_FIELDS) * 32 + lane
   long SS;               // stage stride in doubles = n_warps * N_FIELDS * 32
   TileRef tl;            // this lane's column of the warp's two staging tiles
+  mutable int ls_flag;   // 1 while the least-squares multiplier estimate runs: the sweeps re-read it from
+                         // shared memory every stage (as a register it was spilled to local memory)
   LM_HD double* stage(int k) const { return ws_opaque(p + (long)k * SS); }
 };
 #define WS_AT(sp, row) (sp)[(row) * LANES]
@@ -816,7 +818,8 @@ double* spd = ws_opaque(sp + dd * LANES);
 // gains K_k, k_k leave the SM; the cost-to-go P, p lives in registers.
 // ---------------------------------------------------------------------------------------
 LM_SWEEP bool riccati_backward(const Params& P, const Mesh& M, const Options& O, const Ws& W, int src,
-                                  const Scal& c0, double mu, double dw, bool ls, double* dtf_out) {
+                                  const Scal& c0, double mu, double dw, bool ls_arg, double* dtf_out) {
+  const bool ls = ls_arg;
   // ls == true: least-squares multiplier estimate (IPOPT section 3.6): Hessian := I, defects := 0,
   // gradient := grad f - zL + zU.
   const int N = M.N;
@@ -855,6 +858,7 @@ LM_SWEEP bool riccati_backward(const Params& P, const Mesh& M, const Options& O,
     if (k > 1) bk7_stage_copy(M, W, k - 1, so); else tl_commit();
     tl_wait_prev();
     const TileRef tb = tl_buf(W, k);
+    const bool ls = W.ls_flag != 0;      // shadows the argument: a shared-memory load per stage
     double lam[6], zm[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i) lam[i] = TL7_CUR(tb, BK_CUR, F_LAM + i);
@@ -1013,8 +1017,9 @@ struct RatioMax {
 };
 
 LM_SWEEP void riccati_forward(const Params& P, const Mesh& M, const Options& O, const Ws& W, int src,
-                                 const Scal& c0, double mu, double tau, double dtf, bool ls, TermStep& ts,
+                                 const Scal& c0, double mu, double tau, double dtf, bool ls_arg, TermStep& ts,
                                  StepInfo& si) {
+  const bool ls = ls_arg;
   const int N = M.N;
   const double tf = c0.tf;
   const int so = src * N_ITER;
@@ -1031,6 +1036,7 @@ LM_SWEEP void riccati_forward(const Params& P, const Mesh& M, const Options& O, 
     if (k < N) fw7_stage_copy(M, W, k + 1, so); else tl_commit();
     tl_wait_prev();
     const TileRef tb = tl_buf(W, k);
+    const bool ls = W.ls_flag != 0;      // shadows the argument: a shared-memory load per stage
     double zn[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i) zn[i] = tl_ld(tb, FW_Z + i);
@@ -1212,6 +1218,7 @@ LM_HD bool ipm_iterate_t(const Params& P, const Mesh& M, const Options& O, const
   const int n_eq = SW::n_eq(N);
   const int n_bd = SW::n_bd(N);
   const bool ls = (S.phase == PH_LSQ);
+  W.ls_flag = ls ? 1 : 0;
   if (!ls) {
     S.err0 = kkt_error(cur, 0.0, n_eq, n_bd);
     // barrier parameter update (IPOPT eq. 7)

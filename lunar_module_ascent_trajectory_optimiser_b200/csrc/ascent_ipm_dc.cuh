@@ -520,7 +520,8 @@ double* spd = ws_opaque(sp + dd * LANES);
 // move v (enters the u row with coefficient 1; its cost is the condensed slack pair, struct Move).
 // ---------------------------------------------------------------------------------------
 LM_SWEEP bool riccati_backward(const Params& P, const Mesh& M, const Options& O, const Ws& W, int src,
-                                  const Scal& c0, double mu, double dw, bool ls, double* dtf_out) {
+                                  const Scal& c0, double mu, double dw, bool ls_arg, double* dtf_out) {
+  const bool ls = ls_arg;
   const int N = M.N;
   const double tf = c0.tf;
   const int so = src * N_ITER;
@@ -554,6 +555,7 @@ LM_SWEEP bool riccati_backward(const Params& P, const Mesh& M, const Options& O,
     if (k > 1) bk_stage_copy(M, W, k - 1, so); else tl_commit();
     tl_wait_prev();
     const TileRef tb = tl_buf(W, k);
+    const bool ls = W.ls_flag != 0;      // shadows the argument: a shared-memory load per stage
     double lam[6], zm[7];
 #pragma unroll
     for (int i = 0; i < 6; ++i) lam[i] = TL_CUR(tb, BK_CUR, F_LAM + i);
@@ -720,8 +722,9 @@ LM_SWEEP bool riccati_backward(const Params& P, const Mesh& M, const Options& O,
 // forward sweep, 8 states
 // ---------------------------------------------------------------------------------------
 LM_SWEEP void riccati_forward(const Params& P, const Mesh& M, const Options& O, const Ws& W, int src,
-                                 const Scal& c0, double mu, double tau, double dtf, bool ls, TermStep& ts,
+                                 const Scal& c0, double mu, double tau, double dtf, bool ls_arg, TermStep& ts,
                                  StepInfo& si) {
+  const bool ls = ls_arg;
   const int N = M.N;
   const double tf = c0.tf;
   const int so = src * N_ITER;
@@ -739,6 +742,7 @@ LM_SWEEP void riccati_forward(const Params& P, const Mesh& M, const Options& O, 
     if (k < N) fw_stage_copy(M, W, k + 1, so); else tl_commit();
     tl_wait_prev();
     const TileRef tb = tl_buf(W, k);
+    const bool ls = W.ls_flag != 0;      // shadows the argument: a shared-memory load per stage
     double zn[7];
 #pragma unroll
     for (int i = 0; i < 7; ++i) zn[i] = tl_ld(tb, FW_Z + i);
