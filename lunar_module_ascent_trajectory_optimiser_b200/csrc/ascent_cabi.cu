@@ -126,6 +126,46 @@ __device__ __forceinline__ Params derive_params(const double* __restrict__ p, lo
 // shared memory are bank-conflict free (stride 19 doubles = 38 words; 38 mod 32 = 6).
 struct alignas(8) ParamsSlot { Params p; double pad[(sizeof(Params) / 8) % 2 == 0 ? 1 : 2]; };
 
+// Results of one finished problem (LO:178-202: tf, the per-node values of all ten variables, final
+// mass, status).  The iterate is read back from the thread's workspace column; ydoubledot,
+// xdoubledot and mass, which the device formulation eliminates, are recomputed (LO:123, 127-136).
+template <class SW>
+__device__ __noinline__ void write_results(const KArgs& a, const Params& P, const Ws& W, const IpmState& S, long b) {
+  SolveOut out;
+  ipm_result(S, out);
+  const int nt = a.N + 1;
+  a.tf[b] = out.tf;
+  a.fmass[b] = P.M0 - P.fuel * (P.mflow * P.T * out.tf);   // mass(nt-1) = mflow*T*tf (LO:123)
+  a.status[b] = out.status;
+  a.iters[b] = out.iters;
+  if (a.kkt) a.kkt[b] = out.kkt;
+  if (!a.traj) return;
+  double* __restrict__ t = a.traj;
+  const long B = a.B;
+#pragma unroll
+  for (int v = 0; v < LMATO_NVAR; ++v) t[((long)v * nt) * B + b] = 0.0;   // node 0 pinned
+  for (int k = 1; k <= a.N; ++k) {
+    const double* sp = W.stage(k);
+    double z[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) z[i] = WS_AT(sp, out.cur * SW::NITER + SW::FZ + i);
+    const double u = WS_AT(sp, out.cur * SW::NITER + SW::FU);
+    const double m = P.mflow * P.T * a.tau[k] * out.tf;
+    double ay, ax;
+    accel_value(P, z[0], z[2], z[4], m, ay, ax);
+    t[((long)LMATO_V_Y * nt + k) * B + b] = z[0];
+    t[((long)LMATO_V_YDOT * nt + k) * B + b] = z[1];
+    t[((long)LMATO_V_YDOUBLEDOT * nt + k) * B + b] = ay;
+    t[((long)LMATO_V_X * nt + k) * B + b] = z[2];
+    t[((long)LMATO_V_XDOT * nt + k) * B + b] = z[3];
+    t[((long)LMATO_V_XDOUBLEDOT * nt + k) * B + b] = ax;
+    t[((long)LMATO_V_ANGLE * nt + k) * B + b] = z[4];
+    t[((long)LMATO_V_ANGLEDOT * nt + k) * B + b] = z[5];
+    t[((long)LMATO_V_MASS * nt + k) * B + b] = m;
+    t[((long)LMATO_V_ANGLEDOUBLEDOT * nt + k) * B + b] = u;
+  }
+}
+
 // SW = Sweeps7 (dcost = 0) or Sweeps8 (with the reference's move-suppression term, LO:99)
 template <class SW>
 __global__ void __launch_bounds__(kBlock, kBlocksPerSM) ascent_ipm_kernel(KArgs a) {
@@ -152,9 +192,9 @@ __global__ void __launch_bounds__(kBlock, kBlocksPerSM) ascent_ipm_kernel(KArgs 
   Ws* sW = reinterpret_cast<Ws*>(sTiles + (size_t)(kBlock / 32) * 2 * TILE_ROWS * LANES);   // after the tiles
   sW[threadIdx.x] = Ws{a.ws + ((slot / LANES) * SW::NFIELDS) * LANES + lane, nwarps * SW::NFIELDS * LANES, tile0};
   const Ws& W = sW[threadIdx.x];
-  const int nt = a.N + 1;
   IpmState S;
   bool active = false;        // this lane holds an unfinished problem
+  bool pending = false;       // this lane holds a finished problem whose results are not written yet
   bool exhausted = false;     // the queue is empty (warp-uniform)
   bool first = true;
   long b = -1;
@@ -162,7 +202,15 @@ __global__ void __launch_bounds__(kBlock, kBlocksPerSM) ascent_ipm_kernel(KArgs 
   unsigned round = 0;
   while (true) {
     // ---- a warp whose 32 problems are all finished claims the next 32 (warp-uniform branch) ----
-    if (!exhausted && !__any_sync(0xffffffffu, active)) {
+    const bool chunk_done = !__any_sync(0xffffffffu, active);
+    // ---- a finished chunk writes its results with all 32 lanes together: every row of the
+    //      [variable][node][problem] output is then one coalesced 256-byte store per warp (the output
+    //      may be pinned host memory written over PCIe while the other warps keep computing) ----
+    if (chunk_done && __any_sync(0xffffffffu, pending)) {
+      if (pending) write_results<SW>(a, P, W, S, b);
+      pending = false;
+    }
+    if (!exhausted && chunk_done) {
       // first chunk: static round-robin over CTAs (spreads a small batch over all SMs);
       // afterwards: the device-wide queue
       int chunk = 0;
@@ -206,43 +254,13 @@ __global__ void __launch_bounds__(kBlock, kBlocksPerSM) ascent_ipm_kernel(KArgs 
         continue;
       }
       active = false;
-      SolveOut out;
-      ipm_result(S, out);
       if (a.ref_mode == 1) {
+        SolveOut out;
+        ipm_result(S, out);
         SW::store_ref(P, M, W, out.cur, S.cur, S.ctl.mu, out.status == ST_CONVERGED, a.ref);
         continue;
       }
-      a.tf[b] = out.tf;
-      a.fmass[b] = P.M0 - P.fuel * (P.mflow * P.T * out.tf);   // mass(nt-1) = mflow*T*tf (LO:123)
-      a.status[b] = out.status;
-      a.iters[b] = out.iters;
-      if (a.kkt) a.kkt[b] = out.kkt;
-      if (a.traj) {
-        double* __restrict__ t = a.traj;
-        const long B = a.B;
-#pragma unroll
-        for (int v = 0; v < LMATO_NVAR; ++v) t[((long)v * nt) * B + b] = 0.0;   // node 0 pinned
-        for (int k = 1; k <= a.N; ++k) {
-          const double* sp = W.stage(k);
-          double z[6];
-#pragma unroll
-          for (int i = 0; i < 6; ++i) z[i] = WS_AT(sp, out.cur * SW::NITER + SW::FZ + i);
-          const double u = WS_AT(sp, out.cur * SW::NITER + SW::FU);
-          const double m = P.mflow * P.T * a.tau[k] * out.tf;
-          double ay, ax;
-          accel_value(P, z[0], z[2], z[4], m, ay, ax);
-          t[((long)LMATO_V_Y * nt + k) * B + b] = z[0];
-          t[((long)LMATO_V_YDOT * nt + k) * B + b] = z[1];
-          t[((long)LMATO_V_YDOUBLEDOT * nt + k) * B + b] = ay;
-          t[((long)LMATO_V_X * nt + k) * B + b] = z[2];
-          t[((long)LMATO_V_XDOT * nt + k) * B + b] = z[3];
-          t[((long)LMATO_V_XDOUBLEDOT * nt + k) * B + b] = ax;
-          t[((long)LMATO_V_ANGLE * nt + k) * B + b] = z[4];
-          t[((long)LMATO_V_ANGLEDOT * nt + k) * B + b] = z[5];
-          t[((long)LMATO_V_MASS * nt + k) * B + b] = m;
-          t[((long)LMATO_V_ANGLEDOUBLEDOT * nt + k) * B + b] = u;
-        }
-      }
+      pending = true;      // results are written when the whole chunk is done (see above)
     }
   }
 }
@@ -533,6 +551,17 @@ lmato_status_t lmato_last_kernel_ms(lmato_handle* h, double* ms) {
   return LMATO_OK;
 }
 
+// Device-usable alias of a host buffer if the caller pinned it (cudaHostAlloc / cudaHostRegister /
+// torch pin_memory), else nullptr.  With unified addressing pinned host memory is mapped into the
+// device's address space, so the kernel can store results straight into it.
+static double* pinned_alias(double* host) {
+  if (!host) return nullptr;
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (attr.type != cudaMemoryTypeHost || !attr.devicePointer) return nullptr;
+  return static_cast<double*>(attr.devicePointer);
+}
+
 lmato_status_t lmato_solve_batch_host(lmato_handle* h, const double* params, int64_t B,
                                       double* out_traj, double* out_tf, double* out_final_mass,
                                       int32_t* out_status, int32_t* out_iters, double* out_kkt) {
@@ -551,17 +580,22 @@ lmato_status_t lmato_solve_batch_host(lmato_handle* h, const double* params, int
     CUDA_TRY(cudaMalloc(&h->d_params, pbytes));
     h->params_bytes = pbytes;
   }
+  // The per-node trajectories are 16 KB per problem (1 GB for 65 536 problems).  If the caller's
+  // buffer is pinned the kernel writes them there directly, chunk by chunk as problems finish, so the
+  // transfer over PCIe overlaps the solve; a pageable buffer is filled by a copy after the kernel.
+  double* traj_alias = pinned_alias(out_traj);
   const size_t traj_n = out_traj ? (size_t)LMATO_NVAR * h->nt * (size_t)B : 0;
-  // layout of d_out: traj | tf | fmass | kkt | status | iters
-  const size_t obytes = sizeof(double) * (traj_n + 3 * (size_t)B) + sizeof(int32_t) * 2 * (size_t)B;
+  const size_t traj_stage = traj_alias ? 0 : traj_n;
+  // layout of d_out: traj (only when staged) | tf | fmass | kkt | status | iters
+  const size_t obytes = sizeof(double) * (traj_stage + 3 * (size_t)B) + sizeof(int32_t) * 2 * (size_t)B;
   if (obytes > h->out_bytes) {
     if (h->d_out) CUDA_TRY(cudaFree(h->d_out));
     h->d_out = nullptr; h->out_bytes = 0;
     CUDA_TRY(cudaMalloc(&h->d_out, obytes));
     h->out_bytes = obytes;
   }
-  double* d_traj = out_traj ? h->d_out : nullptr;
-  double* d_tf = h->d_out + traj_n;
+  double* d_traj = out_traj ? (traj_alias ? traj_alias : h->d_out) : nullptr;
+  double* d_tf = h->d_out + traj_stage;
   double* d_fm = d_tf + B;
   double* d_kkt = d_fm + B;
   int32_t* d_st = (int32_t*)(d_kkt + B);
@@ -570,7 +604,8 @@ lmato_status_t lmato_solve_batch_host(lmato_handle* h, const double* params, int
   CUDA_TRY(cudaMemcpyAsync(h->d_params, params, pbytes, cudaMemcpyHostToDevice, st));
   lmato_status_t rc = lmato_solve_batch(h, h->d_params, B, d_traj, d_tf, d_fm, d_st, d_it, d_kkt, st);
   if (rc != LMATO_OK) return rc;
-  if (out_traj) CUDA_TRY(cudaMemcpyAsync(out_traj, d_traj, sizeof(double) * traj_n, cudaMemcpyDeviceToHost, st));
+  if (out_traj && !traj_alias)
+    CUDA_TRY(cudaMemcpyAsync(out_traj, d_traj, sizeof(double) * traj_n, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaMemcpyAsync(out_tf, d_tf, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaMemcpyAsync(out_final_mass, d_fm, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
   if (out_kkt) CUDA_TRY(cudaMemcpyAsync(out_kkt, d_kkt, sizeof(double) * B, cudaMemcpyDeviceToHost, st));

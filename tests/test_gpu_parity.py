@@ -168,6 +168,15 @@ def test_ragged_batches_and_device_path(lm, B):
     assert torch.equal(raw["status"].cpu(), host.status.cpu())
     assert torch.equal(raw["traj"].cpu()[0].T, host.states["y"].cpu())
     assert int((host.status != 0).sum()) == 0
+    # host entry point: pinned result buffers are written by the kernel directly (zero copy),
+    # pageable ones through a staging copy; both must give what the device entry point gives
+    pinned = solver.alloc_outputs(B, True, on_device=False)
+    assert pinned["traj"].is_pinned()
+    pageable = {k: torch.full(v.shape, -7, dtype=v.dtype) for k, v in pinned.items()}
+    for out in (pinned, pageable):
+        r = solver.solve_rows(p.rows(B), out=out)
+        for k in ("traj", "tf", "final_mass", "status", "iterations", "kkt"):
+            assert torch.equal(r[k], raw[k].cpu()), k
 
 
 def test_empty_batch_and_errors(lm):
