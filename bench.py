@@ -228,16 +228,22 @@ def main():
     traj = not args.no_traj
     opts = lm.SolverOptions()
     solver = lm.AscentSolver(lm.Mesh(nt=nt), opts, device=dev)
-    p = lm.dispersed_params(B, seed=11 + rank)
-    rows_host = p.rows(B).pin_memory()
-    rows_dev = rows_host.to(dev)
+    # Successive steps get DIFFERENT batches (three draws of the same dispersion, cycled), so nothing
+    # a step computes -- including the warm start's reference solve, which starts from the previous
+    # call's reference -- can be a replay of the step before.
+    NBATCH = 3
+    rows_hosts = [lm.dispersed_params(B, seed=11 + rank + 1000 * j).rows(B).pin_memory() for j in range(NBATCH)]
+    rows_devs = [r.to(dev) for r in rows_hosts]
+    rows_host, rows_dev = rows_hosts[0], rows_devs[0]
+    step_no = [0]
     gathered = torch.empty((world * B, 4), dtype=torch.float64, device=dev) if world > 1 else None
 
     out_dev = solver.alloc_outputs(B, traj, on_device=True)      # result buffers, reused every step
     out_host = solver.alloc_outputs(B, traj, on_device=False)    # pinned host memory for the e2e leg
 
     def step_device():
-        raw = solver.solve_rows(rows_dev, trajectories=traj, out=out_dev)
+        step_no[0] += 1
+        raw = solver.solve_rows(rows_devs[step_no[0] % NBATCH], trajectories=traj, out=out_dev)
         if world > 1:   # the single allgather of per-problem results (tf, final mass, status, iterations)
             send = torch.stack([raw["tf"], raw["final_mass"], raw["status"].double(), raw["iterations"].double()], dim=1)
             dist.all_gather_into_tensor(gathered, send)
@@ -284,15 +290,15 @@ def main():
     value = conv_all / (ms * 1e-3)
 
     # ---- end-to-end through the host API (pinned host tensors in, pinned host tensors out) ----
-    for _ in range(2):
-        solver.solve_rows(rows_host, trajectories=traj, out=out_host)
+    for j in range(2):
+        solver.solve_rows(rows_hosts[j % NBATCH], trajectories=traj, out=out_host)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     conv_e = 0
-    for _ in range(args.steps):
-        r = solver.solve_rows(rows_host, trajectories=traj, out=out_host)   # synchronous: H2D + solve + D2H
+    for j in range(args.steps):
+        r = solver.solve_rows(rows_hosts[(j + 2) % NBATCH], trajectories=traj, out=out_host)   # synchronous: H2D + solve + D2H
         conv_e += int((r["status"] == 0).sum())
     e2e_s = time.perf_counter() - t0
     e = torch.tensor([e2e_s, float(conv_e)], dtype=torch.float64, device=dev)
@@ -336,7 +342,7 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"cfg4: elliptical ascent (Launch_Optimiser.py defaults), nt={nt}, NODES=2, "
-                               f"6-parameter dispersions, seed 11+rank",
+                               f"6-parameter dispersions; {NBATCH} different draws (seed 11+rank+1000j) cycled over the steps",
                    "batch_per_gpu": B, "global_batch": B * world, "tol": opts.tol, "obj_scale": opts.obj_scale,
                    "dcost": 1e-5 if opts.dcost is None else opts.dcost, "warm_start": bool(opts.warm_start),
                    "trajectories": traj, "parallelism": f"index-sharded x{world}, one allgather of results" if world > 1 else "single GPU",
@@ -367,7 +373,7 @@ def main():
         _tf, st, it, wall = pool.solve(rows_host[:, :n].numpy(), nt, opts.tol, opts.obj_scale)
         pool.close()
         # parity spot-check of this very run: same inputs, GPU vs oracle
-        gpu_tf = raw["tf"][:n].cpu().numpy()
+        gpu_tf = solver.solve_rows(rows_devs[0][:, :n].contiguous(), trajectories=False)["tf"].cpu().numpy()
         line["cpu_baseline"] = {"value": float((st == 0).sum() / wall), "unit": "solves/s", "cores": pool.cores, "kind": "port",
                                 "sample": f"first {n} problems of this rank's batch, one problem per process on {pool.cores} cores",
                                 "note": "oracle restatement (numpy/scipy sparse IPM), not GEKKO/IPOPT (absent from this image)",

@@ -67,7 +67,8 @@ struct KArgs {
   int* counter;
   int model;             // lmato_model_t
   double* ref;           // reference column (warm start), or null
-  int ref_mode;          // 0 cold start; 1 solve and store the reference; 2 start from the reference
+  int ref_mode;          // 0 cold start; 1 solve and store the reference (starting from the previous one,
+                         // if any); 2 start from the reference
   Options O;
 };
 
@@ -229,7 +230,10 @@ __global__ void __launch_bounds__(kBlock, kBlocksPerSM) ascent_ipm_kernel(KArgs 
           P = derive_params(a.params, a.B, b, a.model);
           ipm_begin(O, S);
           double mu0 = 0.0;
-          if (a.ref_mode == 2 && SW::load_ref(P, M, O, W, a.ref, S.cur, &mu0)) {
+          // ref_mode 2: start from the batch reference.  ref_mode 1 (the reference solve itself):
+          // start from the previous call's reference if the handle has one (consecutive batches of a
+          // campaign have nearly the same mean, so it re-converges in one or two iterations).
+          if (a.ref_mode != 0 && SW::load_ref(P, M, O, W, a.ref, S.cur, &mu0)) {
             S.warm = true;
             S.ctl.mu = mu0;
             S.ctl.tau = dmax(O.tau_min, 1.0 - mu0);
@@ -416,6 +420,7 @@ lmato_status_t lmato_create(lmato_handle** out, int32_t device, int32_t nt, cons
   CUDA_TRY(cudaMemcpy(H->d_tau, tau.data(), sizeof(double) * nt, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMalloc(&H->d_counter, sizeof(int)));
   CUDA_TRY(cudaMalloc(&H->d_ref, sizeof(double) * (size_t)dc::REF_ROWS * nt));   // dc:: is the larger layout
+  CUDA_TRY(cudaMemset(H->d_ref, 0, sizeof(double) * (size_t)dc::REF_ROWS * nt));   // REF_OK = 0: no reference yet
   CUDA_TRY(cudaMalloc(&H->d_refparams, sizeof(double) * (LMATO_NPARAM + 8)));
   CUDA_TRY(cudaEventCreate(&H->ev0));
   CUDA_TRY(cudaEventCreate(&H->ev1));
@@ -515,7 +520,8 @@ lmato_status_t lmato_solve_batch(lmato_handle* h, const double* params, int64_t 
   const int grid = (int)(slots / kBlock);
   CUDA_TRY(cudaEventRecord(h->ev0, st));
   if (h->opt.warm_start && B >= kWarmStartMinBatch) {
-    // reference problem = batch mean, solved down to mu_ref only (one thread, ~8 iterations)
+    // reference problem = batch mean, solved down to mu_ref only (one thread; ~10 iterations from the
+    // cold start on the first call, 1-2 from the previous call's reference afterwards)
     mean_params_kernel<<<LMATO_NPARAM, 256, 0, st>>>(params, B, h->d_refparams);
     CUDA_TRY(cudaGetLastError());
     KArgs r = a;

@@ -260,6 +260,16 @@ def test_warm_start_is_reproducible_and_faster(lm):
     assert float(rel[:9].max()) < STATE_RTOL, rel
     assert float(rel[9]) < 5e-3, rel           # the MV on the singular arc, see CONTROL_RTOL above
     assert float(res[True]["iterations"].double().mean()) < float(res[False]["iterations"].double().mean()) - 4
+    # A handle keeps its last reference and starts the next reference solve from it.  A second batch
+    # (different draws, and a deliberately different regime: +3 % thrust) solved on the used handle
+    # must equal the same batch solved on a fresh handle.
+    rows2 = lm.dispersed_params(B, seed=12).rows(B).cuda()
+    rows2[3] *= 1.03                      # row LMATO_P_FT (thrust)
+    used = solver.solve_rows(rows2)
+    fresh = lm.AscentSolver(lm.Mesh(), lm.SolverOptions(), device=0).solve_rows(rows2)
+    torch.cuda.synchronize()
+    assert int((used["status"] != 0).sum()) == 0 and int((fresh["status"] != 0).sum()) == 0
+    assert float((used["tf"] - fresh["tf"]).abs().max()) < 1e-10
 
 
 def test_dense_mesh_matches_golden(lm, golden_dir):
