@@ -89,9 +89,11 @@ typedef struct {
   int32_t max_ls;    /* max backtracking steps per iteration; default 40 */
   int32_t n_polish;  /* Newton iterations taken after tol is first met; default -1 = automatic: 2 with the
                         DCOST term (it regularises the flat control directions), 4 without (DESIGN.md "Tolerance") */
-  int32_t warm_start; /* 1 (default): batches of >= 16384 problems (below that the serial reference solve costs more than it saves) first solve the batch-mean problem down to
+  int32_t warm_start; /* 1 (default): batches of >= 1024 problems (below that the serial reference solve costs more than it saves) first solve the batch-mean problem down to
                          mu_ref and start every problem from that central-path point; a problem that fails
-                         from there is restarted from the generic cold start.  0: always cold start. */
+                         from there is restarted from the generic cold start.  0: always cold start.  2: warm start for
+                         every batch size.  The handle keeps its last reference and the next reference solve
+                         starts from it. */
   double mu_ref;     /* barrier parameter at which the reference solve stops; default 1e-3 */
   double dcost;      /* LO:99 angledoubledot.DCOST: l1 move suppression dcost*sum|MV_k - MV_{k-1}|; default
                         1e-5 (the reference's value); 0 switches the term off (7-state fast path) */

@@ -134,7 +134,7 @@ class SolverOptions:
     max_ls: int = 40
     mu_min_factor: float = 1e-3    # barrier floor = mu_min_factor * tol
     n_polish: int = -1             # Newton iterations after tol is first met; -1 = 2 with DCOST, 4 without
-    warm_start: bool = True        # batches >= 16384: start from the batch-mean problem's central path
+    warm_start: int = 1            # 1: batches >= 1024 start from the batch-mean problem's central path; 0: never; 2: always
     mu_ref: float = 1e-3           # barrier parameter at which that reference solve stops
     dcost: Optional[float] = None  # LO:99; None = take AscentParams.dcost (1e-5 in the reference)
     objective_nodes: int = 0       # APMonitor sums the objective over the horizon; 0 = nt-1
@@ -204,7 +204,7 @@ class AscentSolver:
         co = _cabi.LmatoOptions(tol=o.tol, mu_init=o.mu_init, obj_scale=o.obj_scale, tf_guess=o.tf_guess,
                                 delta_c=o.delta_c, mu_min_factor=o.mu_min_factor, max_iter=int(o.max_iter),
                                 max_ls=int(o.max_ls), n_polish=int(o.n_polish),
-                                warm_start=int(bool(o.warm_start)), mu_ref=o.mu_ref,
+                                warm_start=int(o.warm_start), mu_ref=o.mu_ref,
                                 dcost=float(1e-5 if o.dcost is None else o.dcost),
                                 kappa_eps=float(o.kappa_eps), objective_nodes=int(o.objective_nodes))
         _cabi.check(_cabi.lib().lmato_set_options(self._h, C.byref(co)), "lmato_set_options")

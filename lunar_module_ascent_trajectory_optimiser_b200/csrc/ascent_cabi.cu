@@ -48,7 +48,9 @@ constexpr int kBlocksPerSM = 1;
 // dynamic shared memory: the staging tiles, then one workspace view per thread
 constexpr size_t kTileSmem = (size_t)(kBlock / 32) * 2 * TILE_ROWS * LANES * sizeof(double) + kBlock * sizeof(Ws);
 // The warm start costs one serial single-problem solve (~13 ms); measured break-even is ~8k problems.
-constexpr long kWarmStartMinBatch = 16384;
+// measured break-even of the first call on a handle (7.6 ms single-thread reference solve against ~6 saved
+// iterations): 512-2048 problems; later calls re-converge the reference in ~1.5 ms and win at every size
+constexpr long kWarmStartMinBatch = 1024;
 
 struct KArgs {
   const double* params;  // [NPARAM][B]
@@ -444,7 +446,7 @@ lmato_status_t lmato_set_options(lmato_handle* h, const lmato_options* o) {
   if (!(o->tol > 0) || !(o->mu_init > 0) || !(o->obj_scale > 0) || !(o->delta_c > 0) ||
       !(o->tf_guess > 0 && o->tf_guess < 1) || o->max_iter < 0 || o->max_ls < 1 ||
       !(o->mu_min_factor > 0 && o->mu_min_factor <= 1) || o->n_polish < -1 ||
-      (o->warm_start != 0 && o->warm_start != 1) || !(o->mu_ref > 0 && o->mu_ref <= o->mu_init) ||
+      (o->warm_start < 0 || o->warm_start > 2) || !(o->mu_ref > 0 && o->mu_ref <= o->mu_init) ||
       !(o->dcost >= 0) || o->objective_nodes < 0 || !(o->kappa_eps >= 1.0)) {
     set_err("lmato_set_options: option out of range");
     return LMATO_ERR_INVALID;
@@ -519,7 +521,7 @@ lmato_status_t lmato_solve_batch(lmato_handle* h, const double* params, int64_t 
   a.ref = nullptr; a.ref_mode = 0;
   const int grid = (int)(slots / kBlock);
   CUDA_TRY(cudaEventRecord(h->ev0, st));
-  if (h->opt.warm_start && B >= kWarmStartMinBatch) {
+  if (h->opt.warm_start == 2 || (h->opt.warm_start == 1 && B >= kWarmStartMinBatch)) {
     // reference problem = batch mean, solved down to mu_ref only (one thread; ~10 iterations from the
     // cold start on the first call, 1-2 from the previous call's reference afterwards)
     mean_params_kernel<<<LMATO_NPARAM, 256, 0, st>>>(params, B, h->d_refparams);

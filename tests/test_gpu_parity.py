@@ -242,10 +242,10 @@ def test_circular_model_matches_golden_and_pdf(lm, golden_dir):
 
 def test_warm_start_is_reproducible_and_faster(lm):
     """The batch warm start (reference central-path point of the batch-mean problem) must not change
-    the answers: two solves of the same 16 384 problems from different start points agree on tf to
+    the answers: two solves of the same 4 096 problems from different start points agree on tf to
     rounding and on every state to well inside north_star's 1e-4, and the warm one needs fewer
     iterations."""
-    B = 16384          # the warm start engages from 16 384 problems
+    B = 4096           # the warm start engages from 1 024 problems
     rows = lm.dispersed_params(B, seed=11).rows(B).cuda()
     res = {}
     for warm in (False, True):
