@@ -28,7 +28,7 @@ from __future__ import annotations
 import ctypes as C
 import dataclasses
 import math
-from typing import Callable, Dict, Optional, Sequence, Union
+from typing import Callable, Dict, List, Optional, Sequence, Union
 
 import torch
 
@@ -406,6 +406,42 @@ def sharded_solve(rows: torch.Tensor, solve_fn: Callable[[torch.Tensor], Dict[st
     return out
 
 
+def multi_device_solve(rows: torch.Tensor, solvers: List["AscentSolver"], trajectories: bool = True,
+                       out_device: Union[str, torch.device, None] = None) -> Dict[str, torch.Tensor]:
+    """One host process, several GPUs (no torchrun): problem i goes to GPU ``floor(i*G/B)`` (the same
+    contiguous index partition as :func:`sharded_solve`).  The device entry point is asynchronous, so
+    all launches are issued first and every GPU solves its shard concurrently; the shards are then
+    copied into one result block on ``out_device`` (default: the first solver's device; peer copies
+    over NVLink) or into pinned host memory (``"cpu"``)."""
+    G = len(solvers)
+    B = int(rows.shape[1])
+    parts = []
+    for g, solver in enumerate(solvers):
+        lo, hi = shard_bounds(B, G, g)
+        shard = rows[:, lo:hi].to(solver.device, non_blocking=True).contiguous()
+        with torch.cuda.device(solver.device):
+            parts.append(solver.solve_rows(shard, trajectories) if hi > lo else None)
+    dst = torch.device(out_device) if out_device is not None else solvers[0].device
+    kw = dict(pin_memory=True) if dst.type == "cpu" else dict(device=dst)
+    ref = next(p for p in parts if p is not None)
+    keys = [k for k, v in ref.items() if v is not None]
+    out: Dict[str, Optional[torch.Tensor]] = {k: None for k in ref}
+    for k in keys:
+        shape = list(ref[k].shape)
+        shape[-1] = B
+        out[k] = torch.empty(shape, dtype=ref[k].dtype, **kw)
+    for g, part in enumerate(parts):
+        if part is None:
+            continue
+        lo, hi = shard_bounds(B, G, g)
+        with torch.cuda.device(solvers[g].device):
+            for k in keys:
+                out[k][..., lo:hi].copy_(part[k], non_blocking=True)
+    for solver in solvers:
+        torch.cuda.synchronize(solver.device)
+    return out
+
+
 def final_state_si(sol: AscentBatchSolution, params: AscentParams) -> torch.Tensor:
     """Final ascent state in the PDF's plotting frame (src 189-192): ``[4, B]`` = (-x*S, y*S+R0, -xdot*S, ydot*S)."""
     B = len(sol)
@@ -437,7 +473,8 @@ def _get_solver(mesh: Mesh, options: SolverOptions, device, model: str) -> Ascen
 
 def optimise_batch(params: AscentParams, mesh: Optional[Mesh] = None,
                    options: Optional[SolverOptions] = None, device=None, batch: Optional[int] = None,
-                   trajectories: bool = True, group=None) -> AscentBatchSolution:
+                   trajectories: bool = True, group=None,
+                   devices: Optional[Sequence[int]] = None) -> AscentBatchSolution:
     """Solve a batch of ascent problems (one per entry of the ``[B]`` parameter tensors).
 
     Results follow the placement of the inputs: CPU parameter tensors (or plain floats) give
@@ -447,6 +484,9 @@ def optimise_batch(params: AscentParams, mesh: Optional[Mesh] = None,
     ``group``: a ``torch.distributed`` process group (or ``True`` for the default group).  Every
     rank passes the same full batch; rank r solves the contiguous index shard
     ``[B*r/G, B*(r+1)/G)`` on its own GPU and one allgather returns the full result everywhere.
+
+    ``devices``: GPU indices to shard over from THIS process (same partition, no process group, no
+    collective: the shards are copied into one result block, see :func:`multi_device_solve`).
     """
     mesh = mesh or Mesh()
     options = options or SolverOptions()
@@ -454,6 +494,17 @@ def optimise_batch(params: AscentParams, mesh: Optional[Mesh] = None,
         options = dataclasses.replace(options, dcost=float(params.dcost))
     on_dev = any(isinstance(getattr(params, f.name), torch.Tensor) and getattr(params, f.name).is_cuda
                  for f in dataclasses.fields(params))
+    if devices is not None:
+        if group is not None:
+            raise ValueError("pass either `group` (one process per GPU) or `devices` (one process), not both")
+        if len(devices) == 0:
+            raise ValueError("`devices` is empty")
+        solvers = [_get_solver(mesh, options, d, params.model) for d in devices]
+        rows = params.rows(batch, device=solvers[0].device if on_dev else "cpu")
+        if not on_dev:
+            rows = rows.pin_memory()
+        raw = multi_device_solve(rows, solvers, trajectories, out_device=None if on_dev else "cpu")
+        return package_solution(raw, rows, solvers[0].time, params.model)
     solver = _get_solver(mesh, options, device, params.model)
     rows = params.rows(batch, device=solver.device if on_dev else "cpu")
     if group is not None:

@@ -357,3 +357,27 @@ def test_coast_orbit_matches_pdf_propagator(lm):
     cst = lm.final_state_si(c, lm.AscentParams.circular()).cuda()
     cf = solver.coast_orbit(cst, t_coast=6600.0, dt=1e-3)
     assert abs(float(cf["r_max"][0]) - 1738100.0 - 53108.4) < 5.0e3 and abs(float(cf["r_min"][0]) - 1738100.0 - 53108.4) < 5.0e3
+
+
+def test_single_process_device_list(lm):
+    """`optimise_batch(..., devices=[...])`: one host process shards the batch over a device list
+    (a plain function call, no torchrun).  With one GPU the list names it twice, which
+    exercises the partition and the reassembly; with two or more GPUs the shards run concurrently."""
+    B = 101
+    p = lm.dispersed_params(B, seed=21)
+    one = lm.optimise_batch(p)
+    ngpu = torch.cuda.device_count()
+    for devices in ([0, 0], [0, 0, 0]) + (([0, 1],) if ngpu >= 2 else ()):
+        many = lm.optimise_batch(p, devices=list(devices))
+        assert len(many) == B and int((many.status != 0).sum()) == 0
+        assert torch.equal(many.tf, one.tf) and torch.equal(many.iterations, one.iterations)
+        for k in one.states:
+            assert torch.equal(many.states[k], one.states[k]), k
+        assert torch.equal(many.control, one.control)
+    import dataclasses
+    pc = dataclasses.replace(p, **{f.name: getattr(p, f.name).cuda() for f in dataclasses.fields(p)
+                                   if isinstance(getattr(p, f.name), torch.Tensor)})
+    dev = lm.optimise_batch(pc, devices=[0, 0])
+    assert dev.tf.is_cuda and torch.equal(dev.tf.cpu(), one.tf)
+    with pytest.raises(ValueError):
+        lm.optimise_batch(p, devices=[])
