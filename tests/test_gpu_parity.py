@@ -381,3 +381,29 @@ def test_single_process_device_list(lm):
     assert dev.tf.is_cuda and torch.equal(dev.tf.cpu(), one.tf)
     with pytest.raises(ValueError):
         lm.optimise_batch(p, devices=[])
+
+
+def test_pathological_inputs_fail_fast_and_alone(lm):
+    """NaN / infinite / zero / negative parameters of one problem must come back as a non-zero status
+    within a normal batch time and must not disturb the other problems of the batch (the reference
+    raises `@error: Solution Not Found`, LO:177)."""
+    import time
+    from lunar_module_ascent_trajectory_optimiser_b200 import _cabi
+    solver = lm.AscentSolver(lm.Mesh(), lm.SolverOptions(), device=0)
+    base = lm.dispersed_params(64, seed=3).rows(64)
+    good = solver.solve_rows(base.cuda())
+    torch.cuda.synchronize()
+    for name, val in [("Ft", float("nan")), ("Ft", float("inf")), ("Ft", 0.0), ("Ft", -15346.0),
+                      ("M_dot", 0.0), ("M0", float("nan")), ("fuel_mass", 0.0),
+                      ("angle_doubledot_max", 0.0), ("r_periapsis", 0.0), ("final_time", 0.0)]:
+        rows = base.clone()
+        rows[_cabi.PARAM_ROWS.index(name), 5] = val
+        t0 = time.time()
+        raw = solver.solve_rows(rows.cuda())
+        torch.cuda.synchronize()
+        assert time.time() - t0 < 5.0, (name, val)
+        st = raw["status"].cpu()
+        assert int(st[5]) != 0, (name, val)
+        keep = torch.arange(64) != 5
+        assert int((st[keep] != 0).sum()) == 0, (name, val)
+        assert torch.equal(raw["tf"].cpu()[keep], good["tf"].cpu()[keep]), (name, val)
