@@ -1,10 +1,12 @@
-"""Developer A/B timing of one library build: B=65536 dispersions, kernel ms (CUDA events)."""
+"""Developer A/B timing of one library build: B dispersions, kernel ms (CUDA events); later calls on one handle.
+usage: gpu_ab.py [B] [nt] [kappa_eps]   (LMATO_LIB_OVERRIDE selects another build)"""
 import sys, torch
 sys.path.insert(0, '.')
 import lunar_module_ascent_trajectory_optimiser_b200 as lm
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 nt = int(sys.argv[2]) if len(sys.argv) > 2 else 200
-solver = lm.AscentSolver(lm.Mesh(nt=nt), lm.SolverOptions(), device=0)
+keps = float(sys.argv[3]) if len(sys.argv) > 3 else 30.0
+solver = lm.AscentSolver(lm.Mesh(nt=nt), lm.SolverOptions(kappa_eps=keps), device=0)
 rows = lm.dispersed_params(B).rows(B).cuda()
 best = 1e9
 for rep in range(4):
