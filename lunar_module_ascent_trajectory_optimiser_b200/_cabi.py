@@ -43,7 +43,7 @@ class LmatoError(RuntimeError):
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/ascent_cabi.cu for sm_100a into the in-tree shared library."""
-    srcs = [os.path.join(CSRC, f) for f in ("ascent_cabi.cu", "ascent_ipm.cuh", "ascent_model.cuh")]
+    srcs = [os.path.join(CSRC, f) for f in ("ascent_cabi.cu", "ascent_ipm.cuh", "ascent_ipm_dc.cuh", "ascent_model.cuh")]
     srcs.append(os.path.join(INCLUDE, "lmato_b200.h"))
     if not force and os.path.exists(LIB_PATH):
         if all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
