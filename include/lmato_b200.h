@@ -141,6 +141,21 @@ lmato_status_t lmato_solve_batch_host(lmato_handle* h, const double* params, int
                                       double* out_traj, double* out_tf, double* out_final_mass,
                                       int32_t* out_status, int32_t* out_iters, double* out_kkt);
 
+/* Parametric sensitivities of the optimal final time (no counterpart in the reference).
+ * Registers an extra output for the following solves on this handle: out_dtf [LMATO_NSENS][B] = d tf / d parameter
+ * (tf in the reference's scaled units, parameter in the units of the params block) for the parameters of
+ * lmato_sens_t, from the multipliers at the solution (envelope theorem; costs one pass over the converged
+ * iterate).  A DEVICE pointer for lmato_solve_batch, a HOST pointer for lmato_solve_batch_host; NULL (the
+ * default) switches the output off.  Entries of problems that did not converge are meaningless. */
+#define LMATO_NSENS 4
+typedef enum lmato_sens {
+  LMATO_S_FT = 0,                   /* thrust Ft (LO:61) */
+  LMATO_S_M0 = 1,                   /* wet mass M0 (LO:62) */
+  LMATO_S_M_DOT = 2,                /* propellant flow M_dot (LO:63) */
+  LMATO_S_ANGLE_DOUBLEDOT_MAX = 3   /* pitch acceleration limit (LO:66) */
+} lmato_sens_t;
+lmato_status_t lmato_set_sensitivity_output(lmato_handle* h, double* out_dtf);
+
 /* Introspection (for benchmarks and tests). */
 lmato_status_t lmato_workspace_bytes(lmato_handle* h, int64_t B, int64_t* bytes);
 lmato_status_t lmato_kernel_launches(lmato_handle* h, int64_t* n);  /* launches so far */

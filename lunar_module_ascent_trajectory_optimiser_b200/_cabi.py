@@ -19,6 +19,8 @@ INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 
 NPARAM = 14
 NVAR = 10
+NSENS = 4
+SENS_ROWS = ["Ft", "M0", "M_dot", "angle_doubledot_max"]      # lmato_sens_t
 PARAM_ROWS = ["G", "M", "R0", "Ft", "M0", "M_dot", "fuel_mass", "angle_doubledot_max",
               "r_periapsis", "r_apoapsis", "final_time", "mass_scalar", "angle_ub", "u_bound"]
 VAR_ROWS = ["y", "ydot", "ydoubledot", "x", "xdot", "xdoubledot", "angle", "angledot", "mass",
@@ -87,9 +89,11 @@ def lib() -> C.CDLL:
     L.lmato_measure_fp64_peak.argtypes = [vp, C.POINTER(C.c_double)]
     L.lmato_selftest_math.argtypes = [vp, C.POINTER(C.c_double)]
     L.lmato_coast_orbit.argtypes = [vp, vp, i64, C.c_double, C.c_double, i64, vp, vp]
+    L.lmato_set_sensitivity_output.argtypes = [vp, vp]
     for name in ("lmato_create", "lmato_destroy", "lmato_set_options", "lmato_solve_batch",
                  "lmato_solve_batch_host", "lmato_workspace_bytes", "lmato_kernel_launches",
-                 "lmato_last_kernel_ms", "lmato_measure_fp64_peak", "lmato_selftest_math", "lmato_coast_orbit"):
+                 "lmato_last_kernel_ms", "lmato_measure_fp64_peak", "lmato_selftest_math", "lmato_coast_orbit",
+                 "lmato_set_sensitivity_output"):
         getattr(L, name).restype = C.c_int
     _lib = L
     return L
@@ -98,7 +102,8 @@ def lib() -> C.CDLL:
 EXPORTED_SYMBOLS = ["lmato_default_options", "lmato_create", "lmato_destroy", "lmato_set_options",
                     "lmato_solve_batch", "lmato_solve_batch_host", "lmato_workspace_bytes",
                     "lmato_kernel_launches", "lmato_last_kernel_ms", "lmato_measure_fp64_peak",
-                    "lmato_selftest_math", "lmato_coast_orbit", "lmato_last_error", "lmato_version"]
+                    "lmato_selftest_math", "lmato_coast_orbit", "lmato_set_sensitivity_output", "lmato_last_error",
+                    "lmato_version"]
 
 
 def check(rc: int, what: str) -> None:

@@ -152,6 +152,9 @@ class AscentBatchSolution:
     iterations: torch.Tensor         # [B] int32
     kkt_error: torch.Tensor          # [B]
     time: torch.Tensor               # [nt] normalised mesh (m.time)
+    # optional: d tf / d parameter, name -> [B] (scaled tf per unit of the raw parameter), for
+    # Ft, M0, M_dot, angle_doubledot_max; only with ``sensitivities=True``
+    dtf_dparam: Optional[Dict[str, torch.Tensor]] = None
 
     @property
     def converged(self) -> torch.Tensor:
@@ -235,11 +238,14 @@ class AscentSolver:
         }
 
     def solve_rows(self, rows: torch.Tensor, trajectories: bool = True,
-                   out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+                   out: Optional[Dict[str, torch.Tensor]] = None,
+                   sensitivities: bool = False) -> Dict[str, torch.Tensor]:
         """``rows``: ``[NPARAM, B]`` float64.  CUDA tensor -> device entry point, results stay on
         the device (asynchronous on the current stream).  CPU tensor -> host entry point
         (H2D + solve + D2H, synchronous), results in pinned host memory.  ``out``: buffers from
-        :meth:`alloc_outputs` to write into (avoids re-allocating ~1 GB of trajectories per call)."""
+        :meth:`alloc_outputs` to write into (avoids re-allocating ~1 GB of trajectories per call).
+        ``sensitivities``: also return ``"dtf"`` ``[NSENS, B]`` = d tf / d (Ft, M0, M_dot,
+        angle_doubledot_max) from the multipliers at the solution (``lmato_set_sensitivity_output``)."""
         L = _cabi.lib()
         if rows.dtype != torch.float64 or rows.dim() != 2 or rows.shape[0] != _cabi.NPARAM:
             raise ValueError("rows must be float64 [NPARAM, B]")
@@ -255,9 +261,22 @@ class AscentSolver:
                 raise ValueError("out buffers do not match this call (batch size / placement / trajectories)")
             if not trajectories:
                 out = dict(out, traj=None)
+        if sensitivities:
+            kw = dict(device=self.device) if on_dev else dict(pin_memory=True)
+            out = dict(out, dtf=torch.empty((_cabi.NSENS, B), dtype=torch.float64, **kw))
         if B == 0:
             return out
         ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p()
+        if sensitivities:
+            _cabi.check(L.lmato_set_sensitivity_output(self._h, ptr(out["dtf"])), "lmato_set_sensitivity_output")
+        try:
+            self._solve_call(L, rows, B, out, on_dev, ptr)
+        finally:
+            if sensitivities:
+                L.lmato_set_sensitivity_output(self._h, C.c_void_p())
+        return out
+
+    def _solve_call(self, L, rows, B, out, on_dev, ptr) -> None:
         if on_dev:
             with torch.cuda.device(self.device):
                 stream = torch.cuda.current_stream(self.device).cuda_stream
@@ -270,7 +289,6 @@ class AscentSolver:
                                                  ptr(out["final_mass"]), ptr(out["status"]),
                                                  ptr(out["iterations"]), ptr(out["kkt"])),
                         "lmato_solve_batch_host")
-        return out
 
     def last_kernel_ms(self) -> float:
         ms = C.c_double()
@@ -341,9 +359,11 @@ def package_solution(raw: Dict[str, torch.Tensor], rows: torch.Tensor, time: tor
         else:
             control = states.pop("angledoubledot")
     T = rows[_cabi.PARAM_ROWS.index("final_time")]
+    dtf = raw.get("dtf")
     return AscentBatchSolution(tf=raw["tf"], tf_seconds=raw["tf"] * T.to(raw["tf"].device), states=states,
                                control=control, final_mass=raw["final_mass"], status=raw["status"],
-                               iterations=raw["iterations"], kkt_error=raw["kkt"], time=time)
+                               iterations=raw["iterations"], kkt_error=raw["kkt"], time=time,
+                               dtf_dparam=None if dtf is None else {n: dtf[i] for i, n in enumerate(_cabi.SENS_ROWS)})
 
 
 # ---------------------------------------------------------------------------------------
@@ -407,7 +427,8 @@ def sharded_solve(rows: torch.Tensor, solve_fn: Callable[[torch.Tensor], Dict[st
 
 
 def multi_device_solve(rows: torch.Tensor, solvers: List["AscentSolver"], trajectories: bool = True,
-                       out_device: Union[str, torch.device, None] = None) -> Dict[str, torch.Tensor]:
+                       out_device: Union[str, torch.device, None] = None,
+                       sensitivities: bool = False) -> Dict[str, torch.Tensor]:
     """One host process, several GPUs (no torchrun): problem i goes to GPU ``floor(i*G/B)`` (the same
     contiguous index partition as :func:`sharded_solve`).  The device entry point is asynchronous, so
     all launches are issued first and every GPU solves its shard concurrently; the shards are then
@@ -420,7 +441,7 @@ def multi_device_solve(rows: torch.Tensor, solvers: List["AscentSolver"], trajec
         lo, hi = shard_bounds(B, G, g)
         shard = rows[:, lo:hi].to(solver.device, non_blocking=True).contiguous()
         with torch.cuda.device(solver.device):
-            parts.append(solver.solve_rows(shard, trajectories) if hi > lo else None)
+            parts.append(solver.solve_rows(shard, trajectories, sensitivities=sensitivities) if hi > lo else None)
     dst = torch.device(out_device) if out_device is not None else solvers[0].device
     kw = dict(pin_memory=True) if dst.type == "cpu" else dict(device=dst)
     ref = next(p for p in parts if p is not None)
@@ -474,7 +495,7 @@ def _get_solver(mesh: Mesh, options: SolverOptions, device, model: str) -> Ascen
 def optimise_batch(params: AscentParams, mesh: Optional[Mesh] = None,
                    options: Optional[SolverOptions] = None, device=None, batch: Optional[int] = None,
                    trajectories: bool = True, group=None,
-                   devices: Optional[Sequence[int]] = None) -> AscentBatchSolution:
+                   devices: Optional[Sequence[int]] = None, sensitivities: bool = False) -> AscentBatchSolution:
     """Solve a batch of ascent problems (one per entry of the ``[B]`` parameter tensors).
 
     Results follow the placement of the inputs: CPU parameter tensors (or plain floats) give
@@ -487,6 +508,9 @@ def optimise_batch(params: AscentParams, mesh: Optional[Mesh] = None,
 
     ``devices``: GPU indices to shard over from THIS process (same partition, no process group, no
     collective: the shards are copied into one result block, see :func:`multi_device_solve`).
+
+    ``sensitivities``: also return ``dtf_dparam`` (d tf / d Ft, M0, M_dot, angle_doubledot_max per
+    problem).  Not available together with ``group``.
     """
     mesh = mesh or Mesh()
     options = options or SolverOptions()
@@ -503,11 +527,14 @@ def optimise_batch(params: AscentParams, mesh: Optional[Mesh] = None,
         rows = params.rows(batch, device=solvers[0].device if on_dev else "cpu")
         if not on_dev:
             rows = rows.pin_memory()
-        raw = multi_device_solve(rows, solvers, trajectories, out_device=None if on_dev else "cpu")
+        raw = multi_device_solve(rows, solvers, trajectories, out_device=None if on_dev else "cpu",
+                                 sensitivities=sensitivities)
         return package_solution(raw, rows, solvers[0].time, params.model)
     solver = _get_solver(mesh, options, device, params.model)
     rows = params.rows(batch, device=solver.device if on_dev else "cpu")
     if group is not None:
+        if sensitivities:
+            raise ValueError("sensitivities are not gathered across a process group; use `devices=` or one GPU")
         import torch.distributed as dist
         g = None if group is True else group
         dev_rows = rows.to(solver.device)
@@ -517,7 +544,7 @@ def optimise_batch(params: AscentParams, mesh: Optional[Mesh] = None,
         return package_solution(raw, rows, solver.time, params.model)
     if not on_dev:
         rows = rows.pin_memory()
-    raw = solver.solve_rows(rows, trajectories)
+    raw = solver.solve_rows(rows, trajectories, sensitivities=sensitivities)
     return package_solution(raw, rows, solver.time, params.model)
 
 

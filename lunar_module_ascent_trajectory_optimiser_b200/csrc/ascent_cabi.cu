@@ -61,6 +61,7 @@ struct KArgs {
   int* status;
   int* iters;
   double* kkt;
+  double* sens;          // [LMATO_NSENS][B] d tf / d parameter, or null
   double* ws;            // [N+1][slots/32][N_FIELDS][32]
   long slots;
   int N;
@@ -142,11 +143,18 @@ __device__ __noinline__ void write_results(const KArgs& a, const Params& P, cons
   a.status[b] = out.status;
   a.iters[b] = out.iters;
   if (a.kkt) a.kkt[b] = out.kkt;
-  if (!a.traj) return;
+  if (!a.traj && !a.sens) return;
   double* __restrict__ t = a.traj;
   const long B = a.B;
+  if (t) {
 #pragma unroll
-  for (int v = 0; v < LMATO_NVAR; ++v) t[((long)v * nt) * B + b] = 0.0;   // node 0 pinned
+    for (int v = 0; v < LMATO_NVAR; ++v) t[((long)v * nt) * B + b] = 0.0;   // node 0 pinned
+  }
+  // Parametric sensitivity of the optimum (envelope theorem): d objective* / d theta = d Lagrangian / d theta
+  // = sum_k lambda_k . d c_k / d theta at the solution, with c_k = s_k - s_{k-1} - h_k T tf F(s_k, u_k; theta).
+  // theta enters only the velocity rows (through the thrust acceleration Ft / (M0 - ms*mass), LO:127-136,
+  // and mass = mflow*T*tau*tf, LO:123) and the angledot row (angle_scalar, LO:121).
+  double s_ft = 0.0, s_m0 = 0.0, s_mf = 0.0, s_asc = 0.0;
   for (int k = 1; k <= a.N; ++k) {
     const double* sp = W.stage(k);
     double z[6];
@@ -155,7 +163,23 @@ __device__ __noinline__ void write_results(const KArgs& a, const Params& P, cons
     const double u = WS_AT(sp, out.cur * SW::NITER + SW::FU);
     const double m = P.mflow * P.T * a.tau[k] * out.tf;
     double ay, ax;
-    accel_value(P, z[0], z[2], z[4], m, ay, ax);
+    if (a.sens) {
+      Accel1 f;
+      accel_first(P, z[0], z[2], z[4], m, f);
+      ay = f.ay; ax = f.ax;
+      const double al = a.h[k] * P.T * out.tf;
+      const double l1 = WS_AT(sp, out.cur * SW::NITER + SW::FLAM + 1);     // multiplier of the ydot row
+      const double l3 = WS_AT(sp, out.cur * SW::NITER + SW::FLAM + 3);     // xdot row
+      const double l5 = WS_AT(sp, out.cur * SW::NITER + SW::FLAM + 5);     // angledot row
+      const double thrust = l1 * (f.AT * f.Ty * P.Sinv) + l3 * (f.AT * f.Tx * P.Sinv);
+      s_ft -= al * thrust / P.Ft;
+      s_m0 += al * thrust * (f.AT / P.Ft);                                  // d AT / d M0 = -AT / (M0 - ms*mass)
+      s_mf -= al * (l1 * f.ay_m + l3 * f.ax_m) * (P.T * a.tau[k] * out.tf);
+      s_asc -= al * u * l5;
+    } else {
+      accel_value(P, z[0], z[2], z[4], m, ay, ax);
+    }
+    if (!t) continue;
     t[((long)LMATO_V_Y * nt + k) * B + b] = z[0];
     t[((long)LMATO_V_YDOT * nt + k) * B + b] = z[1];
     t[((long)LMATO_V_YDOUBLEDOT * nt + k) * B + b] = ay;
@@ -166,6 +190,15 @@ __device__ __noinline__ void write_results(const KArgs& a, const Params& P, cons
     t[((long)LMATO_V_ANGLEDOT * nt + k) * B + b] = z[5];
     t[((long)LMATO_V_MASS * nt + k) * B + b] = m;
     t[((long)LMATO_V_ANGLEDOUBLEDOT * nt + k) * B + b] = u;
+  }
+  if (a.sens) {
+    // per unit of the RAW parameters of include/lmato_b200.h: M_dot = mflow * fuel_mass (LO:65),
+    // angle_doubledot_max = 3 * angle_scalar (LO:109); tf in the reference's scaled units (0..1)
+    const double inv = 1.0 / a.O.obj_scale;
+    a.sens[(long)LMATO_S_FT * B + b] = s_ft * inv;
+    a.sens[(long)LMATO_S_M0 * B + b] = s_m0 * inv;
+    a.sens[(long)LMATO_S_M_DOT * B + b] = s_mf * inv / P.fuel;
+    a.sens[(long)LMATO_S_ANGLE_DOUBLEDOT_MAX * B + b] = s_asc * inv / 3.0;
   }
 }
 
@@ -346,6 +379,7 @@ struct lmato_handle {
   double* d_ref = nullptr;        // reference column of the warm start: [REF_ROWS][nt]
   double* d_refparams = nullptr;  // [NPARAM] batch-mean parameters + scratch outputs of the reference solve
   lmato_options opt;
+  double* sens_out = nullptr;     // optional extra output of the next solves (lmato_set_sensitivity_output)
   int64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaStream_t last_stream = nullptr;
@@ -504,7 +538,7 @@ lmato_status_t lmato_solve_batch(lmato_handle* h, const double* params, int64_t 
   CUDA_TRY(cudaMemsetAsync(h->d_counter, 0, sizeof(int), st));
   KArgs a;
   a.params = params; a.B = B; a.traj = out_traj; a.tf = out_tf; a.fmass = out_final_mass;
-  a.status = out_status; a.iters = out_iters; a.kkt = out_kkt;
+  a.status = out_status; a.iters = out_iters; a.kkt = out_kkt; a.sens = h->sens_out;
   a.ws = h->d_ws; a.slots = slots; a.N = h->nt - 1; a.h = h->d_h; a.tau = h->d_tau;
   a.counter = h->d_counter;
   a.model = h->model;
@@ -531,7 +565,7 @@ lmato_status_t lmato_solve_batch(lmato_handle* h, const double* params, int64_t 
     KArgs r = a;
     double* scratch = h->d_refparams + LMATO_NPARAM;
     r.params = h->d_refparams; r.B = 1; r.traj = nullptr; r.tf = scratch; r.fmass = scratch + 1;
-    r.status = (int*)(scratch + 2); r.iters = (int*)(scratch + 3); r.kkt = scratch + 4;
+    r.status = (int*)(scratch + 2); r.iters = (int*)(scratch + 3); r.kkt = scratch + 4; r.sens = nullptr;
     r.ref = h->d_ref; r.ref_mode = 1;
     r.O.tol = 10.0 * h->opt.mu_ref; r.O.mu_min_factor = 0.1; r.O.n_polish = 0;
     r.O.w_dcost = 0.0;     // always the 7-state solve: cheaper, and at mu_ref >> w the move term is immaterial
@@ -596,8 +630,10 @@ lmato_status_t lmato_solve_batch_host(lmato_handle* h, const double* params, int
   double* traj_alias = pinned_alias(out_traj);
   const size_t traj_n = out_traj ? (size_t)LMATO_NVAR * h->nt * (size_t)B : 0;
   const size_t traj_stage = traj_alias ? 0 : traj_n;
-  // layout of d_out: traj (only when staged) | tf | fmass | kkt | status | iters
-  const size_t obytes = sizeof(double) * (traj_stage + 3 * (size_t)B) + sizeof(int32_t) * 2 * (size_t)B;
+  double* sens_host = h->sens_out;       // for this entry point the registered pointer is a HOST buffer
+  const size_t sens_n = sens_host ? (size_t)LMATO_NSENS * (size_t)B : 0;
+  // layout of d_out: traj (only when staged) | sens | tf | fmass | kkt | status | iters
+  const size_t obytes = sizeof(double) * (traj_stage + sens_n + 3 * (size_t)B) + sizeof(int32_t) * 2 * (size_t)B;
   if (obytes > h->out_bytes) {
     if (h->d_out) CUDA_TRY(cudaFree(h->d_out));
     h->d_out = nullptr; h->out_bytes = 0;
@@ -605,15 +641,19 @@ lmato_status_t lmato_solve_batch_host(lmato_handle* h, const double* params, int
     h->out_bytes = obytes;
   }
   double* d_traj = out_traj ? (traj_alias ? traj_alias : h->d_out) : nullptr;
-  double* d_tf = h->d_out + traj_stage;
+  double* d_sens = sens_host ? h->d_out + traj_stage : nullptr;
+  double* d_tf = h->d_out + traj_stage + sens_n;
   double* d_fm = d_tf + B;
   double* d_kkt = d_fm + B;
   int32_t* d_st = (int32_t*)(d_kkt + B);
   int32_t* d_it = d_st + B;
   cudaStream_t st = nullptr;
   CUDA_TRY(cudaMemcpyAsync(h->d_params, params, pbytes, cudaMemcpyHostToDevice, st));
+  h->sens_out = d_sens;
   lmato_status_t rc = lmato_solve_batch(h, h->d_params, B, d_traj, d_tf, d_fm, d_st, d_it, d_kkt, st);
+  h->sens_out = sens_host;
   if (rc != LMATO_OK) return rc;
+  if (sens_host) CUDA_TRY(cudaMemcpyAsync(sens_host, d_sens, sizeof(double) * sens_n, cudaMemcpyDeviceToHost, st));
   if (out_traj && !traj_alias)
     CUDA_TRY(cudaMemcpyAsync(out_traj, d_traj, sizeof(double) * traj_n, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaMemcpyAsync(out_tf, d_tf, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
@@ -622,6 +662,12 @@ lmato_status_t lmato_solve_batch_host(lmato_handle* h, const double* params, int
   CUDA_TRY(cudaMemcpyAsync(out_status, d_st, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaMemcpyAsync(out_iters, d_it, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
+  return LMATO_OK;
+}
+
+lmato_status_t lmato_set_sensitivity_output(lmato_handle* h, double* out_dtf) {
+  if (!h) { set_err("lmato_set_sensitivity_output: NULL handle"); return LMATO_ERR_INVALID; }
+  h->sens_out = out_dtf;
   return LMATO_OK;
 }
 

@@ -1184,7 +1184,7 @@ LM_HD void ipm_begin(const Options& O, IpmState& S) {
 
 // Sweeps policy of the 7-state formulation (dcost = 0); ascent_ipm_dc.cuh provides the 8-state one.
 struct Sweeps7 {
-  enum : int { NFIELDS = N_FIELDS, NITER = N_ITER, FZ = F_Z, FU = F_U, REFROWS = REF_ROWS };
+  enum : int { NFIELDS = N_FIELDS, NITER = N_ITER, FZ = F_Z, FU = F_U, FLAM = F_LAM, REFROWS = REF_ROWS };
   LM_HD static int n_eq(int N) { return 6 * N + 3; }
   LM_HD static int n_bd(int N) { return 4 * N + 4; }
   LM_HD static bool backward(const Params& P, const Mesh& M, const Options& O, const Ws& W, int src, const Scal& c0,

@@ -407,3 +407,34 @@ def test_pathological_inputs_fail_fast_and_alone(lm):
         keep = torch.arange(64) != 5
         assert int((st[keep] != 0).sum()) == 0, (name, val)
         assert torch.equal(raw["tf"].cpu()[keep], good["tf"].cpu()[keep]), (name, val)
+
+
+def test_sensitivities_match_finite_differences(lm):
+    """d tf / d parameter from the multipliers at the solution (envelope theorem) against
+    central finite differences of two further solves, for thrust, wet mass, propellant flow and the
+    pitch-acceleration limit, on dispersed problems and on the host and device entry points."""
+    import dataclasses
+    B = 8
+    p = lm.dispersed_params(B, seed=31)
+    sol = lm.optimise_batch(p, sensitivities=True)
+    assert int((sol.status != 0).sum()) == 0 and set(sol.dtf_dparam) == {"Ft", "M0", "M_dot", "angle_doubledot_max"}
+    for name, rel_step in [("Ft", 1e-4), ("M0", 1e-4), ("M_dot", 1e-4), ("angle_doubledot_max", 1e-3)]:
+        v = getattr(p, name)
+        v = v if isinstance(v, torch.Tensor) else torch.full((B,), float(v), dtype=torch.float64)
+        h = rel_step * v
+        up = lm.optimise_batch(dataclasses.replace(p, **{name: v + h}))
+        dn = lm.optimise_batch(dataclasses.replace(p, **{name: v - h}))
+        fd = (up.tf - dn.tf) / (2 * h)
+        an = sol.dtf_dparam[name]
+        err = float(((an - fd).abs() / fd.abs().max()).max())
+        assert err < 2e-4, (name, err, an[:3], fd[:3])
+    # physically: more thrust or more propellant flow shortens the burn, more mass lengthens it
+    assert bool((sol.dtf_dparam["Ft"] < 0).all()) and bool((sol.dtf_dparam["M0"] > 0).all())
+    # device entry point, and a device list, give the same numbers
+    pc = dataclasses.replace(p, **{f.name: getattr(p, f.name).cuda() for f in dataclasses.fields(p)
+                                   if isinstance(getattr(p, f.name), torch.Tensor)})
+    dev = lm.optimise_batch(pc, sensitivities=True, devices=[0, 0])
+    for name in sol.dtf_dparam:
+        assert torch.allclose(dev.dtf_dparam[name].cpu(), sol.dtf_dparam[name], rtol=1e-12, atol=0)
+    # without the flag nothing extra is computed or returned
+    assert lm.optimise_batch(p).dtf_dparam is None
