@@ -141,6 +141,16 @@ lmato_status_t lmato_solve_batch_host(lmato_handle* h, const double* params, int
                                       double* out_traj, double* out_tf, double* out_final_mass,
                                       int32_t* out_status, int32_t* out_iters, double* out_kkt);
 
+/* Start point for the following solves on this handle (accept a previous solution as the guess;
+ * the reference's counterpart is the `value=` argument of m.Var / m.MV / m.FV, LO:39, 83-96):
+ *   guess_traj [LMATO_NVAR][nt][B]  in the layout of out_traj (the rows of ydoubledot, xdoubledot and mass are
+ *                                   ignored: the device formulation eliminates them),  guess_tf [B].
+ * The primal values are taken as given and pushed into the interior of their bounds; node 0 stays pinned.
+ * DEVICE pointers for lmato_solve_batch, HOST pointers for lmato_solve_batch_host; NULL, NULL (the default)
+ * returns to the built-in start (roll-out / batch warm start).  The buffers must stay valid until the
+ * solve that uses them has finished. */
+lmato_status_t lmato_set_initial_guess(lmato_handle* h, const double* guess_traj, const double* guess_tf);
+
 /* Parametric sensitivities of the optimal final time (no counterpart in the reference).
  * Registers an extra output for the following solves on this handle: out_dtf [LMATO_NSENS][B] = d tf / d parameter
  * (tf in the reference's scaled units, parameter in the units of the params block) for the parameters of

@@ -90,10 +90,11 @@ def lib() -> C.CDLL:
     L.lmato_selftest_math.argtypes = [vp, C.POINTER(C.c_double)]
     L.lmato_coast_orbit.argtypes = [vp, vp, i64, C.c_double, C.c_double, i64, vp, vp]
     L.lmato_set_sensitivity_output.argtypes = [vp, vp]
+    L.lmato_set_initial_guess.argtypes = [vp, vp, vp]
     for name in ("lmato_create", "lmato_destroy", "lmato_set_options", "lmato_solve_batch",
                  "lmato_solve_batch_host", "lmato_workspace_bytes", "lmato_kernel_launches",
                  "lmato_last_kernel_ms", "lmato_measure_fp64_peak", "lmato_selftest_math", "lmato_coast_orbit",
-                 "lmato_set_sensitivity_output"):
+                 "lmato_set_sensitivity_output", "lmato_set_initial_guess"):
         getattr(L, name).restype = C.c_int
     _lib = L
     return L
@@ -102,7 +103,7 @@ def lib() -> C.CDLL:
 EXPORTED_SYMBOLS = ["lmato_default_options", "lmato_create", "lmato_destroy", "lmato_set_options",
                     "lmato_solve_batch", "lmato_solve_batch_host", "lmato_workspace_bytes",
                     "lmato_kernel_launches", "lmato_last_kernel_ms", "lmato_measure_fp64_peak",
-                    "lmato_selftest_math", "lmato_coast_orbit", "lmato_set_sensitivity_output", "lmato_last_error",
+                    "lmato_selftest_math", "lmato_coast_orbit", "lmato_set_sensitivity_output", "lmato_set_initial_guess", "lmato_last_error",
                     "lmato_version"]
 
 

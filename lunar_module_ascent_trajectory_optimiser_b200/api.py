@@ -239,13 +239,16 @@ class AscentSolver:
 
     def solve_rows(self, rows: torch.Tensor, trajectories: bool = True,
                    out: Optional[Dict[str, torch.Tensor]] = None,
-                   sensitivities: bool = False) -> Dict[str, torch.Tensor]:
+                   sensitivities: bool = False,
+                   guess: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
         """``rows``: ``[NPARAM, B]`` float64.  CUDA tensor -> device entry point, results stay on
         the device (asynchronous on the current stream).  CPU tensor -> host entry point
         (H2D + solve + D2H, synchronous), results in pinned host memory.  ``out``: buffers from
         :meth:`alloc_outputs` to write into (avoids re-allocating ~1 GB of trajectories per call).
         ``sensitivities``: also return ``"dtf"`` ``[NSENS, B]`` = d tf / d (Ft, M0, M_dot,
-        angle_doubledot_max) from the multipliers at the solution (``lmato_set_sensitivity_output``)."""
+        angle_doubledot_max) from the multipliers at the solution (``lmato_set_sensitivity_output``).
+        ``guess``: ``{"traj": [NVAR, nt, B], "tf": [B]}`` (e.g. a previous result of this method, same
+        placement as ``rows``) to start from instead of the built-in start (``lmato_set_initial_guess``)."""
         L = _cabi.lib()
         if rows.dtype != torch.float64 or rows.dim() != 2 or rows.shape[0] != _cabi.NPARAM:
             raise ValueError("rows must be float64 [NPARAM, B]")
@@ -267,13 +270,24 @@ class AscentSolver:
         if B == 0:
             return out
         ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p()
+        if guess is not None:
+            gt, gf = guess["traj"], guess["tf"]
+            if (gt is None or tuple(gt.shape) != (_cabi.NVAR, self.nt, B) or tuple(gf.shape) != (B,) or
+                    gt.dtype != torch.float64 or gf.dtype != torch.float64 or gt.is_cuda != on_dev or gf.is_cuda != on_dev):
+                raise ValueError("guess must be {'traj': float64 [NVAR, nt, B], 'tf': float64 [B]} placed like rows")
+            gt, gf = gt.contiguous(), gf.contiguous()
+            _cabi.check(L.lmato_set_initial_guess(self._h, ptr(gt), ptr(gf)), "lmato_set_initial_guess")
         if sensitivities:
             _cabi.check(L.lmato_set_sensitivity_output(self._h, ptr(out["dtf"])), "lmato_set_sensitivity_output")
         try:
             self._solve_call(L, rows, B, out, on_dev, ptr)
+            if guess is not None and on_dev:
+                torch.cuda.current_stream(self.device).synchronize()    # the guess buffers may be temporaries
         finally:
             if sensitivities:
                 L.lmato_set_sensitivity_output(self._h, C.c_void_p())
+            if guess is not None:
+                L.lmato_set_initial_guess(self._h, C.c_void_p(), C.c_void_p())
         return out
 
     def _solve_call(self, L, rows, B, out, on_dev, ptr) -> None:
@@ -495,7 +509,8 @@ def _get_solver(mesh: Mesh, options: SolverOptions, device, model: str) -> Ascen
 def optimise_batch(params: AscentParams, mesh: Optional[Mesh] = None,
                    options: Optional[SolverOptions] = None, device=None, batch: Optional[int] = None,
                    trajectories: bool = True, group=None,
-                   devices: Optional[Sequence[int]] = None, sensitivities: bool = False) -> AscentBatchSolution:
+                   devices: Optional[Sequence[int]] = None, sensitivities: bool = False,
+                   guess: Optional[AscentBatchSolution] = None) -> AscentBatchSolution:
     """Solve a batch of ascent problems (one per entry of the ``[B]`` parameter tensors).
 
     Results follow the placement of the inputs: CPU parameter tensors (or plain floats) give
@@ -511,6 +526,10 @@ def optimise_batch(params: AscentParams, mesh: Optional[Mesh] = None,
 
     ``sensitivities``: also return ``dtf_dparam`` (d tf / d Ft, M0, M_dot, angle_doubledot_max per
     problem).  Not available together with ``group``.
+
+    ``guess``: a previous :class:`AscentBatchSolution` of the same batch size and mesh (elliptical
+    model) to start from -- the counterpart of the ``value=`` arguments at LO:39, 83-96.  Single
+    device only.
     """
     mesh = mesh or Mesh()
     options = options or SolverOptions()
@@ -518,6 +537,8 @@ def optimise_batch(params: AscentParams, mesh: Optional[Mesh] = None,
         options = dataclasses.replace(options, dcost=float(params.dcost))
     on_dev = any(isinstance(getattr(params, f.name), torch.Tensor) and getattr(params, f.name).is_cuda
                  for f in dataclasses.fields(params))
+    if guess is not None and (devices is not None or group is not None):
+        raise ValueError("`guess` is supported on a single device only")
     if devices is not None:
         if group is not None:
             raise ValueError("pass either `group` (one process per GPU) or `devices` (one process), not both")
@@ -544,7 +565,17 @@ def optimise_batch(params: AscentParams, mesh: Optional[Mesh] = None,
         return package_solution(raw, rows, solver.time, params.model)
     if not on_dev:
         rows = rows.pin_memory()
-    raw = solver.solve_rows(rows, trajectories, sensitivities=sensitivities)
+    g = None
+    if guess is not None:
+        if params.model != "elliptical" or guess.control is None or "angledot" not in guess.states:
+            raise ValueError("`guess` must be a solution of the elliptical model with trajectories")
+        cols = [guess.control if n == "angledoubledot" else guess.states[n] for n in _cabi.VAR_ROWS]
+        gt = torch.stack([c.transpose(0, 1) for c in cols]).to(rows.device)        # [NVAR, nt, B]
+        gf = guess.tf.to(rows.device)
+        if not on_dev:
+            gt, gf = gt.pin_memory(), gf.pin_memory()
+        g = {"traj": gt, "tf": gf}
+    raw = solver.solve_rows(rows, trajectories, sensitivities=sensitivities, guess=g)
     return package_solution(raw, rows, solver.time, params.model)
 
 

@@ -62,6 +62,8 @@ struct KArgs {
   int* iters;
   double* kkt;
   double* sens;          // [LMATO_NSENS][B] d tf / d parameter, or null
+  const double* guess_traj;  // caller-supplied start point [NVAR][nt][B] and [B], or null
+  const double* guess_tf;
   double* ws;            // [N+1][slots/32][N_FIELDS][32]
   long slots;
   int N;
@@ -129,6 +131,11 @@ __device__ __forceinline__ Params derive_params(const double* __restrict__ p, lo
 // Params padded to an odd number of 8-byte words per thread so that the per-thread structs in
 // shared memory are bank-conflict free (stride 19 doubles = 38 words; 38 mod 32 = 6).
 struct alignas(8) ParamsSlot { Params p; double pad[(sizeof(Params) / 8) % 2 == 0 ? 1 : 2]; };
+
+static_assert(GuessSrc::V_Y == LMATO_V_Y && GuessSrc::V_YDOT == LMATO_V_YDOT && GuessSrc::V_X == LMATO_V_X &&
+              GuessSrc::V_XDOT == LMATO_V_XDOT && GuessSrc::V_ANGLE == LMATO_V_ANGLE &&
+              GuessSrc::V_ANGLEDOT == LMATO_V_ANGLEDOT && GuessSrc::V_U == LMATO_V_ANGLEDOUBLEDOT,
+              "the guess uses the output layout of include/lmato_b200.h");
 
 // Results of one finished problem (LO:178-202: tf, the per-node values of all ten variables, final
 // mass, status).  The iterate is read back from the thread's workspace column; ydoubledot,
@@ -268,7 +275,9 @@ __global__ void __launch_bounds__(kBlock, kBlocksPerSM) ascent_ipm_kernel(KArgs 
           // ref_mode 2: start from the batch reference.  ref_mode 1 (the reference solve itself):
           // start from the previous call's reference if the handle has one (consecutive batches of a
           // campaign have nearly the same mean, so it re-converges in one or two iterations).
-          if (a.ref_mode != 0 && SW::load_ref(P, M, O, W, a.ref, S.cur, &mu0)) {
+          if (a.guess_traj) {
+            SW::guess_from(P, M, O, W, GuessSrc{a.guess_traj, a.guess_tf, a.B, b}, S.cur);
+          } else if (a.ref_mode != 0 && SW::load_ref(P, M, O, W, a.ref, S.cur, &mu0)) {
             S.warm = true;
             S.ctl.mu = mu0;
             S.ctl.tau = dmax(O.tau_min, 1.0 - mu0);
@@ -380,6 +389,9 @@ struct lmato_handle {
   double* d_refparams = nullptr;  // [NPARAM] batch-mean parameters + scratch outputs of the reference solve
   lmato_options opt;
   double* sens_out = nullptr;     // optional extra output of the next solves (lmato_set_sensitivity_output)
+  const double* guess_traj = nullptr;   // optional start point of the next solves (lmato_set_initial_guess)
+  const double* guess_tf = nullptr;
+  double* d_guess = nullptr; size_t guess_bytes = 0;   // staging of a host guess
   int64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaStream_t last_stream = nullptr;
@@ -468,7 +480,7 @@ lmato_status_t lmato_destroy(lmato_handle* h) {
   if (!h) return LMATO_OK;
   cudaSetDevice(h->device);
   cudaFree(h->d_h); cudaFree(h->d_tau); cudaFree(h->d_ws); cudaFree(h->d_counter);
-  cudaFree(h->d_params); cudaFree(h->d_out); cudaFree(h->d_ref); cudaFree(h->d_refparams);
+  cudaFree(h->d_params); cudaFree(h->d_out); cudaFree(h->d_ref); cudaFree(h->d_refparams); cudaFree(h->d_guess);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   delete h;
@@ -539,6 +551,7 @@ lmato_status_t lmato_solve_batch(lmato_handle* h, const double* params, int64_t 
   KArgs a;
   a.params = params; a.B = B; a.traj = out_traj; a.tf = out_tf; a.fmass = out_final_mass;
   a.status = out_status; a.iters = out_iters; a.kkt = out_kkt; a.sens = h->sens_out;
+  a.guess_traj = h->guess_traj; a.guess_tf = h->guess_tf;
   a.ws = h->d_ws; a.slots = slots; a.N = h->nt - 1; a.h = h->d_h; a.tau = h->d_tau;
   a.counter = h->d_counter;
   a.model = h->model;
@@ -557,7 +570,8 @@ lmato_status_t lmato_solve_batch(lmato_handle* h, const double* params, int64_t 
   a.ref = nullptr; a.ref_mode = 0;
   const int grid = (int)(slots / kBlock);
   CUDA_TRY(cudaEventRecord(h->ev0, st));
-  if (h->opt.warm_start == 2 || (h->opt.warm_start == 1 && B >= kWarmStartMinBatch)) {
+  // (a caller-supplied guess replaces the batch warm start)
+  if (!h->guess_traj && (h->opt.warm_start == 2 || (h->opt.warm_start == 1 && B >= kWarmStartMinBatch))) {
     // reference problem = batch mean, solved down to mu_ref only (one thread; ~10 iterations from the
     // cold start on the first call, 1-2 from the previous call's reference afterwards)
     mean_params_kernel<<<LMATO_NPARAM, 256, 0, st>>>(params, B, h->d_refparams);
@@ -566,6 +580,7 @@ lmato_status_t lmato_solve_batch(lmato_handle* h, const double* params, int64_t 
     double* scratch = h->d_refparams + LMATO_NPARAM;
     r.params = h->d_refparams; r.B = 1; r.traj = nullptr; r.tf = scratch; r.fmass = scratch + 1;
     r.status = (int*)(scratch + 2); r.iters = (int*)(scratch + 3); r.kkt = scratch + 4; r.sens = nullptr;
+    r.guess_traj = nullptr; r.guess_tf = nullptr;
     r.ref = h->d_ref; r.ref_mode = 1;
     r.O.tol = 10.0 * h->opt.mu_ref; r.O.mu_min_factor = 0.1; r.O.n_polish = 0;
     r.O.w_dcost = 0.0;     // always the 7-state solve: cheaper, and at mu_ref >> w the move term is immaterial
@@ -649,9 +664,26 @@ lmato_status_t lmato_solve_batch_host(lmato_handle* h, const double* params, int
   int32_t* d_it = d_st + B;
   cudaStream_t st = nullptr;
   CUDA_TRY(cudaMemcpyAsync(h->d_params, params, pbytes, cudaMemcpyHostToDevice, st));
+  // a registered start point is a HOST buffer for this entry point: stage it
+  const double* guess_traj_host = h->guess_traj;
+  const double* guess_tf_host = h->guess_tf;
+  if (guess_traj_host) {
+    const size_t gn = (size_t)LMATO_NVAR * h->nt * (size_t)B;
+    const size_t gbytes = sizeof(double) * (gn + (size_t)B);
+    if (gbytes > h->guess_bytes) {
+      if (h->d_guess) CUDA_TRY(cudaFree(h->d_guess));
+      h->d_guess = nullptr; h->guess_bytes = 0;
+      CUDA_TRY(cudaMalloc(&h->d_guess, gbytes));
+      h->guess_bytes = gbytes;
+    }
+    CUDA_TRY(cudaMemcpyAsync(h->d_guess, guess_traj_host, sizeof(double) * gn, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(h->d_guess + gn, guess_tf_host, sizeof(double) * (size_t)B, cudaMemcpyHostToDevice, st));
+    h->guess_traj = h->d_guess; h->guess_tf = h->d_guess + gn;
+  }
   h->sens_out = d_sens;
   lmato_status_t rc = lmato_solve_batch(h, h->d_params, B, d_traj, d_tf, d_fm, d_st, d_it, d_kkt, st);
   h->sens_out = sens_host;
+  h->guess_traj = guess_traj_host; h->guess_tf = guess_tf_host;
   if (rc != LMATO_OK) return rc;
   if (sens_host) CUDA_TRY(cudaMemcpyAsync(sens_host, d_sens, sizeof(double) * sens_n, cudaMemcpyDeviceToHost, st));
   if (out_traj && !traj_alias)
@@ -662,6 +694,16 @@ lmato_status_t lmato_solve_batch_host(lmato_handle* h, const double* params, int
   CUDA_TRY(cudaMemcpyAsync(out_status, d_st, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaMemcpyAsync(out_iters, d_it, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
+  return LMATO_OK;
+}
+
+lmato_status_t lmato_set_initial_guess(lmato_handle* h, const double* guess_traj, const double* guess_tf) {
+  if (!h) { set_err("lmato_set_initial_guess: NULL handle"); return LMATO_ERR_INVALID; }
+  if ((guess_traj == nullptr) != (guess_tf == nullptr)) {
+    set_err("lmato_set_initial_guess: pass both the trajectories and tf, or NULL for both");
+    return LMATO_ERR_INVALID;
+  }
+  h->guess_traj = guess_traj; h->guess_tf = guess_tf;
   return LMATO_OK;
 }
 

@@ -392,6 +392,50 @@ LM_NOINLINE void init_guess(const Params& P, const Mesh& M, const Options& O, co
   s.sg1 = 1e-2; s.sg2 = 1e-2; s.zs1 = 1.0; s.zs2 = 1.0; s.nu3 = 0.0;
 }
 
+// Caller-supplied start point: trajectories in the OUTPUT layout of the solver,
+// [variable][node][problem] with the ten variables in the reference's order (LO:83-100), and tf.
+struct GuessSrc {
+  const double* traj;    // [10][nt][B]
+  const double* tf;      // [B]
+  long B, b;
+  enum : int { V_Y = 0, V_YDOT = 1, V_X = 3, V_XDOT = 4, V_ANGLE = 6, V_ANGLEDOT = 7, V_U = 9 };
+  LM_HD double at(int v, int k, int nt) const { return traj[((long)v * nt + k) * B + b]; }
+};
+
+// The primal values are taken as given and only pushed into the interior of their bounds (IPOPT's
+// bound_push); multipliers and slacks start as in the cold start, so iteration 0 is again the
+// least-squares multiplier estimate.  Node 0 is pinned whatever the guess says (LO:145-151).
+LM_NOINLINE void init_from_guess(const Params& P, const Mesh& M, const Options& O, const Ws& W, const GuessSrc& G,
+                                 Scal& s) {
+  const int N = M.N, nt = N + 1;
+  const double tf0 = dmin(dmax(G.tf[G.b], 1e-2 * P.tf_ub), 0.99 * P.tf_ub);
+  const double a_lo = 1e-2 * P.a_ub, a_hi = 0.99 * P.a_ub, u_hi = 0.99 * P.u_ub;
+  {
+    double* s0 = W.stage(0);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { WS_AT(s0, F_Z + i) = 0.0; WS_AT(s0, N_ITER + F_Z + i) = 0.0; WS_AT(s0, F_DS + i) = 0.0; }
+  }
+  for (int k = 1; k <= N; ++k) {
+    double* sp = W.stage(k);
+    const double u = dmin(dmax(G.at(GuessSrc::V_U, k, nt), -u_hi), u_hi);
+    WS_AT(sp, F_Z + 0) = G.at(GuessSrc::V_Y, k, nt);  WS_AT(sp, F_Z + 1) = G.at(GuessSrc::V_YDOT, k, nt);
+    WS_AT(sp, F_Z + 2) = G.at(GuessSrc::V_X, k, nt);  WS_AT(sp, F_Z + 3) = G.at(GuessSrc::V_XDOT, k, nt);
+    WS_AT(sp, F_Z + 4) = dmin(dmax(G.at(GuessSrc::V_ANGLE, k, nt), a_lo), a_hi);
+    WS_AT(sp, F_Z + 5) = G.at(GuessSrc::V_ANGLEDOT, k, nt);
+    WS_AT(sp, F_U) = u;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) WS_AT(sp, F_LAM + i) = 0.0;
+    WS_AT(sp, F_ZLA) = 1.0; WS_AT(sp, F_ZUA) = 1.0;
+    WS_AT(sp, F_ZLU) = P.coup5 != 0.0 ? 1.0 : O.mu_init / (u + P.u_ub);
+    WS_AT(sp, F_ZUU) = P.coup5 != 0.0 ? 1.0 : O.mu_init / (P.u_ub - u);
+#pragma unroll
+    for (int i = 0; i < N_STEP; ++i) WS_AT(sp, R_STEP + i) = 0.0;
+  }
+  s.tf = tf0;
+  s.zLt = 1.0; s.zUt = 1.0;
+  s.sg1 = 1e-2; s.sg2 = 1e-2; s.zs1 = 1.0; s.zs2 = 1.0; s.nu3 = 0.0;
+}
+
 // ---------------------------------------------------------------------------------------
 // shared building blocks of the Newton system (used by the factorisation AND by the adjoint
 // recursion, so that both see exactly the same Hessian)
@@ -1201,6 +1245,9 @@ struct Sweeps7 {
     eval_pass(P, M, O, W, src, dst, c0, ts, mu, dw, alpha, alpha_z, alpha_lam, mode, t, pimax);
   }
   LM_HD static void guess(const Params& P, const Mesh& M, const Options& O, const Ws& W, Scal& s) { init_guess(P, M, O, W, s); }
+  LM_HD static void guess_from(const Params& P, const Mesh& M, const Options& O, const Ws& W, const GuessSrc& G, Scal& s) {
+    init_from_guess(P, M, O, W, G, s);
+  }
   LM_HD static void store_ref(const Params& P, const Mesh& M, const Ws& W, int src, const Scal& c, double mu, bool ok,
                               double* ref) { ref_store(P, M, W, src, c, mu, ok, ref); }
   LM_HD static bool load_ref(const Params& P, const Mesh& M, const Options&, const Ws& W, const double* ref, Scal& s,

@@ -226,6 +226,46 @@ LM_NOINLINE bool init_from_ref7(const Params& P, const Mesh& M, const Options& O
   return true;
 }
 
+// Caller-supplied start point (see ascent_ipm.cuh: init_from_guess), 8-state layout: the move slack pair
+// is put on its central path for the guess's control moves.
+LM_NOINLINE void init_from_guess(const Params& P, const Mesh& M, const Options& O, const Ws& W, const GuessSrc& G,
+                                 Scal& s) {
+  const int N = M.N, nt = N + 1;
+  const double tf0 = dmin(dmax(G.tf[G.b], 1e-2 * P.tf_ub), 0.99 * P.tf_ub);
+  const double a_lo = 1e-2 * P.a_ub, a_hi = 0.99 * P.a_ub, u_hi = 0.99 * P.u_ub;
+  {
+    double* s0 = W.stage(0);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { WS_AT(s0, F_Z + i) = 0.0; WS_AT(s0, N_ITER + F_Z + i) = 0.0; WS_AT(s0, F_DS + i) = 0.0; }
+    WS_AT(s0, F_U) = 0.0; WS_AT(s0, N_ITER + F_U) = 0.0; WS_AT(s0, F_DU) = 0.0;
+  }
+  double u_prev = 0.0;
+  for (int k = 1; k <= N; ++k) {
+    double* sp = W.stage(k);
+    const double u = dmin(dmax(G.at(GuessSrc::V_U, k, nt), -u_hi), u_hi);
+    WS_AT(sp, F_Z + 0) = G.at(GuessSrc::V_Y, k, nt);  WS_AT(sp, F_Z + 1) = G.at(GuessSrc::V_YDOT, k, nt);
+    WS_AT(sp, F_Z + 2) = G.at(GuessSrc::V_X, k, nt);  WS_AT(sp, F_Z + 3) = G.at(GuessSrc::V_XDOT, k, nt);
+    WS_AT(sp, F_Z + 4) = dmin(dmax(G.at(GuessSrc::V_ANGLE, k, nt), a_lo), a_hi);
+    WS_AT(sp, F_Z + 5) = G.at(GuessSrc::V_ANGLEDOT, k, nt);
+    WS_AT(sp, F_U) = u;
+#pragma unroll
+    for (int i = 0; i < 7; ++i) WS_AT(sp, F_LAM + i) = 0.0;
+    WS_AT(sp, F_ZLA) = 1.0; WS_AT(sp, F_ZUA) = 1.0; WS_AT(sp, F_ZLU) = 1.0; WS_AT(sp, F_ZUU) = 1.0;
+    {
+      const double wd = O.w_dcost, v = u - u_prev;
+      const double tt = (O.mu_init + sqrt(O.mu_init * O.mu_init + wd * wd * v * v)) / wd;
+      WS_AT(sp, F_PP) = 0.5 * (tt + v); WS_AT(sp, F_PN) = 0.5 * (tt - v);
+      WS_AT(sp, F_ZPP) = wd; WS_AT(sp, F_ZPN) = wd;
+      u_prev = u;
+    }
+#pragma unroll
+    for (int i = 0; i < N_STEP; ++i) WS_AT(sp, R_STEP + i) = 0.0;
+  }
+  s.tf = tf0;
+  s.zLt = 1.0; s.zUt = 1.0;
+  s.sg1 = 1e-2; s.sg2 = 1e-2; s.zs1 = 1.0; s.zs2 = 1.0; s.nu3 = 0.0;
+}
+
 // ---------------------------------------------------------------------------------------
 // Staging tiles (see ascent_ipm.cuh: tl_*): which rows each sweep reads per stage and where they sit
 // in the tile.  "CUR" = rows F_LAM .. N_ITER-1 of the source iterate at stage k (multipliers and the
@@ -858,6 +898,9 @@ struct Sweeps8 {
     dc::eval_pass(P, M, O, W, src, dst, c0, ts, mu, dw, alpha, alpha_z, alpha_lam, mode, t, pimax);
   }
   LM_HD static void guess(const Params& P, const Mesh& M, const Options& O, const Ws& W, Scal& s) { dc::init_guess(P, M, O, W, s); }
+  LM_HD static void guess_from(const Params& P, const Mesh& M, const Options& O, const Ws& W, const GuessSrc& G, Scal& s) {
+    dc::init_from_guess(P, M, O, W, G, s);
+  }
   LM_HD static void store_ref(const Params& P, const Mesh& M, const Ws& W, int src, const Scal& c, double mu, bool ok,
                               double* ref) { dc::ref_store(P, M, W, src, c, mu, ok, ref); }
   LM_HD static bool load_ref(const Params& P, const Mesh& M, const Options& O, const Ws& W, const double* ref,

@@ -438,3 +438,38 @@ def test_sensitivities_match_finite_differences(lm):
         assert torch.allclose(dev.dtf_dparam[name].cpu(), sol.dtf_dparam[name], rtol=1e-12, atol=0)
     # without the flag nothing extra is computed or returned
     assert lm.optimise_batch(p).dtf_dparam is None
+
+
+def test_initial_guess(lm):
+    """`guess=` (lmato_set_initial_guess): a previous solution of nearby problems as the start point
+    gives the same optimum; a deliberately poor guess (all zeros, the reference's own initial values at
+    LO:39, 83-96) must still converge to it or fail with a status; device and host entry points agree."""
+    import dataclasses
+    B = 40
+    p = lm.dispersed_params(B, seed=41)
+    cold = lm.optimise_batch(p)
+    assert int((cold.status != 0).sum()) == 0
+    # neighbouring problems: +0.5 % thrust, started from the unperturbed solutions
+    p2 = dataclasses.replace(p, Ft=p.Ft * 1.005)
+    ref = lm.optimise_batch(p2)
+    warm = lm.optimise_batch(p2, guess=cold)
+    assert int((warm.status != 0).sum()) == 0
+    assert float(((warm.tf - ref.tf).abs() / ref.tf).max()) < 1e-9
+    for k in ref.states:
+        scale = ref.states[k].abs().amax(dim=1, keepdim=True) + 1e-300
+        assert float(((warm.states[k] - ref.states[k]).abs() / scale).max()) < STATE_RTOL, k
+    # device entry point with the same guess
+    pc = dataclasses.replace(p2, **{f.name: getattr(p2, f.name).cuda() for f in dataclasses.fields(p2)
+                                    if isinstance(getattr(p2, f.name), torch.Tensor)})
+    warm_dev = lm.optimise_batch(pc, guess=cold)
+    assert torch.equal(warm_dev.tf.cpu(), warm.tf) and torch.equal(warm_dev.iterations.cpu(), warm.iterations)
+    # the reference's all-zero initial values
+    zeros = dataclasses.replace(cold, tf=torch.zeros_like(cold.tf),
+                                states={k: torch.zeros_like(v) for k, v in cold.states.items()},
+                                control=torch.zeros_like(cold.control))
+    z = lm.optimise_batch(p, guess=zeros)
+    ok = z.status == 0
+    assert float(((z.tf[ok] - cold.tf[ok]).abs() / cold.tf[ok]).max() if bool(ok.any()) else 0.0) < 1e-8
+    print("all-zero start: converged", int(ok.sum()), "of", B, "iterations", z.iterations.tolist()[:8])
+    with pytest.raises(ValueError):
+        lm.optimise_batch(p, guess=cold, devices=[0])
