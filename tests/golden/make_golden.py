@@ -69,7 +69,7 @@ def main():
              final_mass=np.array(fms), traj=np.stack(trajs), names=np.array(VAR_ROWS))
 
 
-if __name__ == "__main__" and "--dense" not in sys.argv and "--dcost" not in sys.argv:
+if __name__ == "__main__" and not any(a in sys.argv for a in ("--dense", "--dcost", "--sens")):
     main()
 
 
@@ -112,3 +112,26 @@ def dcost():
 
 if __name__ == "__main__" and "--dcost" in sys.argv:
     dcost()
+
+
+def sensitivities():
+    """d tf / d parameter of the nominal problem (nt = 40, no DCOST) by central finite differences of
+    oracle solves: the independent check of the device's multiplier-based sensitivities."""
+    import dataclasses
+    base = AscentParams()
+    names = ["Ft", "M0", "M_dot", "angle_doubledot_max"]
+    steps = {"Ft": 1e-4, "M0": 1e-4, "M_dot": 1e-4, "angle_doubledot_max": 1e-3}
+    out = {}
+    for n in names:
+        v = getattr(base, n)
+        h = steps[n] * v
+        up = solve(dataclasses.replace(base, **{n: v + h}), nt=40)["tf"]
+        dn = solve(dataclasses.replace(base, **{n: v - h}), nt=40)["tf"]
+        out[n] = (up - dn) / (2 * h)
+        print("d tf / d", n, "=", out[n])
+    np.savez(os.path.join(HERE, "sens_nominal_nt40.npz"), names=np.array(names),
+             dtf=np.array([out[n] for n in names]), tf=solve(base, nt=40)["tf"])
+
+
+if __name__ == "__main__" and "--sens" in sys.argv:
+    sensitivities()

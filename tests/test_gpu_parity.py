@@ -440,6 +440,17 @@ def test_sensitivities_match_finite_differences(lm):
     assert lm.optimise_batch(p).dtf_dparam is None
 
 
+def test_sensitivities_match_oracle_finite_differences(lm, golden_dir):
+    """The same derivatives against the ORACLE: central differences of oracle solves of the nominal
+    problem at nt = 40 without DCOST (tests/golden/make_golden.py --sens)."""
+    g = np.load(os.path.join(golden_dir, "sens_nominal_nt40.npz"))
+    sol = lm.optimise_batch(lm.AscentParams(dcost=0.0), lm.Mesh(nt=40), batch=1, sensitivities=True)
+    assert int(sol.status[0]) == 0 and abs(float(sol.tf[0]) - float(g["tf"])) / float(g["tf"]) < 1e-8
+    for name, fd in zip(g["names"], g["dtf"]):
+        an = float(sol.dtf_dparam[str(name)][0])
+        assert abs(an - fd) / abs(fd) < 2e-4, (name, an, fd)
+
+
 def test_initial_guess(lm):
     """`guess=` (lmato_set_initial_guess): a previous solution of nearby problems as the start point
     gives the same optimum; a deliberately poor guess (all zeros, the reference's own initial values at

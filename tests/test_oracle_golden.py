@@ -124,3 +124,14 @@ def test_higher_order_collocation_converges_to_continuous_optimum():
     r = solve_ipm(nlp, nlp.initial_guess(0.9), IPMOptions(tol=1e-8))
     assert r.status == 0
     assert 434.5 < r.x[nlp.i_tf] * 470 < 435.8
+
+
+def test_sensitivity_fixture_is_consistent():
+    """tests/golden/sens_nominal_nt40.npz (oracle finite differences, `make_golden.py --sens`): signs and
+    magnitudes follow the physics (more thrust / flow / pitch authority shorten the burn, more mass
+    lengthens it) and the first-order mass relation d tf/d M0 ~ -(Ft/M0) d tf/d Ft holds to 10 %."""
+    import numpy as np
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "sens_nominal_nt40.npz"))
+    d = dict(zip([str(n) for n in g["names"]], g["dtf"]))
+    assert d["Ft"] < 0 and d["M_dot"] < 0 and d["angle_doubledot_max"] < 0 and d["M0"] > 0
+    assert abs(d["M0"] / (-(15346.0 / 4821.0) * d["Ft"]) - 1.0) < 0.4
