@@ -212,9 +212,9 @@ __device__ __noinline__ void write_results(const KArgs& a, const Params& P, cons
 // SW = Sweeps7 (dcost = 0) or Sweeps8 (with the reference's move-suppression term, LO:99)
 template <class SW>
 __global__ void __launch_bounds__(kBlock, kBlocksPerSM) ascent_ipm_kernel(KArgs a) {
-  // The sweeps are separate (noinline) functions taking `const Params&`: keeping the per-problem
-  // constants in shared memory instead of the thread's local-memory stack removes a dozen
-  // L1-missing local loads from the critical path of every stage.
+  // Per-problem constants are read in every stage of every sweep.  They live in shared memory: as
+  // registers they would be spilled (255 are already in use), and a spill is reloaded from local
+  // memory, which misses the thrashed L1 every stage.
   __shared__ ParamsSlot sP[kBlock];
   __shared__ Options sO;
   __shared__ Mesh sM;
@@ -230,8 +230,8 @@ __global__ void __launch_bounds__(kBlock, kBlocksPerSM) ascent_ipm_kernel(KArgs 
   extern __shared__ __align__(16) double sTiles[];
   const unsigned tile0 = (unsigned)__cvta_generic_to_shared(sTiles) +
                          (unsigned)(((threadIdx.x / 32) * 2 * TILE_ROWS * LANES + lane) * sizeof(double));
-  // the workspace view is read inside every stage of the noinline sweeps: shared memory, not the
-  // local-memory stack (24-byte stride: conflict-free per half warp)
+  // the workspace view is read inside every stage as well: shared memory for the same reason
+  // (24-byte stride: conflict-free per half warp)
   Ws* sW = reinterpret_cast<Ws*>(sTiles + (size_t)(kBlock / 32) * 2 * TILE_ROWS * LANES);   // after the tiles
   sW[threadIdx.x] = Ws{a.ws + ((slot / LANES) * SW::NFIELDS) * LANES + lane, nwarps * SW::NFIELDS * LANES, tile0};
   const Ws& W = sW[threadIdx.x];

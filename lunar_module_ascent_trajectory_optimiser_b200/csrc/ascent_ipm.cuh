@@ -6,14 +6,15 @@
 //   subsystem (2) residual/Jacobian/Hessian  ascent_model.cuh + the Q assembly in riccati_backward()
 //   subsystem (3) KKT factorisation ...... riccati_backward() / riccati_forward(): stage-wise
 //                 block-tridiagonal LDL^T (Riccati recursion) with inertia read from the pivots
-//   subsystem (4) barrier / fraction-to-boundary / filter line search: ipm_solve()
+//   subsystem (4) barrier / fraction-to-boundary / filter line search: ipm_iterate_t()
 //
 // IPM = Waechter & Biegler, Math. Prog. 106 (2006) (the algorithm behind SOLVER=3, LO:26).
 //
 // Data layout (HBM): ws[stage][warp][field][lane] -- for one warp and one stage the N_FIELDS
 // fields are N_FIELDS consecutive 256-byte rows, so every field access is the stage pointer plus
 // a compile-time offset (no address arithmetic per access) and every warp access is one fully
-// coalesced, 256-byte-aligned transaction.  All sweeps stream stage by stage through HBM.
+// coalesced, 256-byte-aligned transaction.  All sweeps stream stage by stage through HBM; the rows a
+// stage reads are staged one stage ahead in shared memory with cp.async (tl_* below).
 #pragma once
 #include "ascent_model.cuh"
 
@@ -26,9 +27,9 @@ struct Options {
   double tol;            // scaled KKT error (IPOPT `tol`)
   double mu_init;        // 0.1
   double obj_scale;      // objective = obj_scale * tf
-  double kappa_eps;      // 10
+  double kappa_eps;      // sub-problem tolerance kappa_eps * mu (IPOPT: 10; default here 30)
   double kappa_mu;       // 0.2
-  double theta_mu;       // 1.5
+  double theta_mu;       // barrier decrease mu <- min(kappa_mu mu, mu^theta_mu) (IPOPT: 1.5; here 2)
   double tau_min;        // 0.99
   double delta_c;        // dual regularisation of the terminal equality row
   double tf_guess;       // initial tf (scaled, 0..1)
@@ -689,7 +690,7 @@ LM_SWEEP void eval_pass(const Params& P, const Mesh& M, const Options& O, const 
     slam += t.zs1 + t.zs2 + fabs(t.nu3);
     gtf += O.obj_scale - t.zLt + t.zUt;
   }
-  // state of node k at the old point and its step (software-pipelined: node k-1 is loaded while
+  // state of node k at the old point and its step (carried in registers: node k-1 is read while
   // node k is processed, because the defect of node k needs the trial state of node k-1)
   double zo[6], ds[6];
   {
