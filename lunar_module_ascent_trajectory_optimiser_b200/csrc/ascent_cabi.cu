@@ -556,9 +556,10 @@ lmato_status_t lmato_solve_batch(lmato_handle* h, const double* params, int64_t 
   a.counter = h->d_counter;
   a.model = h->model;
   a.O.tol = h->opt.tol; a.O.mu_init = h->opt.mu_init; a.O.obj_scale = h->opt.obj_scale;
-  // theta_mu = 2 (IPOPT's default is 1.5, its admissible range (1, 2)): measured on the benchmark batch
-  // 1.3 / 1.5 / 1.7 / 2.0 / 2.5 / 3.0 -> 91 / 96 / 95 / 88 / 88 / 115 ms; kappa_mu and tau_min do not matter
-  a.O.kappa_eps = h->opt.kappa_eps; a.O.kappa_mu = 0.2; a.O.theta_mu = 2.0; a.O.tau_min = 0.99;
+  // barrier decrease exponent: IPOPT's 1.5 from the cold start, 2 from the batch warm start.  Measured on the
+  // benchmark batch (warm): 1.3 / 1.5 / 1.7 / 2.0 / 2.5 / 3.0 -> 91 / 96 / 95 / 88 / 88 / 115 ms; from the cold
+  // start 2.0 costs 0.7 iterations more than 1.5.  kappa_mu and tau_min do not matter.
+  a.O.kappa_eps = h->opt.kappa_eps; a.O.kappa_mu = 0.2; a.O.theta_mu = 1.5; a.O.theta_mu_warm = 2.0; a.O.tau_min = 0.99;
   a.O.delta_c = h->opt.delta_c; a.O.tf_guess = h->opt.tf_guess;
   a.O.max_iter = h->opt.max_iter; a.O.max_ls = h->opt.max_ls;
   a.O.mu_min_factor = h->opt.mu_min_factor;

@@ -29,7 +29,8 @@ struct Options {
   double obj_scale;      // objective = obj_scale * tf
   double kappa_eps;      // sub-problem tolerance kappa_eps * mu (IPOPT: 10; default here 30)
   double kappa_mu;       // 0.2
-  double theta_mu;       // barrier decrease mu <- min(kappa_mu mu, mu^theta_mu) (IPOPT: 1.5; here 2)
+  double theta_mu;       // barrier decrease mu <- min(kappa_mu mu, mu^theta_mu): IPOPT's 1.5 from the cold start,
+  double theta_mu_warm;  // 2 from the batch warm start (measured: cold 30.0 vs 30.7 iterations, warm 24.6 vs 23.2)
   double tau_min;        // 0.99
   double delta_c;        // dual regularisation of the terminal equality row
   double tf_guess;       // initial tf (scaled, 0..1)
@@ -1275,7 +1276,7 @@ LM_HD bool ipm_iterate_t(const Params& P, const Mesh& M, const Options& O, const
     //  than the final test does, and more than FP64 can deliver for the dual residual)
     bool mu_changed = false;
     while (kkt_error(cur, ctl.mu, n_eq, n_bd) <= dmax(O.kappa_eps * ctl.mu, O.tol) && ctl.mu > mu_min * (1.0 + 1e-12)) {
-      ctl.mu = dmax(mu_min, dmin(O.kappa_mu * ctl.mu, pow(ctl.mu, O.theta_mu)));
+      ctl.mu = dmax(mu_min, dmin(O.kappa_mu * ctl.mu, pow(ctl.mu, S.warm ? O.theta_mu_warm : O.theta_mu)));
       ctl.tau = dmax(O.tau_min, 1.0 - ctl.mu);
       ctl.nf = 0;
       mu_changed = true;

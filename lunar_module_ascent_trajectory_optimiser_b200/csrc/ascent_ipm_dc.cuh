@@ -443,7 +443,7 @@ LM_SWEEP void eval_pass(const Params& P, const Mesh& M, const Options& O, const 
         zlu = clip_mult(zlu, dLu, mu); zuu = clip_mult(zuu, dUu, mu);
       }
     }
-    sumlog += lm_log_pos((dLa * dUa) * (dLu * dUu));
+    const double slack4 = (dLa * dUa) * (dLu * dUu);      // its logarithm is taken together with the pair's below
     {
       const double c1 = dLa * zla, c2 = dUa * zua, c3 = dLu * zlu, c4 = dUu * zuu;
       cmin = dmin(cmin, dmin(dmin(c1, c2), dmin(c3, c4)));
@@ -471,7 +471,7 @@ LM_SWEEP void eval_pass(const Params& P, const Mesh& M, const Options& O, const 
       const double c1 = pp * zpp, c2 = pn * zpn;
       if (dmax(c1, c2) > 1e10 * mu || dmin(c1, c2) < 1e-10 * mu) { zpp = clip_mult(zpp, pp, mu); zpn = clip_mult(zpn, pn, mu); }
     }
-    sumlog += lm_log_pos(pp * pn);
+    sumlog += lm_log_pos(slack4 * (pp * pn));             // six slacks in (0, ~2): no underflow
     {
       const double c1 = pp * zpp, c2 = pn * zpn;
       cmin = dmin(cmin, dmin(c1, c2));

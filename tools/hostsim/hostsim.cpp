@@ -41,7 +41,7 @@ int main(int argc, char** argv) {
   for (int k = 0; k <= N; ++k) { tau[k] = (double)k / N; h[k] = k ? tau[k] - tau[k - 1] : 0.0; }
   Mesh M{N, h.data(), tau.data()};
   Options O;
-  O.tol = 1e-10; O.mu_init = 0.1; O.obj_scale = 10.0; O.kappa_eps = 30.0; O.kappa_mu = 0.2; O.theta_mu = 2.0;
+  O.tol = 1e-10; O.mu_init = 0.1; O.obj_scale = 10.0; O.kappa_eps = 30.0; O.kappa_mu = 0.2; O.theta_mu = 1.5; O.theta_mu_warm = 2.0;
   O.tau_min = 0.99; O.delta_c = 1e-8; O.tf_guess = 0.9; O.max_iter = 500; O.max_ls = 40; O.mu_min_factor = 1e-3; O.n_polish = 4;
   if (getenv("MMF")) O.mu_min_factor = atof(getenv("MMF"));
   if (getenv("NPOL")) O.n_polish = atoi(getenv("NPOL"));
@@ -109,7 +109,7 @@ extern "C" int hostsim_solve(const double* raw14, int nt, const double* time, do
   for (int k = 0; k <= N; ++k) { tau[k] = time ? time[k] : (double)k / N; h[k] = k ? tau[k] - tau[k - 1] : 0.0; }
   Mesh M{N, h.data(), tau.data()};
   Options O;
-  O.tol = tol; O.mu_init = 0.1; O.obj_scale = obj_scale; O.kappa_eps = 30.0; O.kappa_mu = 0.2; O.theta_mu = 2.0;
+  O.tol = tol; O.mu_init = 0.1; O.obj_scale = obj_scale; O.kappa_eps = 30.0; O.kappa_mu = 0.2; O.theta_mu = 1.5; O.theta_mu_warm = 2.0;
   O.tau_min = 0.99; O.delta_c = 1e-8; O.tf_guess = 0.9; O.max_iter = 500; O.max_ls = 40; O.mu_min_factor = mu_min_factor; O.n_polish = getenv("NPOL") ? atoi(getenv("NPOL")) : 4;
   O.w_dcost = getenv("WDC") ? atof(getenv("WDC")) : 0.0;
   Params P;
