@@ -35,10 +35,10 @@ enum : int {
 struct Move {
   double R, r;          // effective Hessian / gradient of the move
   double Sp, Sn, gp, gn, sinv, c;
+  double ip, in_;       // 1/p, 1/n (one division for both; reused by the callers)
   LM_HD void build(double pp, double pn, double zp, double zn, double v, double w, double mu, bool ls) {
-    double ip, in_, d0, d1;
-    recip4(pp, pn, 1.0, 1.0, ip, in_, d0, d1);
-    (void)d0; (void)d1;
+    const double ipn = lm_rcp(pp * pn);
+    ip = ipn * pn; in_ = ipn * pp;
     if (!ls) { Sp = zp * ip; Sn = zn * in_; gp = w - mu * ip; gn = w - mu * in_; c = v - pp + pn; }
     else     { Sp = 1.0; Sn = 1.0; gp = w - zp; gn = w - zn; c = 0.0; }
     sinv = lm_rcp(Sp + Sn);
@@ -458,9 +458,7 @@ LM_SWEEP void eval_pass(const Params& P, const Mesh& M, const Options& O, const 
       mv.build(pp, pn, zpp, zpn, u_old - zpo[6], wdc, mu, false);
       double dp, dn;
       mv.steps(du - dsp[6], dp, dn);
-      double ip, in_, d0, d1;
-      recip4(pp, pn, 1.0, 1.0, ip, in_, d0, d1);
-      (void)d0; (void)d1;
+      const double ip = mv.ip, in_ = mv.in_;
       zpp += alpha_z * ((mu - zpp * dp) * ip - zpp);
       zpn += alpha_z * ((mu - zpn * dn) * in_ - zpn);
       pp = fma(alpha, dp, pp);
@@ -816,9 +814,7 @@ LM_SWEEP void riccati_forward(const Params& P, const Mesh& M, const Options& O, 
       mv.build(pp, pn, zpp, zpn, u - zm[6], wdc, mu, ls);
       double dp, dn;
       mv.steps(dv, dp, dn);
-      double ip, in_, d0, d1;
-      recip4(pp, pn, 1.0, 1.0, ip, in_, d0, d1);
-      (void)d0; (void)d1;
+      const double ip = mv.ip, in_ = mv.in_;
       rp.push(-dp, pp); rp.push(-dn, pn);
       rz.push(-((mu - zpp * dp) * ip - zpp), zpp);
       rz.push(-((mu - zpn * dn) * in_ - zpn), zpn);
