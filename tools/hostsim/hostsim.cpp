@@ -150,3 +150,50 @@ extern "C" int hostsim_solve(const double* raw14, int nt, const double* time, do
   }
   return out.status;
 }
+
+// Finite-difference check of the hand-derived model derivatives (ascent_model.cuh) at one point:
+// returns the largest relative error of accel_first's eight first derivatives and of the
+// second-derivative contraction used by the Hessian (accel_second) against central differences.
+extern "C" double hostsim_check_derivatives(const double* raw14, double y, double x, double a, double m) {
+  Params P;
+  const double* r = raw14;
+  P.GM = r[0] * r[1]; P.R0 = r[2]; P.Ft = r[3]; P.M0 = r[4]; P.S = r[8]; P.ms = r[11]; P.mflow = r[5] / r[6];
+  P.asc = r[7] / 3.0; P.T = r[10]; P.a_ub = r[12]; P.u_ub = r[13];
+  P.fuel = r[6]; P.Sinv = 1.0 / P.S; P.coup5 = 1.0; P.mT = P.mflow * P.T;
+  Accel1 f;
+  accel_first(P, y, x, a, m, f);
+  const double v[4] = {y, x, a, m};
+  const double an1[2][4] = {{f.ay_y, f.ay_x, f.ay_a, f.ay_m}, {f.ax_y, f.ax_x, f.ax_a, f.ax_m}};
+  double worst = 0.0;
+  Accel1 fp[4], fm[4];
+  double hs[4];
+  for (int j = 0; j < 4; ++j) {
+    double p[4] = {v[0], v[1], v[2], v[3]}, q[4] = {v[0], v[1], v[2], v[3]};
+    hs[j] = 1e-6 * std::fmax(1.0, std::fabs(v[j]));
+    p[j] += hs[j]; q[j] -= hs[j];
+    accel_first(P, p[0], p[1], p[2], p[3], fp[j]);
+    accel_first(P, q[0], q[1], q[2], q[3], fm[j]);
+    const double fd[2] = {(fp[j].ay - fm[j].ay) / (2 * hs[j]), (fp[j].ax - fm[j].ax) / (2 * hs[j])};
+    for (int i = 0; i < 2; ++i)
+      worst = std::fmax(worst, std::fabs(fd[i] - an1[i][j]) / std::fmax(1e-12, std::fabs(an1[i][j])));
+  }
+  // second derivatives: H = wy * d2 ay + wx * d2 ax over (y, x, a, m), against differences of the first ones
+  const double wy = 0.7, wx = -1.3;
+  Accel2 h2;
+  accel_second(P, f, wy, wx, h2);
+  const double an2[4][4] = {{h2.yy, h2.yx, h2.ya, h2.ym}, {h2.yx, h2.xx, h2.xa, h2.xm},
+                            {h2.ya, h2.xa, h2.aa, h2.am}, {h2.ym, h2.xm, h2.am, h2.mm}};
+  for (int j = 0; j < 4; ++j) {
+    const double gp[4] = {wy * fp[j].ay_y + wx * fp[j].ax_y, wy * fp[j].ay_x + wx * fp[j].ax_x,
+                          wy * fp[j].ay_a + wx * fp[j].ax_a, wy * fp[j].ay_m + wx * fp[j].ax_m};
+    const double gm[4] = {wy * fm[j].ay_y + wx * fm[j].ax_y, wy * fm[j].ay_x + wx * fm[j].ax_x,
+                          wy * fm[j].ay_a + wx * fm[j].ax_a, wy * fm[j].ay_m + wx * fm[j].ax_m};
+    for (int i = 0; i < 4; ++i) {
+      const double fd = (gp[i] - gm[i]) / (2 * hs[j]);
+      double scale = 0.0;
+      for (int a2 = 0; a2 < 4; ++a2) scale = std::fmax(scale, std::fabs(an2[i][a2]));
+      worst = std::fmax(worst, std::fabs(fd - an2[i][j]) / std::fmax(1e-12, scale));
+    }
+  }
+  return worst;
+}
