@@ -75,7 +75,9 @@ enum {
   LMATO_ST_MAX_ITER = 1,         /* MAX_ITER reached (LO:28) */
   LMATO_ST_LINESEARCH_FAIL = 2,  /* filter line search could not make progress */
   LMATO_ST_INERTIA_FAIL = 3,     /* KKT inertia could not be corrected */
-  LMATO_ST_NUMERICAL = 4         /* NaN/Inf encountered */
+  LMATO_ST_NUMERICAL = 4,        /* NaN/Inf encountered */
+  LMATO_ST_STALLED = 5           /* no progress: ten consecutive steps shorter than 1e-6, or no improvement of the KKT
+                                    error for 200 iterations (what IPOPT's restoration phase reports as infeasible) */
 };
 
 typedef struct {

@@ -25,7 +25,8 @@ PARAM_ROWS = ["G", "M", "R0", "Ft", "M0", "M_dot", "fuel_mass", "angle_doubledot
               "r_periapsis", "r_apoapsis", "final_time", "mass_scalar", "angle_ub", "u_bound"]
 VAR_ROWS = ["y", "ydot", "ydoubledot", "x", "xdot", "xdoubledot", "angle", "angledot", "mass",
             "angledoubledot"]
-STATUS_NAMES = {0: "converged", 1: "max_iter", 2: "linesearch_fail", 3: "inertia_fail", 4: "numerical"}
+STATUS_NAMES = {0: "converged", 1: "max_iter", 2: "linesearch_fail", 3: "inertia_fail", 4: "numerical",
+                5: "stalled"}
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]

@@ -47,6 +47,7 @@ enum Status : int {
   ST_LINESEARCH_FAIL = 2,
   ST_INERTIA_FAIL = 3,
   ST_NUMERICAL = 4,
+  ST_STALLED = 5,
   ST_RUNNING = -1,
 };
 
@@ -196,6 +197,11 @@ struct Ctl {
   int nf;
   int iter;
   int status;
+  // stall guard (this solver has no restoration phase): consecutive accepted steps shorter than 1e-6, and the
+  // iteration at which the KKT error last improved
+  int tiny_steps;
+  int iter_best;
+  double err_best;
 };
 
 // ---------------------------------------------------------------------------------------
@@ -1219,6 +1225,7 @@ LM_HD void ipm_begin(const Options& O, IpmState& S) {
   S.ctl.mu = O.mu_init;
   S.ctl.tau = dmax(O.tau_min, 1.0 - S.ctl.mu);
   S.ctl.nf = 0; S.ctl.dw_last = 0.0; S.ctl.iter = 0; S.ctl.status = ST_RUNNING;
+  S.ctl.tiny_steps = 0; S.ctl.iter_best = 0; S.ctl.err_best = 1e300;
   S.ctl.theta_max = 1e300; S.ctl.theta_min = 0.0;
   S.err0 = 1e300;
   S.src = 0;
@@ -1297,6 +1304,12 @@ LM_HD bool ipm_iterate_t(const Params& P, const Mesh& M, const Options& O, const
       S.polishing = false;
     }
     if (ctl.iter >= O.max_iter) { ctl.status = S.polishing ? ST_CONVERGED : ST_MAX_ITER; return true; }
+    // Stall guard.  An infeasible problem (e.g. too little pitch authority to reach the orbit with tf <= 1)
+    // ends up pressed against a bound, where the fraction-to-boundary rule allows only steps of ~1e-9 that the
+    // filter keeps accepting; IPOPT would switch to its restoration phase and report infeasibility.  Here the
+    // problem is stopped -- in a batch one such lane would otherwise hold its whole SM for MAX_ITER iterations.
+    if (S.err0 < 0.9 * ctl.err_best) { ctl.err_best = S.err0; ctl.iter_best = ctl.iter; }
+    if (!S.polishing && (ctl.tiny_steps >= 10 || ctl.iter - ctl.iter_best >= 200)) { ctl.status = ST_STALLED; return true; }
   }
   const bool polishing = S.polishing;
   // factorisation with inertia correction (IPOPT Algorithm IC)
@@ -1385,6 +1398,7 @@ LM_HD bool ipm_iterate_t(const Params& P, const Mesh& M, const Options& O, const
   if (!ftype) filter_add(ctl, (1.0 - g_th) * theta, phi - g_ph * theta);
   cur = trial; S.src = 1 - S.src;
   ++ctl.iter;
+  ctl.tiny_steps = (alpha < 1e-6) ? ctl.tiny_steps + 1 : 0;
 #if defined(LMATO_TRACE) && !defined(__CUDA_ARCH__)
   printf("%3d tf %.8f th %.3e err %.3e mu %.1e a %.3e az %.3e dw %.1e dphi %.2e dx %.2e nf %d %s\n", ctl.iter, cur.tf,
          cur.theta, S.err0, ctl.mu, alpha, si.a_z, dw, dphi, si.dxmax, ctl.nf, ftype ? "f" : "h");

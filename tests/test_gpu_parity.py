@@ -407,6 +407,20 @@ def test_pathological_inputs_fail_fast_and_alone(lm):
         keep = torch.arange(64) != 5
         assert int((st[keep] != 0).sum()) == 0, (name, val)
         assert torch.equal(raw["tf"].cpu()[keep], good["tf"].cpu()[keep]), (name, val)
+    # An infeasible problem that neither diverges nor trips the line search (too little pitch authority:
+    # it ends pressed against tf <= 1 taking steps of ~1e-9) must be stopped by the stall guard, not run
+    # for MAX_ITER = 20000 iterations (it held its SM for 150 s before the guard existed).
+    rows = base.clone()
+    for name, val in [("Ft", 15147.66154), ("M0", 4657.257368), ("M_dot", 4.95030077),
+                      ("angle_doubledot_max", 6.212104013e-05), ("r_periapsis", 15055.13058),
+                      ("r_apoapsis", 71289.66498)]:
+        rows[_cabi.PARAM_ROWS.index(name), 5] = val
+    t0 = time.time()
+    raw = solver.solve_rows(rows.cuda())
+    torch.cuda.synchronize()
+    assert time.time() - t0 < 5.0
+    assert int(raw["status"][5]) == 5 and int(raw["iterations"][5]) < 400      # LMATO_ST_STALLED
+    assert int((raw["status"].cpu()[torch.arange(64) != 5] != 0).sum()) == 0
 
 
 def test_sensitivities_match_finite_differences(lm):
