@@ -77,7 +77,7 @@ enum {
   LMATO_ST_INERTIA_FAIL = 3,     /* KKT inertia could not be corrected */
   LMATO_ST_NUMERICAL = 4,        /* NaN/Inf encountered */
   LMATO_ST_STALLED = 5           /* no progress: ten consecutive steps shorter than 1e-6, or no improvement of the KKT
-                                    error for 200 iterations (what IPOPT's restoration phase reports as infeasible) */
+                                    error for 100 iterations (what IPOPT's restoration phase reports as infeasible) */
 };
 
 typedef struct {

@@ -1309,7 +1309,7 @@ LM_HD bool ipm_iterate_t(const Params& P, const Mesh& M, const Options& O, const
     // filter keeps accepting; IPOPT would switch to its restoration phase and report infeasibility.  Here the
     // problem is stopped -- in a batch one such lane would otherwise hold its whole SM for MAX_ITER iterations.
     if (S.err0 < 0.9 * ctl.err_best) { ctl.err_best = S.err0; ctl.iter_best = ctl.iter; }
-    if (!S.polishing && (ctl.tiny_steps >= 10 || ctl.iter - ctl.iter_best >= 200)) { ctl.status = ST_STALLED; return true; }
+    if (!S.polishing && (ctl.tiny_steps >= 10 || ctl.iter - ctl.iter_best >= 100)) { ctl.status = ST_STALLED; return true; }
   }
   const bool polishing = S.polishing;
   // factorisation with inertia correction (IPOPT Algorithm IC)
