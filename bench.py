@@ -37,7 +37,7 @@ METRIC = "converged ascent-NLP solves/sec at batch 64K"
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE ascent_ipm_kernel launch, from the `ncu --set full`
 # capture summarised in profiles/r01_ncu_ascent_ipm_kernel_metrics.csv; keyed by (dcost on, batch, nt) and
 # only reported when the run matches that workload, otherwise null.
-NCU_TRAFFIC_BYTES = {(True, 65536, 200): 217.426e9 + 123.500e9}
+NCU_TRAFFIC_BYTES = {(True, 65536, 200): 217.488e9 + 123.538e9}
 
 
 def load_peaks():
