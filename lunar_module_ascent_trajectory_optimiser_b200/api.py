@@ -450,30 +450,49 @@ def multi_device_solve(rows: torch.Tensor, solvers: List["AscentSolver"], trajec
     over NVLink) or into pinned host memory (``"cpu"``)."""
     G = len(solvers)
     B = int(rows.shape[1])
-    parts = []
+    # distribute ALL shards first: a peer copy is ordered behind whatever its source device has queued, so
+    # copying shard g+1 after launching solve g would make every other GPU wait for the first one's kernel
+    shards = []
     for g, solver in enumerate(solvers):
         lo, hi = shard_bounds(B, G, g)
-        shard = rows[:, lo:hi].to(solver.device, non_blocking=True).contiguous()
+        shards.append(rows[:, lo:hi].to(solver.device, non_blocking=True).contiguous())
+    if rows.is_cuda:
+        torch.cuda.synchronize(rows.device)
+    parts = []
+    for g, solver in enumerate(solvers):
         with torch.cuda.device(solver.device):
-            parts.append(solver.solve_rows(shard, trajectories, sensitivities=sensitivities) if hi > lo else None)
-    dst = torch.device(out_device) if out_device is not None else solvers[0].device
-    kw = dict(pin_memory=True) if dst.type == "cpu" else dict(device=dst)
+            parts.append(solver.solve_rows(shards[g], trajectories, sensitivities=sensitivities)
+                         if shards[g].shape[1] > 0 else None)
+    # Assemble on the first solver's device: each shard travels as ONE contiguous peer copy (NVLink) and is
+    # placed into its strided slot of the [.., B] block by a local copy kernel; a host result is then a single
+    # contiguous transfer into pinned memory.
+    hub = solvers[0].device
     ref = next(p for p in parts if p is not None)
     keys = [k for k, v in ref.items() if v is not None]
     out: Dict[str, Optional[torch.Tensor]] = {k: None for k in ref}
-    for k in keys:
-        shape = list(ref[k].shape)
-        shape[-1] = B
-        out[k] = torch.empty(shape, dtype=ref[k].dtype, **kw)
-    for g, part in enumerate(parts):
-        if part is None:
-            continue
-        lo, hi = shard_bounds(B, G, g)
-        with torch.cuda.device(solvers[g].device):
-            for k in keys:
-                out[k][..., lo:hi].copy_(part[k], non_blocking=True)
     for solver in solvers:
         torch.cuda.synchronize(solver.device)
+    with torch.cuda.device(hub):
+        for k in keys:
+            shape = list(ref[k].shape)
+            shape[-1] = B
+            out[k] = torch.empty(shape, dtype=ref[k].dtype, device=hub)
+        for g, part in enumerate(parts):
+            if part is None:
+                continue
+            lo, hi = shard_bounds(B, G, g)
+            for k in keys:
+                out[k][..., lo:hi] = part[k].to(hub, non_blocking=True)
+        torch.cuda.synchronize(hub)
+        dst = torch.device(out_device) if out_device is not None else hub
+        if dst.type == "cpu":
+            for k in keys:
+                host = torch.empty(out[k].shape, dtype=out[k].dtype, pin_memory=True)
+                host.copy_(out[k], non_blocking=True)
+                out[k] = host
+            torch.cuda.synchronize(hub)
+        elif dst != hub:
+            out = {k: (v.to(dst) if v is not None else None) for k, v in out.items()}
     return out
 
 
@@ -544,6 +563,10 @@ def optimise_batch(params: AscentParams, mesh: Optional[Mesh] = None,
             raise ValueError("pass either `group` (one process per GPU) or `devices` (one process), not both")
         if len(devices) == 0:
             raise ValueError("`devices` is empty")
+        nB = batch if batch is not None else (params.batch_size() or 1)
+        if options.warm_start == 1 and nB >= 1024:
+            # the shards belong to one batch: they keep the batch warm start even if a shard alone is small
+            options = dataclasses.replace(options, warm_start=2)
         solvers = [_get_solver(mesh, options, d, params.model) for d in devices]
         rows = params.rows(batch, device=solvers[0].device if on_dev else "cpu")
         if not on_dev:
