@@ -40,6 +40,26 @@ METRIC = "converged ascent-NLP solves/sec at batch 64K"
 NCU_TRAFFIC_BYTES = {(True, 65536, 200): 217.488e9 + 123.538e9}
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this rank to the CPUs NVML reports as local to its GPU, so that the pinned host buffers of the
+    end-to-end leg (first touch) live on the NUMA node the GPU's PCIe root hangs on.  Multi-rank runs only:
+    eight ranks each stream 1 GB of results per step into host memory."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -220,6 +240,7 @@ def main():
     import lunar_module_ascent_trajectory_optimiser_b200 as lm
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -340,7 +361,7 @@ def main():
                                f"6-parameter dispersions; {NBATCH} different draws (seed 11+rank+1000j) cycled over the steps",
                    "batch_per_gpu": B, "global_batch": B * world, "tol": opts.tol, "obj_scale": opts.obj_scale,
                    "dcost": 1e-5 if opts.dcost is None else opts.dcost, "warm_start": bool(opts.warm_start),
-                   "trajectories": traj, "parallelism": f"index-sharded x{world}, one allgather of results" if world > 1 else "single GPU",
+                   "trajectories": traj, "parallelism": (f"index-sharded x{world}, one allgather of results" + (f"; ranks bound to their GPU's NUMA node ({numa} CPUs)" if numa else "")) if world > 1 else "single GPU",
                    "l2": f"no flush needed: the kernel streams a {solver.workspace_bytes(B) / 2**30:.1f} GiB workspace (>> 126 MB L2) every sweep"},
         "converged_fraction": conv_all / (B * world * args.steps),
         "mean_iterations": iters_all / (B * world * args.steps),
