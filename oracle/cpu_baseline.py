@@ -11,7 +11,7 @@ from __future__ import annotations
 import multiprocessing as mp
 import os
 import time
-from typing import List, Sequence, Tuple
+from typing import Tuple
 
 import numpy as np
 

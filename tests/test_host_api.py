@@ -2,7 +2,6 @@
 multi-rank gather (world_size 2 over gloo with a stub in place of the CUDA solve)."""
 import math
 import os
-import sys
 
 import pytest
 import torch

@@ -2,7 +2,6 @@
 import sys, time, torch
 sys.path.insert(0, '.')
 import lunar_module_ascent_trajectory_optimiser_b200 as lm
-from lunar_module_ascent_trajectory_optimiser_b200 import _cabi
 B = 65536
 solver = lm.AscentSolver(lm.Mesh(), lm.SolverOptions(), device=0)
 for seed in (1, 2, 3):

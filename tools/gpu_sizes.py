@@ -1,4 +1,4 @@
-import sys, time, torch
+import sys, torch
 sys.path.insert(0, '.')
 import lunar_module_ascent_trajectory_optimiser_b200 as lm
 solver = lm.AscentSolver(lm.Mesh(), lm.SolverOptions(), device=0)
