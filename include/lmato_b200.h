@@ -11,7 +11,9 @@
  * the text of the last failure on the calling thread.
  *
  * Threading: a handle is bound to one CUDA device and must be used from one host thread
- * at a time.  Distinct handles are independent.  Ownership: the caller owns every
+ * at a time.  Solves on one handle share its workspace: they are serialised on the device even when
+ * issued on different streams (a solve on a new stream waits for the handle's previous solve).
+ * Distinct handles are independent.  Ownership: the caller owns every
  * input/output buffer; the library owns only the workspace inside the handle.
  */
 #ifndef LMATO_B200_H
@@ -103,7 +105,23 @@ typedef struct {
                         reduced once E_mu <= kappa_eps*mu; default 30 (2.4 fewer iterations, same answers) */
   int32_t objective_nodes; /* APMonitor sums the objective over the horizon: minimise objective_nodes*tf +
                         dcost*sum|dMV|; 0 (default) = nt-1.  Only the ratio dcost/objective_nodes matters. */
+  int32_t kernel;    /* lmato_kernel_t: which kernel solves a batch; default LMATO_KERNEL_AUTO (by batch size) */
+  int32_t coop_lanes; /* COOP kernel: lanes per problem in the stage-parallel phases, 8 or 32; 0 (default) = by batch size */
+  int32_t reserved_;
+  double otol;       /* LO:31 m.options.OTOL and */
+  double rtol;       /* LO:32 m.options.RTOL (the reference sets both to 1e-3, the defaults here).  How APMonitor
+                        maps them onto IPOPT's `tol` cannot be verified without GEKKO; the rule here is the
+                        conservative one: a solve runs to min(tol, otol, rtol), so the reference's 1e-3 never
+                        loosens the default 1e-10 and a tighter OTOL/RTOL tightens it.  0 = ignore. */
 } lmato_options;
+
+/* Kernel mapping (both solve the same NLP with the same IPM and agree to rounding):
+ *   THREAD  one problem per thread, one coalesced workspace row per warp and stage: least HBM traffic per
+ *           problem, needs ~37 888 problems in flight to fill a B200;
+ *   COOP    eight lanes of a warp per problem, stage-parallel model evaluation, cost-to-go distributed by rows:
+ *           short critical path per problem, fills the GPU with ~4 700 problems;
+ *   AUTO    COOP up to 24 576 problems per call, THREAD above. */
+typedef enum { LMATO_KERNEL_AUTO = 0, LMATO_KERNEL_THREAD = 1, LMATO_KERNEL_COOP = 2 } lmato_kernel_t;
 
 /* Fill `o` with the defaults above. */
 void lmato_default_options(lmato_options* o);

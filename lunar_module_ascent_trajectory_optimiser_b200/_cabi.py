@@ -13,7 +13,7 @@ import sys
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("LMATO_LIB_OVERRIDE") or os.path.join(_HERE, "liblmato_b200.so")   # override: developer A/B builds only
+LIB_PATH = os.path.join(_HERE, "liblmato_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 
@@ -28,6 +28,8 @@ VAR_ROWS = ["y", "ydot", "ydoubledot", "x", "xdot", "xdoubledot", "angle", "angl
 STATUS_NAMES = {0: "converged", 1: "max_iter", 2: "linesearch_fail", 3: "inertia_fail", 4: "numerical",
                 5: "stalled"}
 
+KERNEL_IDS = {"auto": 0, "thread": 1, "coop": 2}     # lmato_kernel_t
+
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 
@@ -37,7 +39,8 @@ class LmatoOptions(C.Structure):
                 ("tf_guess", C.c_double), ("delta_c", C.c_double), ("mu_min_factor", C.c_double),
                 ("max_iter", C.c_int32), ("max_ls", C.c_int32), ("n_polish", C.c_int32),
                 ("warm_start", C.c_int32), ("mu_ref", C.c_double), ("dcost", C.c_double),
-                ("kappa_eps", C.c_double), ("objective_nodes", C.c_int32)]
+                ("kappa_eps", C.c_double), ("objective_nodes", C.c_int32), ("kernel", C.c_int32),
+                ("coop_lanes", C.c_int32), ("reserved_", C.c_int32), ("otol", C.c_double), ("rtol", C.c_double)]
 
 
 class LmatoError(RuntimeError):
@@ -46,7 +49,8 @@ class LmatoError(RuntimeError):
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/ascent_cabi.cu for sm_100a into the in-tree shared library."""
-    srcs = [os.path.join(CSRC, f) for f in ("ascent_cabi.cu", "ascent_ipm.cuh", "ascent_ipm_dc.cuh", "ascent_model.cuh")]
+    srcs = [os.path.join(CSRC, f) for f in ("ascent_cabi.cu", "ascent_ipm.cuh", "ascent_ipm_dc.cuh", "ascent_coop.cuh",
+                                            "ascent_model.cuh")]
     srcs.append(os.path.join(INCLUDE, "lmato_b200.h"))
     if not force and os.path.exists(LIB_PATH):
         if all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):

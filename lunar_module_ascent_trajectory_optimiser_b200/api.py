@@ -124,8 +124,8 @@ class Mesh:
 class SolverOptions:
     """LO:26-33 plus solver-native knobs."""
     max_iter: int = 20000          # LO:28
-    otol: float = 1e-3             # LO:31 (recorded; the device IPM converges to `tol`)
-    rtol: float = 1e-3             # LO:32
+    otol: float = 1e-3             # LO:31  } the solve runs to min(tol, otol, rtol): the reference's 1e-3 never loosens
+    rtol: float = 1e-3             # LO:32  } the default tol, a tighter OTOL/RTOL tightens it (lmato_b200.h)
     tol: float = 1e-10             # scaled KKT error at which a problem counts as converged
     mu_init: float = 0.1
     obj_scale: float = 10.0
@@ -139,6 +139,8 @@ class SolverOptions:
     dcost: Optional[float] = None  # LO:99; None = take AscentParams.dcost (1e-5 in the reference)
     objective_nodes: int = 0       # APMonitor sums the objective over the horizon; 0 = nt-1
     kappa_eps: float = 30.0        # barrier sub-problem tolerance factor (IPOPT's default is 10)
+    kernel: str = "auto"           # "auto" | "thread" (one problem per thread) | "coop" (eight lanes per problem)
+    coop_lanes: int = 0            # coop kernel: lanes per problem in the stage-parallel phases (8 | 32; 0 = by batch size)
 
 
 @dataclasses.dataclass
@@ -209,7 +211,8 @@ class AscentSolver:
                                 max_ls=int(o.max_ls), n_polish=int(o.n_polish),
                                 warm_start=int(o.warm_start), mu_ref=o.mu_ref,
                                 dcost=float(1e-5 if o.dcost is None else o.dcost),
-                                kappa_eps=float(o.kappa_eps), objective_nodes=int(o.objective_nodes))
+                                kappa_eps=float(o.kappa_eps), objective_nodes=int(o.objective_nodes),
+                                kernel=_cabi.KERNEL_IDS[o.kernel], coop_lanes=int(o.coop_lanes), otol=float(o.otol), rtol=float(o.rtol))
         _cabi.check(_cabi.lib().lmato_set_options(self._h, C.byref(co)), "lmato_set_options")
         self.options = o
 

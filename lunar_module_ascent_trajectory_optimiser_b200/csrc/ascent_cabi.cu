@@ -1,14 +1,18 @@
 // C ABI + kernels of the batched ascent solver (sm_100a).  See include/lmato_b200.h.
 //
-// Kernel mapping: ONE PROBLEM PER THREAD, persistent warps.  A warp claims 32 consecutive
-// problems from a device-side counter, solves them to convergence without returning to the
-// host (barrier updates, fraction-to-boundary, filter line search and convergence masks all
-// live in registers/local memory of the owning thread), writes the results and claims the
-// next 32.  The stage data of a problem is far too large for registers (90 doubles x nt), so
-// it streams through a struct-of-arrays workspace in HBM indexed [field][stage][slot]; the 32
-// lanes of a warp own 32 consecutive slots, so every access is a fully coalesced 256-byte
-// transaction.  Tensor cores are not used: the stage blocks are 7x7 FP64 and the recursion
-// over stages is sequential (see DESIGN.md for the roofline argument).
+// Two kernels solve the same NLP with the same IPM driver (ipm_iterate_t, ascent_ipm.cuh):
+//   ascent_ipm_kernel   ONE PROBLEM PER THREAD, persistent warps, for batches that fill the GPU (>= ~1 wave of
+//                       148 x 256 problems).  The stage data of a problem (55-67 doubles x nt) streams through a
+//                       workspace in HBM laid out [stage][warp][field][lane]: every access of a warp is one
+//                       coalesced 256-byte row, staged one stage ahead in shared memory with cp.async.  Each sweep
+//                       re-evaluates the model, so the HBM traffic stays near 3x the algorithmic minimum.
+//   ascent_coop_kernel  EIGHT LANES PER PROBLEM (ascent_coop.cuh), for everything smaller: a single solve, the
+//                       1 024 / 4 096-problem configurations, a 65 536 batch strong-scaled over 8 GPUs.  Model
+//                       evaluation is stage-parallel over the group and stored per stage; the Riccati recursion
+//                       runs on the stored records with the cost-to-go distributed by rows over the group.
+// Both claim problems from a device-side queue and never return to the host during a solve (barrier updates,
+// fraction-to-boundary, filter line search and convergence masks live in the owning lanes).  Tensor cores are
+// not used: the stage blocks are 8x8 FP64 and the recursion over stages is sequential.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -19,6 +23,7 @@
 
 #include "../../include/lmato_b200.h"
 #include "ascent_ipm_dc.cuh"
+#include "ascent_coop.cuh"
 
 using namespace lmato;
 
@@ -47,9 +52,9 @@ constexpr int kBlock = 256;
 constexpr int kBlocksPerSM = 1;
 // dynamic shared memory: the staging tiles, then one workspace view per thread
 constexpr size_t kTileSmem = (size_t)(kBlock / 32) * 2 * TILE_ROWS * LANES * sizeof(double) + kBlock * sizeof(Ws);
-// The warm start costs one serial single-problem solve (~13 ms); measured break-even is ~8k problems.
-// measured break-even of the first call on a handle (7.6 ms single-thread reference solve against ~6 saved
-// iterations): 512-2048 problems; later calls re-converge the reference in ~1.5 ms and win at every size
+// Batch warm start: one reference solve of the batch-mean problem (cooperative kernel, one group) against ~6 saved
+// iterations per problem.  Measured break-even of the first call on a handle: 512-2048 problems (later calls
+// re-converge the reference from the previous one in 1-2 iterations and win at every size).
 constexpr long kWarmStartMinBatch = 1024;
 
 struct KArgs {
@@ -128,8 +133,8 @@ __device__ __forceinline__ Params derive_params(const double* __restrict__ p, lo
   return P;
 }
 
-// Params padded to an odd number of 8-byte words per thread so that the per-thread structs in
-// shared memory are bank-conflict free (stride 19 doubles = 38 words; 38 mod 32 = 6).
+// Params padded to an odd number of doubles per thread so that the per-thread structs in shared memory
+// are bank-conflict free (Params = 19 doubles -> stride 21 doubles = 42 words; 42 mod 32 = 10).
 struct alignas(8) ParamsSlot { Params p; double pad[(sizeof(Params) / 8) % 2 == 0 ? 1 : 2]; };
 
 static_assert(GuessSrc::V_Y == LMATO_V_Y && GuessSrc::V_YDOT == LMATO_V_YDOT && GuessSrc::V_X == LMATO_V_X &&
@@ -277,6 +282,7 @@ __global__ void __launch_bounds__(kBlock, kBlocksPerSM) ascent_ipm_kernel(KArgs 
           // campaign have nearly the same mean, so it re-converges in one or two iterations).
           if (a.guess_traj) {
             SW::guess_from(P, M, O, W, GuessSrc{a.guess_traj, a.guess_tf, a.B, b}, S.cur);
+            S.from_guess = true;
           } else if (a.ref_mode != 0 && SW::load_ref(P, M, O, W, a.ref, S.cur, &mu0)) {
             S.warm = true;
             S.ctl.mu = mu0;
@@ -295,8 +301,11 @@ __global__ void __launch_bounds__(kBlock, kBlocksPerSM) ascent_ipm_kernel(KArgs 
     //  a few iterations while the warps stay close enough to share the instruction cache)
     if ((round++ % LMATO_SYNC_PERIOD) == 0 && !__syncthreads_or((active || !exhausted) ? 1 : 0)) break;
     if (active && ipm_iterate_t<SW>(P, M, O, W, S)) {
-      if (S.warm && S.ctl.status != ST_CONVERGED) {
-        // a warm start that did not work out: this lane restarts the same problem from the cold start
+      if ((S.warm || S.from_guess) && S.ctl.status != ST_CONVERGED) {
+        // a warm start, or a caller's start point (lmato_set_initial_guess), that did not work out: this lane
+        // restarts the same problem from the built-in roll-out.  (IPOPT would enter its feasibility restoration
+        // phase from such a point, e.g. from the reference's all-zero start values LO:39, 83-96; this solver's
+        // substitute is a start point that is dynamically feasible by construction.)
         ipm_begin(O, S);
         SW::guess(P, M, O, W, S.cur);
         continue;
@@ -309,6 +318,173 @@ __global__ void __launch_bounds__(kBlock, kBlocksPerSM) ascent_ipm_kernel(KArgs 
         continue;
       }
       pending = true;      // results are written when the whole chunk is done (see above)
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// cooperative kernel: G lanes per problem (ascent_coop.cuh)
+// ---------------------------------------------------------------------------------------
+constexpr int kCoopBlock = 256;
+constexpr int kCoopBlocksPerSM = 2;
+constexpr int kCoopG = 8;
+constexpr int kCoopScrStride = coop::SCR_DOUBLES;       // per group: record ring + transpose tiles (even: 16-byte aligned)
+static size_t coop_smem(int gp) { return sizeof(double) * (size_t)(kCoopBlock / gp) * kCoopScrStride; }
+
+template <int G>
+__device__ __noinline__ void coop_write_results(const KArgs& a, const Params& P, const coop::Cws& W, const IpmState& S, long b) {
+  SolveOut out;
+  ipm_result(S, out);
+  const int nt = a.N + 1;
+  const long B = a.B;
+  if (W.g == 0) {
+    a.tf[b] = out.tf;
+    a.fmass[b] = P.M0 - P.fuel * (P.mflow * P.T * out.tf);   // mass(nt-1) = mflow*T*tf (LO:123)
+    a.status[b] = out.status;
+    a.iters[b] = out.iters;
+    if (a.kkt) a.kkt[b] = out.kkt;
+  }
+  if (!a.traj && !a.sens) return;
+  double* __restrict__ t = a.traj;
+  if (t) {
+    for (int v = W.g; v < LMATO_NVAR; v += G) t[((long)v * nt) * B + b] = 0.0;   // node 0 pinned
+  }
+  // (see write_results above for the sensitivity formulas)
+  double s_ft = 0.0, s_m0 = 0.0, s_mf = 0.0, s_asc = 0.0;
+  for (int k = 1 + W.g; k <= a.N; k += G) {
+    double x[coop::XR];
+    coop::ldv<coop::XR>(W.X(out.cur, k), x);
+    const double* z = x + coop::X_Z;
+    const double u = x[coop::X_U];
+    const double m = P.mflow * P.T * a.tau[k] * out.tf;
+    double ay, ax;
+    if (a.sens) {
+      Accel1 f;
+      accel_first(P, z[0], z[2], z[4], m, f);
+      ay = f.ay; ax = f.ax;
+      const double al = a.h[k] * P.T * out.tf;
+      const double l1 = x[coop::X_LAM + 1], l3 = x[coop::X_LAM + 3], l5 = x[coop::X_LAM + 5];
+      const double thrust = l1 * (f.AT * f.Ty * P.Sinv) + l3 * (f.AT * f.Tx * P.Sinv);
+      s_ft -= al * thrust / P.Ft;
+      s_m0 += al * thrust * (f.AT / P.Ft);
+      s_mf -= al * (l1 * f.ay_m + l3 * f.ax_m) * (P.T * a.tau[k] * out.tf);
+      s_asc -= al * u * l5;
+    } else {
+      accel_value(P, z[0], z[2], z[4], m, ay, ax);
+    }
+    if (!t) continue;
+    t[((long)LMATO_V_Y * nt + k) * B + b] = z[0];
+    t[((long)LMATO_V_YDOT * nt + k) * B + b] = z[1];
+    t[((long)LMATO_V_YDOUBLEDOT * nt + k) * B + b] = ay;
+    t[((long)LMATO_V_X * nt + k) * B + b] = z[2];
+    t[((long)LMATO_V_XDOT * nt + k) * B + b] = z[3];
+    t[((long)LMATO_V_XDOUBLEDOT * nt + k) * B + b] = ax;
+    t[((long)LMATO_V_ANGLE * nt + k) * B + b] = z[4];
+    t[((long)LMATO_V_ANGLEDOT * nt + k) * B + b] = z[5];
+    t[((long)LMATO_V_MASS * nt + k) * B + b] = m;
+    t[((long)LMATO_V_ANGLEDOUBLEDOT * nt + k) * B + b] = u;
+  }
+  if (a.sens) {
+    s_ft = coop::Grp<G>::sum(W.mask, s_ft); s_m0 = coop::Grp<G>::sum(W.mask, s_m0);
+    s_mf = coop::Grp<G>::sum(W.mask, s_mf); s_asc = coop::Grp<G>::sum(W.mask, s_asc);
+    if (W.g == 0) {
+      const double inv = 1.0 / a.O.obj_scale;
+      a.sens[(long)LMATO_S_FT * B + b] = s_ft * inv;
+      a.sens[(long)LMATO_S_M0 * B + b] = s_m0 * inv;
+      a.sens[(long)LMATO_S_M_DOT * B + b] = s_mf * inv / P.fuel;
+      a.sens[(long)LMATO_S_ANGLE_DOUBLEDOT_MAX * B + b] = s_asc * inv / 3.0;
+    }
+  }
+}
+
+// A warp holds 32/GP problems; its groups run the IPM driver in lock step (same sweep at the same time, each
+// with its own lane mask), finished groups idle until the warp's chunk is done, then the warp claims the next
+// chunk from the device-wide queue.  IpmState (filter, barrier parameter, ...) is carried redundantly by the
+// GP lanes of a group: every decision of the driver is a function of group-uniform values.
+//   GP = 8 : four problems per warp, for batches that can fill the GPU that way;
+//   GP = 32: the whole warp works on one problem (the stage-parallel phases are four times shorter), for
+//            the latency regime: up to a few problems per SM.
+template <int G, int GP, bool MOVE>
+__global__ void __launch_bounds__(kCoopBlock, (GP == 32 ? 1 : kCoopBlocksPerSM)) ascent_coop_kernel(KArgs a) {
+  using SW = SweepsCoop<G, GP, MOVE>;
+  constexpr int PPW = 32 / GP;                 // problems per warp
+  constexpr int GPB = kCoopBlock / GP;         // groups per block
+  __shared__ ParamsSlot sP[GPB];
+  __shared__ Options sO;
+  __shared__ Mesh sM;
+  extern __shared__ __align__(16) double sScr[];    // [GPB][kCoopScrStride]
+  if (threadIdx.x == 0) { sO = a.O; sM = Mesh{a.N, a.h, a.tau}; }
+  __syncthreads();
+  const Options& O = sO;
+  const Mesh& M = sM;
+  const int lane = threadIdx.x & 31;
+  const int grp = threadIdx.x / GP;
+  const unsigned gmask = GP == 32 ? 0xffffffffu : (((1u << GP) - 1u) << ((lane / GP) * GP));
+  const unsigned smask = ((1u << G) - 1u) << ((lane / GP) * GP);
+  Params& P = sP[grp].p;
+  const long slot = (long)blockIdx.x * GPB + grp;
+  const coop::Cws W{a.ws + slot * coop::coop_doubles_per_problem(a.N + 1), a.N + 1, sScr + grp * kCoopScrStride,
+                    lane % GP, gmask, smask, 0.0, 0.0, 0};
+  IpmState S;
+  bool active = false, pending = false, exhausted = false, first = true;
+  long b = -1;
+  const int warps_per_block = kCoopBlock / 32;
+  while (true) {
+    const bool chunk_done = !__any_sync(0xffffffffu, active);
+    if (chunk_done && __any_sync(0xffffffffu, pending)) {
+      if (pending) coop_write_results<GP>(a, P, W, S, b);
+      pending = false;
+    }
+    if (!exhausted && chunk_done) {
+      int chunk = 0;
+      if (first) {
+        chunk = (threadIdx.x / 32) * gridDim.x + blockIdx.x;     // static round-robin: spreads a small batch over all SMs
+        first = false;
+      } else {
+        if (lane == 0) chunk = atomicAdd(a.counter, 1) + gridDim.x * warps_per_block;
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+      }
+      if ((long)chunk * PPW >= a.B) {
+        exhausted = true;
+      } else {
+        b = (long)chunk * PPW + lane / GP;
+        if (b < a.B) {
+          if (W.g == 0) P = derive_params(a.params, a.B, b, a.model);
+          coop::Grp<GP>::sync(gmask);
+          ipm_begin(O, S);
+          double mu0 = 0.0;
+          if (a.guess_traj) {
+            SW::guess_from(P, M, O, W, GuessSrc{a.guess_traj, a.guess_tf, a.B, b}, S.cur);
+            S.from_guess = true;
+          } else if (a.ref_mode != 0 && SW::load_ref(P, M, O, W, a.ref, S.cur, &mu0)) {
+            S.warm = true;
+            S.ctl.mu = mu0;
+            S.ctl.tau = dmax(O.tau_min, 1.0 - mu0);
+          } else {
+            SW::guess(P, M, O, W, S.cur);
+          }
+          active = true;
+        }
+      }
+    }
+    // (no block barrier per iteration here: the warps of an SM are few and their sweeps are short; a warp that
+    //  waits for its neighbours' line-search retries loses more than the instruction cache gains)
+    if (exhausted && !__any_sync(0xffffffffu, active || pending)) break;
+    if (active && ipm_iterate_t<SW>(P, M, O, W, S)) {
+      if ((S.warm || S.from_guess) && S.ctl.status != ST_CONVERGED) {
+        // a warm start or a caller's guess that did not work out: restart from the built-in roll-out
+        ipm_begin(O, S);
+        SW::guess(P, M, O, W, S.cur);
+        continue;
+      }
+      active = false;
+      if (a.ref_mode == 1) {
+        SolveOut out;
+        ipm_result(S, out);
+        SW::store_ref(P, M, W, out.cur, S.cur, S.ctl.mu, out.status == ST_CONVERGED, a.ref);
+        continue;
+      }
+      pending = true;
     }
   }
 }
@@ -396,7 +572,35 @@ struct lmato_handle {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaStream_t last_stream = nullptr;
   bool timed = false;
+  bool last_coop = false;         // which kernel the last solve used
 };
+
+// device-side part of lmato_create (every failure path returns through the caller's lmato_destroy)
+static lmato_status_t create_device_state(lmato_handle* H, const std::vector<double>& h, const std::vector<double>& tau) {
+  const int nt = H->nt;
+  CUDA_TRY(cudaSetDevice(H->device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, H->device));
+  H->sm_count = prop.multiProcessorCount;
+  // the staging tiles need the opt-in shared-memory size (158 KB dynamic + 42 KB static per CTA)
+  CUDA_TRY(cudaFuncSetAttribute(ascent_ipm_kernel<Sweeps7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmem));
+  CUDA_TRY(cudaFuncSetAttribute(ascent_ipm_kernel<Sweeps8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmem));
+  CUDA_TRY(cudaFuncSetAttribute(ascent_coop_kernel<kCoopG, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coop_smem(8)));
+  CUDA_TRY(cudaFuncSetAttribute(ascent_coop_kernel<kCoopG, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coop_smem(8)));
+  CUDA_TRY(cudaFuncSetAttribute(ascent_coop_kernel<kCoopG, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coop_smem(32)));
+  CUDA_TRY(cudaFuncSetAttribute(ascent_coop_kernel<kCoopG, 32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coop_smem(32)));
+  CUDA_TRY(cudaMalloc(&H->d_h, sizeof(double) * nt));
+  CUDA_TRY(cudaMalloc(&H->d_tau, sizeof(double) * nt));
+  CUDA_TRY(cudaMemcpy(H->d_h, h.data(), sizeof(double) * nt, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(H->d_tau, tau.data(), sizeof(double) * nt, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMalloc(&H->d_counter, sizeof(int)));
+  CUDA_TRY(cudaMalloc(&H->d_ref, sizeof(double) * (size_t)dc::REF_ROWS * nt));   // dc:: is the larger layout
+  CUDA_TRY(cudaMemset(H->d_ref, 0, sizeof(double) * (size_t)dc::REF_ROWS * nt));   // REF_OK = 0: no reference yet
+  CUDA_TRY(cudaMalloc(&H->d_refparams, sizeof(double) * (LMATO_NPARAM + 8)));
+  CUDA_TRY(cudaEventCreate(&H->ev0));
+  CUDA_TRY(cudaEventCreate(&H->ev1));
+  return LMATO_OK;
+}
 
 extern "C" {
 
@@ -417,6 +621,10 @@ void lmato_default_options(lmato_options* o) {
   o->dcost = 1e-5;            // LO:99
   o->kappa_eps = 30.0;
   o->objective_nodes = 0;     // 0 = nt - 1
+  o->kernel = LMATO_KERNEL_AUTO;
+  o->coop_lanes = 0;
+  o->otol = 1e-3;             // LO:31
+  o->rtol = 1e-3;             // LO:32
   o->max_iter = 20000;   // LO:28
   o->max_ls = 40;
 }
@@ -455,23 +663,8 @@ lmato_status_t lmato_create(lmato_handle** out, int32_t device, int32_t nt, cons
   if (!H) { set_err("lmato_create: out of host memory"); return LMATO_ERR_INVALID; }
   H->device = device; H->nt = nt; H->nodes = nodes; H->model = model;
   lmato_default_options(&H->opt);
-  CUDA_TRY(cudaSetDevice(device));
-  cudaDeviceProp prop;
-  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-  H->sm_count = prop.multiProcessorCount;
-  // the staging tiles need the opt-in shared-memory size (158 KB dynamic + 42 KB static per CTA)
-  CUDA_TRY(cudaFuncSetAttribute(ascent_ipm_kernel<Sweeps7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmem));
-  CUDA_TRY(cudaFuncSetAttribute(ascent_ipm_kernel<Sweeps8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmem));
-  CUDA_TRY(cudaMalloc(&H->d_h, sizeof(double) * nt));
-  CUDA_TRY(cudaMalloc(&H->d_tau, sizeof(double) * nt));
-  CUDA_TRY(cudaMemcpy(H->d_h, h.data(), sizeof(double) * nt, cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMemcpy(H->d_tau, tau.data(), sizeof(double) * nt, cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMalloc(&H->d_counter, sizeof(int)));
-  CUDA_TRY(cudaMalloc(&H->d_ref, sizeof(double) * (size_t)dc::REF_ROWS * nt));   // dc:: is the larger layout
-  CUDA_TRY(cudaMemset(H->d_ref, 0, sizeof(double) * (size_t)dc::REF_ROWS * nt));   // REF_OK = 0: no reference yet
-  CUDA_TRY(cudaMalloc(&H->d_refparams, sizeof(double) * (LMATO_NPARAM + 8)));
-  CUDA_TRY(cudaEventCreate(&H->ev0));
-  CUDA_TRY(cudaEventCreate(&H->ev1));
+  const lmato_status_t rc = create_device_state(H, h, tau);
+  if (rc != LMATO_OK) { lmato_destroy(H); return rc; }      // frees whatever was allocated before the failure
   *out = H;
   return LMATO_OK;
 }
@@ -493,7 +686,9 @@ lmato_status_t lmato_set_options(lmato_handle* h, const lmato_options* o) {
       !(o->tf_guess > 0 && o->tf_guess < 1) || o->max_iter < 0 || o->max_ls < 1 ||
       !(o->mu_min_factor > 0 && o->mu_min_factor <= 1) || o->n_polish < -1 ||
       (o->warm_start < 0 || o->warm_start > 2) || !(o->mu_ref > 0 && o->mu_ref <= o->mu_init) ||
-      !(o->dcost >= 0) || o->objective_nodes < 0 || !(o->kappa_eps >= 1.0)) {
+      !(o->dcost >= 0) || o->objective_nodes < 0 || !(o->kappa_eps >= 1.0) ||
+      o->kernel < LMATO_KERNEL_AUTO || o->kernel > LMATO_KERNEL_COOP || !(o->otol >= 0) || !(o->rtol >= 0) ||
+      (o->coop_lanes != 0 && o->coop_lanes != 8 && o->coop_lanes != 32)) {
     set_err("lmato_set_options: option out of range");
     return LMATO_ERR_INVALID;
   }
@@ -504,6 +699,17 @@ lmato_status_t lmato_set_options(lmato_handle* h, const lmato_options* o) {
 // The move-suppression term (LO:99) applies to the MV angledoubledot of the elliptical model; the
 // circular model's MV is the angle itself and runs without it.
 static bool dcost_active(const lmato_handle* h) { return h->opt.dcost > 0.0 && h->model == LMATO_MODEL_ELLIPTICAL; }
+
+// Which kernel solves a batch of B problems.  One thread per problem needs ~1 wave (SMs x 256 problems) to fill
+// the GPU and streams the least HBM traffic per problem; eight lanes per problem fill it with an eighth of that
+// and shorten the critical path of every problem, at ~2.5x the traffic.  Measured cross-over on B200 at nt = 200:
+// between 16 384 and 32 768 problems (profiles/README.md).
+constexpr int64_t kCoopMaxBatch = 24576;
+static bool use_coop(const lmato_handle* h, int64_t B) {
+  if (h->opt.kernel == LMATO_KERNEL_COOP) return true;
+  if (h->opt.kernel == LMATO_KERNEL_THREAD) return false;
+  return B <= kCoopMaxBatch;
+}
 static int fields_for(const lmato_handle* h) { return dcost_active(h) ? (int)dc::N_FIELDS : (int)N_FIELDS; }
 
 static long slots_for(const lmato_handle* h, int64_t B) {
@@ -512,10 +718,29 @@ static long slots_for(const lmato_handle* h, int64_t B) {
   const long grid = chunks < (long)h->sm_count * kBlocksPerSM ? (chunks > 0 ? chunks : 1) : (long)h->sm_count * kBlocksPerSM;
   return grid * kBlock;
 }
+// cooperative kernel: lanes per problem in the stage-parallel phases.  A whole warp per problem while that still
+// gives every SM at most ~8 warps (the latency regime), otherwise 8 lanes (four problems per warp).
+static int coop_gp_for(const lmato_handle* h, int64_t B) {
+  if (h->opt.coop_lanes == 8 || h->opt.coop_lanes == 32) return h->opt.coop_lanes;
+  return B <= (int64_t)h->sm_count * 8 ? 32 : 8;
+}
+// CTAs of 256 threads = 256/GP groups; a warp's chunk is 32/GP problems
+static long coop_grid_for(const lmato_handle* h, int64_t B, int gp) {
+  const long chunks = (B + (32 / gp) - 1) / (32 / gp);
+  const long cap = (long)h->sm_count * (gp == 32 ? 1 : kCoopBlocksPerSM);
+  return chunks < cap ? (chunks > 0 ? chunks : 1) : cap;
+}
+static size_t coop_ws_bytes(const lmato_handle* h, long grid, int gp) {
+  return sizeof(double) * (size_t)coop::coop_doubles_per_problem(h->nt) * (size_t)(grid * (kCoopBlock / gp));
+}
+static size_t ws_bytes_for(const lmato_handle* h, int64_t B) {
+  if (use_coop(h, B)) { const int gp = coop_gp_for(h, B); return coop_ws_bytes(h, coop_grid_for(h, B, gp), gp); }
+  return sizeof(double) * (size_t)fields_for(h) * (size_t)h->nt * (size_t)slots_for(h, B);
+}
 
 lmato_status_t lmato_workspace_bytes(lmato_handle* h, int64_t B, int64_t* bytes) {
   if (!h || !bytes || B < 0) { set_err("lmato_workspace_bytes: bad argument"); return LMATO_ERR_INVALID; }
-  *bytes = (int64_t)sizeof(double) * fields_for(h) * h->nt * slots_for(h, B);
+  *bytes = (int64_t)ws_bytes_for(h, B);
   return LMATO_OK;
 }
 
@@ -538,11 +763,22 @@ lmato_status_t lmato_solve_batch(lmato_handle* h, const double* params, int64_t 
   }
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
+  // Every solve on a handle shares its workspace, work-queue counter and warm-start reference.  A solve issued on
+  // a different stream than the previous one first waits (on the device) for that one to finish.
+  if (h->timed && st != h->last_stream) CUDA_TRY(cudaStreamWaitEvent(st, h->ev1, 0));
+  const bool coopk = use_coop(h, B);
   const long slots = slots_for(h, B);
+  const int gp = coop_gp_for(h, B);
+  const long cgrid = coop_grid_for(h, B, gp);
   const bool use_dc = dcost_active(h);
-  const size_t need = sizeof(double) * (size_t)fields_for(h) * (size_t)h->nt * (size_t)slots;
+  const bool warm = !h->guess_traj && (h->opt.warm_start == 2 || (h->opt.warm_start == 1 && B >= kWarmStartMinBatch));
+  size_t need = ws_bytes_for(h, B);
+  if (warm) { const size_t r = coop_ws_bytes(h, 1, 32); if (r > need) need = r; }     // the reference solve: one warp of one CTA
   if (need > h->ws_bytes) {
-    if (h->d_ws) { CUDA_TRY(cudaStreamSynchronize(st)); CUDA_TRY(cudaFree(h->d_ws)); h->d_ws = nullptr; h->ws_bytes = 0; }
+    if (h->d_ws) {
+      if (h->timed) CUDA_TRY(cudaEventSynchronize(h->ev1));     // the previous solve may still be using it
+      CUDA_TRY(cudaFree(h->d_ws)); h->d_ws = nullptr; h->ws_bytes = 0;
+    }
     CUDA_TRY(cudaMalloc(&h->d_ws, need));
     h->ws_bytes = need;
   }
@@ -555,7 +791,12 @@ lmato_status_t lmato_solve_batch(lmato_handle* h, const double* params, int64_t 
   a.ws = h->d_ws; a.slots = slots; a.N = h->nt - 1; a.h = h->d_h; a.tau = h->d_tau;
   a.counter = h->d_counter;
   a.model = h->model;
-  a.O.tol = h->opt.tol; a.O.mu_init = h->opt.mu_init; a.O.obj_scale = h->opt.obj_scale;
+  // OTOL / RTOL (LO:31-32): how APMonitor maps them onto IPOPT's `tol` is not verifiable here, so the rule is
+  // the conservative one: the solve runs to the tightest of tol, otol and rtol (defaults 1e-10, 1e-3, 1e-3).
+  double tol = h->opt.tol;
+  if (h->opt.otol > 0.0 && h->opt.otol < tol) tol = h->opt.otol;
+  if (h->opt.rtol > 0.0 && h->opt.rtol < tol) tol = h->opt.rtol;
+  a.O.tol = tol; a.O.mu_init = h->opt.mu_init; a.O.obj_scale = h->opt.obj_scale;
   // barrier decrease exponent: IPOPT's 1.5 from the cold start, 2 from the batch warm start.  Measured on the
   // benchmark batch (warm): 1.3 / 1.5 / 1.7 / 2.0 / 2.5 / 3.0 -> 91 / 96 / 95 / 88 / 88 / 115 ms; from the cold
   // start 2.0 costs 0.7 iterations more than 1.5.  kappa_mu and tau_min do not matter.
@@ -569,12 +810,12 @@ lmato_status_t lmato_solve_batch(lmato_handle* h, const double* params, int64_t 
     a.O.w_dcost = use_dc ? h->opt.obj_scale * h->opt.dcost / (double)on : 0.0;
   }
   a.ref = nullptr; a.ref_mode = 0;
-  const int grid = (int)(slots / kBlock);
   CUDA_TRY(cudaEventRecord(h->ev0, st));
   // (a caller-supplied guess replaces the batch warm start)
-  if (!h->guess_traj && (h->opt.warm_start == 2 || (h->opt.warm_start == 1 && B >= kWarmStartMinBatch))) {
-    // reference problem = batch mean, solved down to mu_ref only (one thread; ~10 iterations from the
-    // cold start on the first call, 1-2 from the previous call's reference afterwards)
+  if (warm) {
+    // reference problem = batch mean, solved down to mu_ref only by ONE group of the cooperative kernel without
+    // the move term (at mu_ref >> w it is immaterial): ~10 iterations from the cold start on the first call,
+    // 1-2 from the previous call's reference afterwards
     mean_params_kernel<<<LMATO_NPARAM, 256, 0, st>>>(params, B, h->d_refparams);
     CUDA_TRY(cudaGetLastError());
     KArgs r = a;
@@ -584,18 +825,30 @@ lmato_status_t lmato_solve_batch(lmato_handle* h, const double* params, int64_t 
     r.guess_traj = nullptr; r.guess_tf = nullptr;
     r.ref = h->d_ref; r.ref_mode = 1;
     r.O.tol = 10.0 * h->opt.mu_ref; r.O.mu_min_factor = 0.1; r.O.n_polish = 0;
-    r.O.w_dcost = 0.0;     // always the 7-state solve: cheaper, and at mu_ref >> w the move term is immaterial
-    ascent_ipm_kernel<Sweeps7><<<1, kBlock, kTileSmem, st>>>(r);
+    r.O.w_dcost = 0.0;
+    ascent_coop_kernel<kCoopG, 32, false><<<1, kCoopBlock, coop_smem(32), st>>>(r);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemsetAsync(h->d_counter, 0, sizeof(int), st));
     a.ref = h->d_ref; a.ref_mode = 2;
     h->launches += 2;
   }
-  if (use_dc) ascent_ipm_kernel<Sweeps8><<<grid, kBlock, kTileSmem, st>>>(a);
-  else ascent_ipm_kernel<Sweeps7><<<grid, kBlock, kTileSmem, st>>>(a);
+  if (coopk) {
+    if (gp == 32) {
+      if (use_dc) ascent_coop_kernel<kCoopG, 32, true><<<(int)cgrid, kCoopBlock, coop_smem(32), st>>>(a);
+      else ascent_coop_kernel<kCoopG, 32, false><<<(int)cgrid, kCoopBlock, coop_smem(32), st>>>(a);
+    } else {
+      if (use_dc) ascent_coop_kernel<kCoopG, 8, true><<<(int)cgrid, kCoopBlock, coop_smem(8), st>>>(a);
+      else ascent_coop_kernel<kCoopG, 8, false><<<(int)cgrid, kCoopBlock, coop_smem(8), st>>>(a);
+    }
+  } else {
+    const int grid = (int)(slots / kBlock);
+    if (use_dc) ascent_ipm_kernel<Sweeps8><<<grid, kBlock, kTileSmem, st>>>(a);
+    else ascent_ipm_kernel<Sweeps7><<<grid, kBlock, kTileSmem, st>>>(a);
+  }
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaEventRecord(h->ev1, st));
   h->last_stream = st; h->timed = true;
+  h->last_coop = coopk;
   h->launches += 1;
   return LMATO_OK;
 }

@@ -1,0 +1,1121 @@
+// Cooperative sweeps: G lanes of a warp per problem (G = 8 on the device; G = 1 is the same code run by
+// one lane, which is how tests/test_device_source_on_host.py checks it on the CPU).
+//
+// Same NLP, same Newton system and same IPM driver (ipm_iterate_t, ascent_ipm.cuh) as the one-thread-per-
+// problem sweeps of ascent_ipm_dc.cuh, organised for the regime that kernel cannot serve: batches too
+// small to fill the GPU with one thread per problem (a single solve, SURVEY's configs 1-3 and 5, a
+// 65 536 batch strong-scaled over 8 GPUs).  There the time is the latency of one thread walking every
+// stage of every sweep.  Here
+//   * everything that does not depend on the recursion is evaluated STAGE-PARALLEL: lane g of a group
+//     takes stages g+1, g+1+G, ...  The trial point, its defects, merit and KKT-error terms, and the
+//     model of the next Newton system (dynamics Jacobian with its structured inverse, Lagrangian
+//     Hessian, condensed move cost: the "M record") are produced in one such pass per line-search
+//     trial and kept, so the model is evaluated once per trial instead of once per sweep;
+//   * the block-tridiagonal LDL^T (Riccati recursion) runs over the stored M records with the 8x8
+//     cost-to-go distributed by rows over the group: W E^-1 is a row operation, E^-T (W E^-1) is the
+//     same row operation after a transpose of the 8x8 block across the group (through shared memory),
+//     and the rank-one condensation of the move needs one row broadcast;
+//   * the forward substitution and the adjoint recursion for the new multipliers are 8-vector affine
+//     recursions (40-70 flops per stage); every lane of the group carries them redundantly, which
+//     costs nothing in SIMT time and needs no communication;
+//   * fraction-to-boundary ratios, the merit slope and the right-hand sides of the adjoint recursion
+//     are again stage-parallel.
+// Formulation: always the 8-state one of ascent_ipm_dc.cuh, s = (y, vy, x, vx | angle, angledot, u, tf),
+// control = the move v_k = u_k - u_{k-1}.  MOVE = true carries the reference's l1 move-suppression term
+// (angledoubledot.DCOST, LO:99) as the slack pair (p, n); MOVE = false is the same NLP with a free move
+// (dcost = 0) and also serves the circular model (coup5 = 0), so there is ONE implementation.
+//
+// Data layout (HBM/L2): per problem one contiguous block of per-stage records,
+//   X[2][N+1][24]  iterate (ping-pong)      D[N+1][16]  step (ds, du, dv, pi)
+//   M[2][N+1][52]  model at the iterate     K[N+1][10]  feedback law     H[N+1][8]  adjoint right-hand sides
+// Records are 16-byte aligned and read with 128-bit loads.  A sequential phase reads one record per
+// stage (the same addresses on all lanes of the group: one transaction); a stage-parallel phase reads
+// G consecutive records per group.
+#pragma once
+#include "ascent_ipm_dc.cuh"
+
+namespace lmato {
+namespace coop {
+
+enum : int {
+  X_Z = 0, X_U = 6, X_LAM = 7 /* 7 */, X_ZLA = 14, X_ZUA = 15, X_ZLU = 16, X_ZUU = 17,
+  X_PP = 18, X_PN = 19, X_ZPP = 20, X_ZPN = 21, XR = 24,
+  D_DS = 0 /* ds[0..5], du */, D_DV = 7, D_PI = 8 /* 7 */, DR = 16,
+  // M record: stage Jacobian with its structured inverse, defects, Hessian and gradient pieces
+  J_AL = 0, J_ALA, J_ALB, J_ALC, J_ALD, J_M11, J_M13, J_M31, J_M33, J_GA1, J_GA3,
+  J_E0, J_E1, J_E2, J_E3, J_E4, J_E5, J_BETA, JR = 20,
+  M_J = 0, M_C = JR /* 6 defects */, M_Q = JR + 8,
+  Q_00 = 0, Q_02, Q_22, Q_04, Q_24, Q_44, Q_T0 /* tf column, rows 0..6 */, Q_77 = Q_T0 + 7, Q_RU, Q_D0,
+  Q_G4A, Q_G4B /* gradient of angle = A + mu*B */, Q_GUA, Q_GUB /* gradient of u */,
+  Q_MVR, Q_MVA, Q_MVB /* condensed move cost: Hessian, gradient A + mu*B */, QR = 24,
+  MR = M_Q + QR,
+  K_FF = 8, KR = 10,
+  HR = 8,
+  PER_STAGE = 2 * XR + DR + 2 * MR + KR + HR,
+  SCR_TR1 = 80, SCR_TR2 = 72,                                    // group scratch: the two transpose tiles of backward()
+  // record ring of the sequential phases (cp.async, see rg_*): slots of backward / forward / adjoint
+  RING_D = 4,                             // slots (a power of two): records travel RING_D-1 stages ahead
+  RING_SB = MR,                           // backward: the whole M record
+  RING_SF = M_Q + KR,                     // forward: J, c of the M record, then the feedback law
+  RING_SA = JR + HR,                      // adjoint: J, then the right-hand side
+  RING_DOUBLES = RING_D * RING_SB,
+  SCR_DOUBLES = SCR_TR1 + SCR_TR2 + RING_DOUBLES
+};
+
+// 128-bit moves of N (even) doubles
+template <int N>
+LM_HD void ldv(const double* __restrict__ p, double* out) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+  for (int i = 0; i < N; i += 2) { const double2 v = *reinterpret_cast<const double2*>(p + i); out[i] = v.x; out[i + 1] = v.y; }
+#else
+  for (int i = 0; i < N; ++i) out[i] = p[i];
+#endif
+}
+template <int N>
+LM_HD void stv(double* __restrict__ p, const double* in) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+  for (int i = 0; i < N; i += 2) *reinterpret_cast<double2*>(p + i) = make_double2(in[i], in[i + 1]);
+#else
+  for (int i = 0; i < N; ++i) p[i] = in[i];
+#endif
+}
+
+// Group primitives.  A group = G consecutive lanes of a warp (aligned); `m` is its lane mask.
+template <int G>
+struct Grp {
+  LM_HD static double sum(unsigned m, double v) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(m, v, o);
+#endif
+    return v;
+  }
+  LM_HD static double max(unsigned m, double v) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v = dmax(v, __shfl_xor_sync(m, v, o));
+#endif
+    return v;
+  }
+  LM_HD static double min(unsigned m, double v) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v = dmin(v, __shfl_xor_sync(m, v, o));
+#endif
+    return v;
+  }
+  LM_HD static int any(unsigned m, int v) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v |= __shfl_xor_sync(m, v, o);
+#endif
+    return v;
+  }
+  LM_HD static int bcast_int(unsigned m, int v, int src) {
+#if defined(__CUDA_ARCH__)
+    if (G > 1) v = __shfl_sync(m, v, src, G);
+#endif
+    return v;
+  }
+  // value of lane `src` (index inside the group) on every lane
+  LM_HD static double bcast(unsigned m, double v, int src) {
+#if defined(__CUDA_ARCH__)
+    if (G > 1) v = __shfl_sync(m, v, src, G);
+#endif
+    return v;
+  }
+  // running maximum of num/den across the group (the pair travels; ties keep the lower lane's)
+  LM_HD static void ratio_max(unsigned m, RatioMax& r) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+      const double n2 = __shfl_xor_sync(m, r.n, o), d2 = __shfl_xor_sync(m, r.d, o);
+      if (n2 * r.d > r.n * d2) { r.n = n2; r.d = d2; }
+    }
+    r.n = bcast(m, r.n, 0); r.d = bcast(m, r.d, 0);
+#endif
+  }
+  LM_HD static void sync(unsigned m) {
+#if defined(__CUDA_ARCH__)
+    if (G > 1) __syncwarp(m);
+#endif
+  }
+};
+
+// View of one problem's workspace block for one lane of its group.
+struct Cws {
+  double* base;
+  int N1;                // N + 1 records per array
+  double* scr;           // group scratch, SCR_DOUBLES doubles (shared memory on the device, 16-byte aligned): ring, then the tiles
+  int g;                 // lane inside the group (0 .. GP-1)
+  unsigned mask;         // the GP lanes of the group (stage-parallel phases, phase boundaries)
+  unsigned smask;        // its first G lanes (sequential phases)
+  mutable double dw;     // delta_w of the last factorisation (the adjoint recursion uses the same Hessian)
+  mutable double pimax;  // largest new defect multiplier of the last adjoint recursion
+  mutable int ls_flag;   // set by the driver while the least-squares multiplier estimate runs
+  LM_HD double* ring() const { return scr; }
+  LM_HD double* tiles() const { return scr + RING_DOUBLES; }
+  LM_HD double* X(int buf, int k) const { return base + ((long)buf * N1 + k) * XR; }
+  LM_HD double* D(int k) const { return base + (2L * N1) * XR + (long)k * DR; }
+  LM_HD double* Mo(int buf, int k) const { return base + (2L * N1) * XR + (long)N1 * DR + ((long)buf * N1 + k) * MR; }
+  LM_HD double* K(int k) const { return base + (2L * N1) * XR + (long)N1 * DR + (2L * N1) * MR + (long)k * KR; }
+  LM_HD double* H(int k) const { return base + (2L * N1) * XR + (long)N1 * DR + (2L * N1) * MR + (long)N1 * KR + (long)k * HR; }
+};
+LM_HD long coop_doubles_per_problem(int nt) { return (long)nt * PER_STAGE; }
+static_assert(RING_SF <= RING_SB && RING_SA <= RING_SB, "ring too small");
+
+// Record ring.  A sequential phase reads one small record set per stage, at addresses known in advance; without
+// help each stage would start with an exposed L2/HBM round trip (~700 cycles against 100-400 cycles of
+// arithmetic).  The group copies the records DEPTH-1 stages ahead into its shared-memory ring with cp.async
+// (LDGSTS: 16-byte chunks spread over the lanes, no registers), one commit group per stage; a stage waits for
+// its own group, then a group barrier makes every lane's chunks visible.
+#if defined(__CUDA_ARCH__)
+typedef unsigned RingRef;      // shared-space byte address of this lane's first 16-byte chunk of slot 0
+#else
+typedef double* RingRef;
+#endif
+LM_HD RingRef rg_ref(double* ring, int g) {
+#if defined(__CUDA_ARCH__)
+  return (unsigned)__cvta_generic_to_shared(ring) + 16u * (unsigned)g;
+#else
+  return ring + 2 * g;
+#endif
+}
+// copy a record of NDBL doubles (16-byte chunks, chunk c*G+g by lane g) to offset `off` (doubles) of the ring;
+// `src` already points at this lane's first chunk
+template <int G, int NDBL>
+LM_HD void rg_copy(RingRef r, int off, const double* src, int g) {
+#pragma unroll
+  for (int c = 0; c < (NDBL / 2 + G - 1) / G; ++c) {
+    if (c * G + g < NDBL / 2) {
+#if defined(__CUDA_ARCH__)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(r + 8u * (unsigned)(off + 2 * c * G)), "l"(src + 2 * c * G) : "memory");
+#else
+      r[off + 2 * c * G] = src[2 * c * G]; r[off + 2 * c * G + 1] = src[2 * c * G + 1];
+#endif
+    }
+  }
+}
+LM_HD void rg_commit() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int PENDING>
+LM_HD void rg_wait() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory");
+#endif
+}
+
+LM_HD void jac_load(const double* m, StageJac& J) {
+  double j[JR];
+  ldv<JR>(m + M_J, j);
+  J.al = j[J_AL]; J.ala = j[J_ALA]; J.alb = j[J_ALB]; J.alc = j[J_ALC]; J.ald = j[J_ALD];
+  J.m11 = j[J_M11]; J.m13 = j[J_M13]; J.m31 = j[J_M31]; J.m33 = j[J_M33];
+  J.ga1 = j[J_GA1]; J.ga3 = j[J_GA3];
+  J.e0 = j[J_E0]; J.e1 = j[J_E1]; J.e2 = j[J_E2]; J.e3 = j[J_E3]; J.e4 = j[J_E4]; J.e5 = j[J_E5];
+  J.beta = j[J_BETA];
+}
+
+// ---------------------------------------------------------------------------------------
+// Model of the Newton system at one stage of one point -> M record.  Gradient pieces that depend
+// on the barrier parameter are kept as (A, B) with value A + mu*B, and delta_w is added by the
+// consumers, so a record stays valid when mu or delta_w change.  ls: the least-squares multiplier
+// estimate of IPOPT section 3.6 (Hessian := I, gradient := grad f - zL + zU), as in stage_hessian().
+// ---------------------------------------------------------------------------------------
+template <bool MOVE>
+LM_HD void build_stage(const Params& P, const Options& O, double kap, double taum, double tf, bool ls,
+                       const double* z, double u, const double* zp, double up, const double* lam,
+                       double zla, double zua, double zlu, double zuu,
+                       double pp, double pn, double zpp, double zpn, double* mrec) {
+  Accel1 f;
+  accel_first(P, z[0], z[2], z[4], taum * tf, f);
+  StageJac J;
+  stagejac_build(P, kap, tf, taum, f, z[1], z[3], z[5], u, J);
+  stagejac_invert(J);
+  double j[JR];
+  j[J_AL] = J.al; j[J_ALA] = J.ala; j[J_ALB] = J.alb; j[J_ALC] = J.alc; j[J_ALD] = J.ald;
+  j[J_M11] = J.m11; j[J_M13] = J.m13; j[J_M31] = J.m31; j[J_M33] = J.m33;
+  j[J_GA1] = J.ga1; j[J_GA3] = J.ga3;
+  j[J_E0] = J.e0; j[J_E1] = J.e1; j[J_E2] = J.e2; j[J_E3] = J.e3; j[J_E4] = J.e4; j[J_E5] = J.e5;
+  j[J_BETA] = J.beta; j[18] = 0.0; j[19] = 0.0;
+  stv<JR>(mrec + M_J, j);
+  const double al = J.al;
+  double c[8];
+  c[0] = z[0] - zp[0] - al * z[1];
+  c[1] = z[1] - zp[1] - al * f.ay;
+  c[2] = z[2] - zp[2] - al * z[3];
+  c[3] = z[3] - zp[3] - al * f.ax;
+  c[4] = z[4] - zp[4] - al * z[5];
+  c[5] = z[5] - P.coup5 * zp[5] - J.beta * u;
+  c[6] = 0.0; c[7] = 0.0;
+  stv<8>(mrec + M_C, c);
+  StageQ q;
+  stage_hessian(P, f, J, kap, taum, lam, z[4], u, zla, zua, zlu, zuu, 1.0, 0.0, ls, q);
+  double o[QR];
+  o[Q_00] = q.q00; o[Q_02] = q.q02; o[Q_22] = q.q22; o[Q_04] = q.q04; o[Q_24] = q.q24; o[Q_44] = q.q44;
+  o[Q_T0 + 0] = q.q06; o[Q_T0 + 1] = q.q16; o[Q_T0 + 2] = q.q26; o[Q_T0 + 3] = q.q36;
+  o[Q_T0 + 4] = q.q46; o[Q_T0 + 5] = q.q56; o[Q_T0 + 6] = q.sig;
+  o[Q_77] = q.q66; o[Q_RU] = q.R; o[Q_D0] = q.d;
+  o[Q_G4A] = ls ? q.q4 : 0.0; o[Q_G4B] = ls ? 0.0 : q.q4;
+  o[Q_GUA] = ls ? q.r : 0.0;  o[Q_GUB] = ls ? 0.0 : q.r;
+  if (MOVE) {
+    dc::Move mv;
+    mv.build(pp, pn, zpp, zpn, u - up, O.w_dcost, 0.0, ls);
+    o[Q_MVR] = mv.R; o[Q_MVA] = mv.r;
+    o[Q_MVB] = ls ? 0.0 : -(mv.ip * mv.Sn - mv.in_ * mv.Sp) * mv.sinv;
+  } else {
+    o[Q_MVR] = 0.0; o[Q_MVA] = 0.0; o[Q_MVB] = 0.0;
+  }
+  o[QR - 1] = 0.0;
+  stv<QR>(mrec + M_Q, o);
+}
+
+// (re)build the M records of buffer `buf` from its X records (start point; least-squares phase)
+template <int GP, bool MOVE>
+LM_SWEEP void coop_build(const Params& P, const Mesh& M, const Options& O, const Cws& W, int buf, double tf, bool ls) {
+  const int N = M.N;
+  for (int k = 1 + W.g; k <= N; k += GP) {
+    double x[XR], xm[8];
+    ldv<XR>(W.X(buf, k), x);
+    ldv<8>(W.X(buf, k - 1), xm);
+    build_stage<MOVE>(P, O, M.h[k] * P.T, P.mT * M.tau[k], tf, ls, x + X_Z, x[X_U], xm + X_Z, xm[X_U], x + X_LAM,
+                      x[X_ZLA], x[X_ZUA], x[X_ZLU], x[X_ZUU], x[X_PP], x[X_PN], x[X_ZPP], x[X_ZPN], W.Mo(buf, k));
+  }
+  Grp<GP>::sync(W.mask);
+}
+
+// ---------------------------------------------------------------------------------------
+// backward sweep: block LDL^T of the KKT matrix in stage order over the stored M records.
+// Lane g owns rows g*R .. g*R+R-1 of the 8x8 cost-to-go and the same elements of its affine part
+// (R = 8/G).  Per stage
+//   W = P_k + Q_k,  g = p_k + q_k
+//   X = W E^-1                      row operation on the owned rows
+//   transpose [X | g] across the group (shared-memory tile), g becomes known to every lane
+//   Wt = X^T E^-1 (= E^-T W E^-1),  g~ = E^-T g
+//   symmetrise Wt through a second tile: 0.5 (Wt + Wt^T).  This is not cosmetic: with barrier terms
+//   Sigma ~ 1e13 on the diagonal, entries (i,j) and (j,i) computed by different lanes differ by ~1e-3
+//   absolute, and un-symmetrised the recursion loses Newton's quadratic convergence near the solution
+//   (measured on the host build: 33-35 instead of 28-32 iterations, inertia corrections appear)
+//   condense the move (row / column 6, read from the same tile), P_{k-1} = D (Wt - ...) D
+// identical, up to rounding, to dc::riccati_backward.  Returns false on wrong inertia.
+// ---------------------------------------------------------------------------------------
+template <int G, bool MOVE>
+LM_SWEEP bool coop_backward_seq(const Params& P, const Mesh& M, const Options& O, const Cws& W, int src,
+                                const Scal& c0, double mu, double dw, bool ls, double* dtf_out) {
+  constexpr int R = 8 / G;
+  const int N = M.N;
+  const int g = W.g;
+  const unsigned gm = W.smask;
+  double Pr[R][8], pr[R];
+  {
+    double zn[8];
+    ldv<8>(W.X(src, N), zn);
+    TermQP tq;
+    terminal_qp(P, O, c0, zn, mu, dw, ls, tq);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int i = g * R + r;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) Pr[r][j] = 0.0;
+      pr[r] = 0.0;
+#pragma unroll
+      for (int ii = 0; ii < 4; ++ii)
+        if (i == ii) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) Pr[r][j] = tq.H[ii][j];
+          pr[r] = tq.g[ii];
+        }
+      if (i == 7) { Pr[r][7] = tq.H66; pr[r] = tq.g6; }
+    }
+  }
+  const double cw = ls ? 0.0 : 1.0;     // defects are dropped in the least-squares mode
+  const double cp = P.coup5;
+  double* tr1 = W.tiles();              // 8 x 10: X rows with the affine part as ninth column
+  double* tr2 = W.tiles() + SCR_TR1;    // 8 x 9 : Wt rows
+  bool ok = true;
+  double* ring = W.ring();
+  const RingRef rr = rg_ref(ring, g);
+  const double* pm = W.Mo(src, N) + 2 * g;     // next record to copy (this lane's first chunk), stepping down
+  int kn = N;
+#pragma unroll
+  for (int d = 0; d < RING_D - 1; ++d) {
+    if (kn >= 1) rg_copy<G, MR>(rr, (kn & (RING_D - 1)) * RING_SB, pm, g);
+    rg_commit();
+    --kn; pm -= MR;
+  }
+  rg_wait<RING_D - 2>();                       // stage N has landed; made visible by the barrier below
+  Grp<G>::sync(gm);
+  for (int k = N; k >= 1; --k) {
+    if (kn >= 1) rg_copy<G, MR>(rr, (kn & (RING_D - 1)) * RING_SB, pm, g);
+    rg_commit();
+    --kn; pm -= MR;
+    const double* m = ring + (k & (RING_D - 1)) * RING_SB;
+    StageJac J;
+    jac_load(m, J);
+    double c[8], q[QR];
+    ldv<8>(m + M_C, c);
+    ldv<QR>(m + M_Q, q);
+    const double dd = q[Q_D0] + dw;
+    // ---- W = Q_k + P_k (owned rows), g = q_k + p_k ----
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int i = g * R + r;
+      const bool e0 = (i == 0), e2 = (i == 2), e4 = (i == 4), e7 = (i == 7);
+      Pr[r][0] += e0 ? q[Q_00] + dw : e2 ? q[Q_02] : e4 ? q[Q_04] : e7 ? q[Q_T0 + 0] : 0.0;
+      Pr[r][2] += e0 ? q[Q_02] : e2 ? q[Q_22] + dw : e4 ? q[Q_24] : e7 ? q[Q_T0 + 2] : 0.0;
+      Pr[r][4] += e0 ? q[Q_04] : e2 ? q[Q_24] : e4 ? q[Q_44] + dw : e7 ? q[Q_T0 + 4] : 0.0;
+      Pr[r][1] += (i == 1) ? dd : e7 ? q[Q_T0 + 1] : 0.0;
+      Pr[r][3] += (i == 3) ? dd : e7 ? q[Q_T0 + 3] : 0.0;
+      Pr[r][5] += (i == 5) ? dd : e7 ? q[Q_T0 + 5] : 0.0;
+      Pr[r][6] += (i == 6) ? q[Q_RU] + dw : e7 ? q[Q_T0 + 6] : 0.0;
+      double t7 = q[Q_77];
+#pragma unroll
+      for (int ii = 0; ii < 7; ++ii) t7 = (i == ii) ? q[Q_T0 + ii] : t7;
+      Pr[r][7] += t7;
+      pr[r] += e4 ? q[Q_G4A] + mu * q[Q_G4B] : (i == 6) ? q[Q_GUA] + mu * q[Q_GUB] : 0.0;
+    }
+    // ---- X = W E^-1 (row operation), transpose [X | g] across the group ----
+#pragma unroll
+    for (int r = 0; r < R; ++r) dc::solveET8(J, Pr[r]);
+    double gt[8];
+    if (G > 1) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int i = g * R + r;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) tr1[i * 10 + j] = Pr[r][j];
+        tr1[i * 10 + 8] = pr[r];
+      }
+      Grp<G>::sync(gm);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int i = g * R + r;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) Pr[r][j] = tr1[j * 10 + i];
+      }
+#pragma unroll
+      for (int l = 0; l < 8; ++l) gt[l] = tr1[l * 10 + 8];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        gt[i] = pr[i % R];
+#pragma unroll
+        for (int j = 0; j < i; ++j) { const double t = Pr[i % R][j]; Pr[i % R][j] = Pr[j % R][i]; Pr[j % R][i] = t; }
+      }
+    }
+    // ---- Wt = X^T E^-1,  g~ = E^-T g (every lane) ----
+#pragma unroll
+    for (int r = 0; r < R; ++r) dc::solveET8(J, Pr[r]);
+    dc::solveET8(J, gt);
+    // ---- symmetrise; row 6 (= column 6) of Wt to every lane ----
+    double w6[8];
+    if (G > 1) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int i = g * R + r;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) tr2[i * 9 + j] = Pr[r][j];
+      }
+      rg_wait<RING_D - 2>();                   // the next stage's record has landed (this lane's chunks) ...
+      Grp<G>::sync(gm);                        // ... and, after the barrier, everyone's
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int i = g * R + r;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) Pr[r][j] = 0.5 * (Pr[r][j] + tr2[j * 9 + i]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) w6[j] = 0.5 * (tr2[6 * 9 + j] + tr2[j * 9 + 6]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < i; ++j) { const double v = 0.5 * (Pr[i % R][j] + Pr[j % R][i]); Pr[i % R][j] = v; Pr[j % R][i] = v; }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) w6[j] = Pr[6 % R][j];
+      rg_wait<RING_D - 2>();
+    }
+    // ---- condense the move: it enters the u row (index 6) with coefficient 1 ----
+    double wc6 = 0.0;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) wc6 = fma(w6[j], c[j], wc6);
+    const double rx6 = gt[6] - cw * wc6;
+    const double Ruu = q[Q_MVR] + (MOVE && !ls ? dw : 0.0) + w6[6];
+    const double ru = q[Q_MVA] + mu * q[Q_MVB] + rx6;
+    if (!(Ruu > 0.0) || !(Ruu < 1e300)) ok = false;
+    const double Rinv = lm_rcp(Ruu);
+    w6[5] *= cp;                          // d defect_k / d s_{k-1} = -D, D = diag(1,1,1,1,1,coup5,1,1)
+    double w6s[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w6s[j] = w6[j] * Rinv;
+    const double kff = ru * Rinv;
+    if (g == 6 / R) {
+      double kk[KR];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) kk[j] = -w6s[j];
+      kk[K_FF] = -kff; kk[9] = 0.0;
+      stv<KR>(W.K(k), kk);
+    }
+    // ---- P_{k-1} = D Wt D - (D w6)(D w6)^T / Ruu ,  p_{k-1} = D (g~ - Wt c) - D w6 ru / Ruu ----
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int i = g * R + r;
+      double wc = 0.0;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) wc = fma(Pr[r][j], c[j], wc);
+      double gti = gt[7];
+#pragma unroll
+      for (int ii = 0; ii < 7; ++ii) gti = (i == ii) ? gt[ii] : gti;
+      const double rs = (i == 5) ? cp : 1.0;
+      const double w6i = rs * Pr[r][6];
+      Pr[r][5] *= cp;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) Pr[r][j] = fma(-w6i, w6s[j], rs * Pr[r][j]);
+      pr[r] = fma(-w6i, kff, rs * (gti - cw * wc));
+    }
+    if (!ok) return false;
+  }
+  // node 0: everything pinned except tf
+  const double P77 = Grp<G>::bcast(gm, Pr[7 % R][7], 7 / R);
+  const double p7 = Grp<G>::bcast(gm, pr[7 % R], 7 / R);
+  if (!(P77 > 0.0)) return false;
+  *dtf_out = -p7 / P77;
+  return true;
+}
+
+// the G lanes of the sequential group factorise; the result goes to all GP lanes of the group
+template <int G, int GP, bool MOVE>
+LM_SWEEP bool coop_backward(const Params& P, const Mesh& M, const Options& O, const Cws& W, int src,
+                            const Scal& c0, double mu, double dw, bool ls, double* dtf_out) {
+  W.dw = dw;
+  double dtf = 0.0;
+  int ok = 0;
+  if (W.g < G) ok = coop_backward_seq<G, MOVE>(P, M, O, W, src, c0, mu, dw, ls, &dtf) ? 1 : 0;
+  Grp<GP>::sync(W.mask);                     // the feedback law K is read by forward()
+  if (GP > G) { ok = Grp<GP>::bcast_int(W.mask, ok, 0); dtf = Grp<GP>::bcast(W.mask, dtf, 0); }
+  *dtf_out = dtf;
+  return ok != 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// forward sweep: (1) primal Newton step, an 8-vector recursion carried redundantly by every lane;
+// (2) stage-parallel: steps of the move slack pair and of the bound multipliers, fraction-to-boundary
+// ratios, merit slope, and the right-hand sides Q_k ds_k + q_k of the adjoint recursion; (3) the adjoint
+// recursion E_k^T pi_k = D pi_{k+1} - (Q_k ds_k + q_k) for the new defect multipliers.
+// ---------------------------------------------------------------------------------------
+template <int G, int GP, bool MOVE>
+LM_SWEEP void coop_forward(const Params& P, const Mesh& M, const Options& O, const Cws& W, int src,
+                           const Scal& c0, double mu, double tau, double dtf, bool ls, TermStep& ts, StepInfo& si) {
+  const int N = M.N;
+  const int g = W.g;
+  const unsigned gm = W.smask;       // sequential group
+  const unsigned pmk = W.mask;       // parallel group
+  const double cw = ls ? 0.0 : 1.0;
+  const double cp = P.coup5;
+  const double dw = W.dw;
+  const double wdc = O.w_dcost;
+  // ---- (1) ds_k = E_k^-1 (D ds_{k-1} + e_6 dv_k - c_k),  dv_k = k_k + K_k ds_{k-1} ----
+  double ds[8] = {0, 0, 0, 0, 0, 0, 0, dtf};
+  double* ring = W.ring();
+  const RingRef rr = rg_ref(ring, g);
+  if (g < G) {
+    const double* pm = W.Mo(src, 1) + 2 * g;
+    const double* pk = W.K(1) + 2 * g;
+    int kn = 1;
+#pragma unroll
+    for (int d = 0; d < RING_D - 1; ++d) {
+      if (kn <= N) { rg_copy<G, M_Q>(rr, (kn & (RING_D - 1)) * RING_SF, pm, g); rg_copy<G, KR>(rr, (kn & (RING_D - 1)) * RING_SF + M_Q, pk, g); }
+      rg_commit();
+      ++kn; pm += MR; pk += KR;
+    }
+    for (int k = 1; k <= N; ++k) {
+      if (kn <= N) { rg_copy<G, M_Q>(rr, (kn & (RING_D - 1)) * RING_SF, pm, g); rg_copy<G, KR>(rr, (kn & (RING_D - 1)) * RING_SF + M_Q, pk, g); }
+      rg_commit();
+      ++kn; pm += MR; pk += KR;
+      rg_wait<RING_D - 1>();
+      Grp<G>::sync(gm);
+      const double* m = ring + (k & (RING_D - 1)) * RING_SF;
+      StageJac J;
+      jac_load(m, J);
+      double c[8], kk[KR];
+      ldv<8>(m + M_C, c);
+      ldv<KR>(m + M_Q, kk);
+    double dv = kk[K_FF];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dv = fma(kk[i], ds[i], dv);
+    double xi[8];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) xi[i] = ds[i] - cw * c[i];
+    xi[5] = cp * ds[5] - cw * c[5];
+    xi[6] = ds[6] + dv;
+    xi[7] = dtf;
+    dc::solveE8(J, xi);
+#pragma unroll
+    for (int i = 0; i < 7; ++i) ds[i] = xi[i];
+      if (g == 0) {
+        double o[8];
+#pragma unroll
+        for (int i = 0; i < 7; ++i) o[i] = ds[i];
+        o[D_DV] = dv;
+        stv<8>(W.D(k) + D_DS, o);
+      }
+    }
+  }
+  Grp<GP>::sync(pmk);
+  // ---- (2) stage-parallel ----
+  double dphi = 0.0, dxmax = 0.0;
+  RatioMax rp, rz;
+  rp.init(); rz.init();
+  TermQP tq;
+  if (((N - 1) % GP) == g) {
+    double zn[8];
+    ldv<8>(W.X(src, N), zn);
+    terminal_qp(P, O, c0, zn, mu, dw, ls, tq);
+  }
+  for (int k = 1 + g; k <= N; k += GP) {
+    double x[XR], d[8], q[QR];
+    ldv<XR>(W.X(src, k), x);
+    ldv<8>(W.D(k), d);
+    ldv<QR>(W.Mo(src, k) + M_Q, q);
+    const double u = x[X_U], du = d[6], da = d[4], dv = d[D_DV];
+    if (MOVE) {
+      const double up = W.X(src, k - 1)[X_U];
+      dc::Move mv;
+      mv.build(x[X_PP], x[X_PN], x[X_ZPP], x[X_ZPN], u - up, wdc, mu, ls);
+      double dp, dn;
+      mv.steps(dv, dp, dn);
+      const double ip = mv.ip, in_ = mv.in_;
+      rp.push(-dp, x[X_PP]); rp.push(-dn, x[X_PN]);
+      rz.push(-((mu - x[X_ZPP] * dp) * ip - x[X_ZPP]), x[X_ZPP]);
+      rz.push(-((mu - x[X_ZPN] * dn) * in_ - x[X_ZPN]), x[X_ZPN]);
+      dphi += (wdc - mu * ip) * dp + (wdc - mu * in_) * dn;
+      dxmax = dmax(dxmax, dmax(fabs(dp), fabs(dn)) * dmin(1.0, dmax(ip, in_)));
+    }
+#pragma unroll
+    for (int i = 0; i < 7; ++i) dxmax = dmax(dxmax, fabs(d[i]));
+    const double a = x[X_Z + 4];
+    const double dLa = a, dUa = P.a_ub - a, dLu = u + P.u_ub, dUu = P.u_ub - u;
+    rp.push(-da, dLa); rp.push(da, dUa); rp.push(-du, dLu); rp.push(du, dUu);
+    const double zla = x[X_ZLA], zua = x[X_ZUA], zlu = x[X_ZLU], zuu = x[X_ZUU];
+    double rLa, rUa, rLu, rUu;
+    recip4(dLa, dUa, dLu, dUu, rLa, rUa, rLu, rUu);
+    rz.push(-((mu - zla * da) * rLa - zla), zla);
+    rz.push(-((mu + zua * da) * rUa - zua), zua);
+    rz.push(-((mu - zlu * du) * rLu - zlu), zlu);
+    rz.push(-((mu + zuu * du) * rUu - zuu), zuu);
+    dphi += mu * ((rUa - rLa) * da + (rUu - rLu) * du);
+    // right-hand side of the adjoint recursion (same Hessian as the factorisation, delta_w included)
+    const double dd = q[Q_D0] + dw;
+    double h[8];
+    h[0] = (q[Q_00] + dw) * d[0] + q[Q_02] * d[2] + q[Q_04] * d[4] + q[Q_T0 + 0] * dtf;
+    h[1] = dd * d[1] + q[Q_T0 + 1] * dtf;
+    h[2] = q[Q_02] * d[0] + (q[Q_22] + dw) * d[2] + q[Q_24] * d[4] + q[Q_T0 + 2] * dtf;
+    h[3] = dd * d[3] + q[Q_T0 + 3] * dtf;
+    h[4] = q[Q_04] * d[0] + q[Q_24] * d[2] + (q[Q_44] + dw) * d[4] + q[Q_T0 + 4] * dtf + q[Q_G4A] + mu * q[Q_G4B];
+    h[5] = dd * d[5] + q[Q_T0 + 5] * dtf;
+    h[6] = (q[Q_RU] + dw) * du + q[Q_T0 + 6] * dtf + q[Q_GUA] + mu * q[Q_GUB];
+    h[7] = 0.0;
+    if (k == N) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        h[i] += tq.H[i][0] * d[0] + tq.H[i][1] * d[1] + tq.H[i][2] * d[2] + tq.H[i][3] * d[3] + tq.g[i];
+    }
+    stv<HR>(W.H(k), h);
+  }
+  dphi = Grp<GP>::sum(pmk, dphi);
+  dxmax = dmax(Grp<GP>::max(pmk, dxmax), fabs(dtf));
+  Grp<GP>::ratio_max(pmk, rp);
+  Grp<GP>::ratio_max(pmk, rz);
+  // ---- terminal slacks and multipliers (every lane) ----
+  {
+    double zm[8];
+    ldv<8>(W.X(src, N), zm);
+    ldv<8>(W.D(N), ds);                  // the step of the last node (lanes outside the sequential group did not carry it)
+    const double tf = c0.tf;
+    Terminal T;
+    terminal_eval(P, zm[0], zm[1], zm[2], zm[3], T);
+    const double rinv = 1.0 / T.rT;
+    const double dg1 = T.Yb * rinv * ds[0] + zm[2] * rinv * ds[2];
+    const double dg2 = 2.0 * zm[1] * ds[1] + 2.0 * zm[3] * ds[3];
+    const double dg3 = zm[1] * ds[0] + T.Yb * ds[1] + zm[3] * ds[2] + zm[2] * ds[3];
+    ts.dtf = dtf;
+    ts.dsg1 = dg1 + cw * (T.g1 - c0.sg1);
+    ts.dsg2 = dg2 + cw * (T.g2 - c0.sg2);
+    ts.dnu3 = (dg3 + cw * T.g3) / O.delta_c;
+    if (!ls) {
+      ts.dzs1 = mu / c0.sg1 - c0.zs1 - c0.zs1 / c0.sg1 * ts.dsg1;
+      ts.dzs2 = mu / c0.sg2 - c0.zs2 - c0.zs2 / c0.sg2 * ts.dsg2;
+    } else {
+      ts.dzs1 = 0.0; ts.dzs2 = 0.0;
+    }
+    const double dLt = tf, dUt = P.tf_ub - tf;
+    ts.dzLt = mu / dLt - c0.zLt - c0.zLt / dLt * dtf;
+    ts.dzUt = mu / dUt - c0.zUt + c0.zUt / dUt * dtf;
+    rp.push(-ts.dsg1, c0.sg1); rp.push(-ts.dsg2, c0.sg2); rp.push(-dtf, dLt); rp.push(dtf, dUt);
+    rz.push(-ts.dzs1, c0.zs1); rz.push(-ts.dzs2, c0.zs2); rz.push(-ts.dzLt, c0.zLt); rz.push(-ts.dzUt, c0.zUt);
+    dphi += (O.obj_scale - mu / dLt + mu / dUt) * dtf - mu / c0.sg1 * ts.dsg1 - mu / c0.sg2 * ts.dsg2;
+    dxmax = dmax(dxmax, dmax(fabs(ts.dsg1), fabs(ts.dsg2)));
+  }
+  si.a_max = (rp.n > tau * rp.d) ? tau * rp.d / rp.n : 1.0;
+  si.a_z = (rz.n > tau * rz.d) ? tau * rz.d / rz.n : 1.0;
+  si.dphi = dphi; si.dxmax = dxmax;
+  Grp<GP>::sync(pmk);
+  // ---- (3) adjoint recursion, every lane of the sequential group ----
+  double pin[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  double pimax = 0.0;
+  if (g < G) {
+  const double* pm = W.Mo(src, N) + 2 * g;
+  const double* ph = W.H(N) + 2 * g;
+  int kn = N;
+#pragma unroll
+  for (int d = 0; d < RING_D - 1; ++d) {
+    if (kn >= 1) { rg_copy<G, JR>(rr, (kn & (RING_D - 1)) * RING_SA, pm, g); rg_copy<G, HR>(rr, (kn & (RING_D - 1)) * RING_SA + JR, ph, g); }
+    rg_commit();
+    --kn; pm -= MR; ph -= HR;
+  }
+  for (int k = N; k >= 1; --k) {
+    if (kn >= 1) { rg_copy<G, JR>(rr, (kn & (RING_D - 1)) * RING_SA, pm, g); rg_copy<G, HR>(rr, (kn & (RING_D - 1)) * RING_SA + JR, ph, g); }
+    rg_commit();
+    --kn; pm -= MR; ph -= HR;
+    rg_wait<RING_D - 1>();
+    Grp<G>::sync(gm);
+    const double* m = ring + (k & (RING_D - 1)) * RING_SA;
+    StageJac J;
+    jac_load(m, J);
+    double h[HR], gg[8];
+    ldv<HR>(m + JR, h);
+#pragma unroll
+    for (int i = 0; i < 7; ++i) gg[i] = pin[i] - h[i];
+    gg[5] = cp * pin[5] - h[5];
+    gg[7] = 0.0;
+    dc::solveET8(J, gg);
+#pragma unroll
+    for (int i = 0; i < 7; ++i) pin[i] = gg[i];
+    if (ls) {        // only the least-squares multiplier estimate looks at the size of the multipliers
+#pragma unroll
+      for (int i = 0; i < 7; ++i) pimax = dmax(pimax, fabs(gg[i]));
+    }
+    if (g == 0) { gg[7] = 0.0; stv<8>(W.D(k) + D_PI, gg); }
+  }
+  }
+  Grp<GP>::sync(pmk);
+  W.pimax = GP > G ? Grp<GP>::bcast(pmk, pimax, 0) : pimax;
+}
+
+// ---------------------------------------------------------------------------------------
+// evaluation pass, stage-parallel: trial point x + alpha dx written to buffer `dst`, its merit and
+// KKT-error terms, and the M records of the trial point (the model of the next Newton system).
+// The per-stage arithmetic is that of dc::eval_pass.
+// ---------------------------------------------------------------------------------------
+template <int GP, bool MOVE>
+LM_SWEEP void coop_eval(const Params& P, const Mesh& M, const Options& O, const Cws& W, int src, int dst,
+                        const Scal& c0, const TermStep& ts, double mu, double alpha, double alpha_z,
+                        double alpha_lam, Scal& t) {
+  const int N = M.N;
+  const int g = W.g;
+  const unsigned gm = W.mask;
+  const double tf0 = c0.tf, dtf = ts.dtf;
+  const double tf = tf0 + alpha * dtf;
+  const double wdc = O.w_dcost;
+  const double cp = P.coup5;
+  t.tf = tf;
+  // ---- terminal scalars of the trial point (every lane) ----
+  t.sg1 = c0.sg1 + alpha * ts.dsg1;
+  t.sg2 = c0.sg2 + alpha * ts.dsg2;
+  t.nu3 = c0.nu3 + alpha_lam * ts.dnu3;
+  t.zs1 = c0.zs1 + alpha_z * ts.dzs1;
+  t.zs2 = c0.zs2 + alpha_z * ts.dzs2;
+  t.zLt = c0.zLt + alpha_z * ts.dzLt;
+  t.zUt = c0.zUt + alpha_z * ts.dzUt;
+  bool bad0 = false;
+  double sumlog0, cmin0, cmax0, sz0, slam0, gtf0;
+  {
+    const double dLt = tf, dUt = P.tf_ub - tf;
+    if (!(t.sg1 > 0 && t.sg2 > 0 && dLt > 0 && dUt > 0)) bad0 = true;
+    t.zs1 = clip_mult(t.zs1, t.sg1, mu);
+    t.zs2 = clip_mult(t.zs2, t.sg2, mu);
+    t.zLt = clip_mult(t.zLt, dLt, mu);
+    t.zUt = clip_mult(t.zUt, dUt, mu);
+    sumlog0 = log((t.sg1 * t.sg2) * (dLt * dUt));
+    const double q1 = t.sg1 * t.zs1, q2 = t.sg2 * t.zs2, q3 = dLt * t.zLt, q4 = dUt * t.zUt;
+    cmin0 = dmin(dmin(q1, q2), dmin(q3, q4));
+    cmax0 = dmax(dmax(q1, q2), dmax(q3, q4));
+    sz0 = t.zs1 + t.zs2 + t.zLt + t.zUt;
+    slam0 = t.zs1 + t.zs2 + fabs(t.nu3);
+    gtf0 = O.obj_scale - t.zLt + t.zUt;
+  }
+  double theta = 0, prim = 0, dual = 0, sumlog = 0, cmin = 1e300, cmax = 0, slam = 0, sz = 0, gtf = 0, movecost = 0;
+  int bad = 0;
+  for (int k = 1 + g; k <= N; k += GP) {
+    double xo[XR], d[DR], xm[8], dm[8];
+    ldv<XR>(W.X(src, k), xo);
+    ldv<DR>(W.D(k), d);
+    ldv<8>(W.X(src, k - 1), xm);          // node k-1: z, u (node 0 rows are zeros)
+    ldv<8>(W.D(k - 1), dm);
+    double z[7], zp[7];                   // index 6 = u
+#pragma unroll
+    for (int i = 0; i < 7; ++i) { z[i] = fma(alpha, d[i], xo[i]); zp[i] = fma(alpha, dm[i], xm[i]); }
+    const double u_old = xo[X_U], du = d[6], u = z[6];
+    double lam[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) lam[i] = fma(alpha_lam, d[D_PI + i] - xo[X_LAM + i], xo[X_LAM + i]);
+    double zla = xo[X_ZLA], zua = xo[X_ZUA], zlu = xo[X_ZLU], zuu = xo[X_ZUU];
+    const double kap = M.h[k] * P.T;
+    const double taum = P.mT * M.tau[k];
+    // ---- bound multipliers: dz = (mu - z dx)/d - z (old d, old z), then the kappa_Sigma clip ----
+    {
+      double rLa, rUa, rLu, rUu;
+      recip4(xo[4], P.a_ub - xo[4], u_old + P.u_ub, P.u_ub - u_old, rLa, rUa, rLu, rUu);
+      const double da = d[4];
+      zla += alpha_z * ((mu - zla * da) * rLa - zla);
+      zua += alpha_z * ((mu + zua * da) * rUa - zua);
+      zlu += alpha_z * ((mu - zlu * du) * rLu - zlu);
+      zuu += alpha_z * ((mu + zuu * du) * rUu - zuu);
+    }
+    const double dLa = z[4], dUa = P.a_ub - z[4], dLu = u + P.u_ub, dUu = P.u_ub - u;
+    if (!(dLa > 0 && dUa > 0 && dLu > 0 && dUu > 0)) bad = 1;
+    {
+      const double c1 = dLa * zla, c2 = dUa * zua, c3 = dLu * zlu, c4 = dUu * zuu;
+      const double hi = 1e10 * mu, lo = 1e-10 * mu;
+      if (dmax(dmax(c1, c2), dmax(c3, c4)) > hi || dmin(dmin(c1, c2), dmin(c3, c4)) < lo) {
+        zla = clip_mult(zla, dLa, mu); zua = clip_mult(zua, dUa, mu);
+        zlu = clip_mult(zlu, dLu, mu); zuu = clip_mult(zuu, dUu, mu);
+      }
+    }
+    double slack = (dLa * dUa) * (dLu * dUu);
+    {
+      const double c1 = dLa * zla, c2 = dUa * zua, c3 = dLu * zlu, c4 = dUu * zuu;
+      cmin = dmin(cmin, dmin(dmin(c1, c2), dmin(c3, c4)));
+      cmax = dmax(cmax, dmax(dmax(c1, c2), dmax(c3, c4)));
+    }
+    sz += (zla + zua) + (zlu + zuu);
+    // ---- move slack pair ----
+    double pp = xo[X_PP], pn = xo[X_PN], zpp = xo[X_ZPP], zpn = xo[X_ZPN];
+    if (MOVE) {
+      dc::Move mv;
+      mv.build(pp, pn, zpp, zpn, u_old - xm[X_U], wdc, mu, false);
+      double dp, dn;
+      mv.steps(du - dm[6], dp, dn);
+      const double ip = mv.ip, in_ = mv.in_;
+      zpp += alpha_z * ((mu - zpp * dp) * ip - zpp);
+      zpn += alpha_z * ((mu - zpn * dn) * in_ - zpn);
+      pp = fma(alpha, dp, pp);
+      pn = fma(alpha, dn, pn);
+      if (!(pp > 0 && pn > 0)) bad = 1;
+      {
+        const double c1 = pp * zpp, c2 = pn * zpn;
+        if (dmax(c1, c2) > 1e10 * mu || dmin(c1, c2) < 1e-10 * mu) { zpp = clip_mult(zpp, pp, mu); zpn = clip_mult(zpn, pn, mu); }
+      }
+      slack *= pp * pn;
+      {
+        const double c1 = pp * zpp, c2 = pn * zpn;
+        cmin = dmin(cmin, dmin(c1, c2));
+        cmax = dmax(cmax, dmax(c1, c2));
+      }
+      sz += zpp + zpn;
+      movecost += pp + pn;
+    }
+    sumlog += lm_log_pos(slack);
+    // ---- dynamics at the trial point: defects, and the model of the next Newton system ----
+    double* mrec = W.Mo(dst, k);
+    build_stage<MOVE>(P, O, kap, taum, tf, false, z, u, zp, zp[6], lam, zla, zua, zlu, zuu, pp, pn, zpp, zpn, mrec);
+    StageJac J;
+    jac_load(mrec, J);
+    double c[8];
+    ldv<8>(mrec + M_C, c);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const double ac = fabs(c[i]);
+      theta += ac;
+      prim = dmax(prim, ac);
+      slam += fabs(lam[i]);
+    }
+    if (MOVE) {
+      slam += fabs(lam[6]);
+      const double c6 = fabs((u - zp[6]) - pp + pn);            // move row: u_k - u_{k-1} = p - n
+      theta += c6;
+      prim = dmax(prim, c6);
+    }
+    // ---- Lagrangian gradient wrt (s_k, u_k) and wrt the move ----
+    double res[7];
+    applyET6(J, lam, res);
+    res[4] += zua - zla;
+    res[6] = -J.beta * lam[5] + lam[6] - zlu + zuu;
+    if (k == N) {
+      Terminal T;
+      terminal_eval(P, z[0], z[1], z[2], z[3], T);
+      const double c1 = T.g1 - t.sg1, c2 = T.g2 - t.sg2, c3 = T.g3;
+      theta += fabs(c1) + fabs(c2) + fabs(c3);
+      prim = dmax(prim, dmax(fabs(c1), dmax(fabs(c2), fabs(c3))));
+      const double rinv = 1.0 / T.rT;
+      res[0] += -t.zs1 * T.Yb * rinv + t.nu3 * z[1];
+      res[2] += -t.zs1 * z[2] * rinv + t.nu3 * z[3];
+      res[1] += -t.zs2 * 2.0 * z[1] + t.nu3 * T.Yb;
+      res[3] += -t.zs2 * 2.0 * z[3] + t.nu3 * z[2];
+    } else {
+      double xn[8], pn8[8];
+      ldv<8>(W.X(src, k + 1) + X_U, xn);     // u, lam_0..6 of node k+1
+      ldv<8>(W.D(k + 1) + D_PI, pn8);
+#pragma unroll
+      for (int i = 0; i < 7; ++i) {
+        const double ln = fma(alpha_lam, pn8[i] - xn[1 + i], xn[1 + i]);
+        res[i] -= (i == 5 ? cp : 1.0) * ln;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 7; ++i) dual = dmax(dual, fabs(res[i]));
+    if (MOVE) dual = dmax(dual, dmax(fabs(wdc - lam[6] - zpp), fabs(wdc + lam[6] - zpn)));   // d L / d p_k, d L / d n_k
+    else dual = dmax(dual, fabs(lam[6]));                                                   // free move: d L / d v_k
+    gtf -= J.e0 * lam[0] + J.e1 * lam[1] + J.e2 * lam[2] + J.e3 * lam[3] + J.e4 * lam[4] + J.e5 * lam[5];
+    // ---- write the trial iterate ----
+    double xo2[XR];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) { xo2[i] = z[i]; xo2[X_LAM + i] = lam[i]; }
+    xo2[X_ZLA] = zla; xo2[X_ZUA] = zua; xo2[X_ZLU] = zlu; xo2[X_ZUU] = zuu;
+    xo2[X_PP] = pp; xo2[X_PN] = pn; xo2[X_ZPP] = zpp; xo2[X_ZPN] = zpn;
+    xo2[22] = 0.0; xo2[23] = 0.0;
+    stv<XR>(W.X(dst, k), xo2);
+  }
+  theta = Grp<GP>::sum(gm, theta);
+  sumlog = Grp<GP>::sum(gm, sumlog) + sumlog0;
+  slam = Grp<GP>::sum(gm, slam) + slam0;
+  sz = Grp<GP>::sum(gm, sz) + sz0;
+  gtf = Grp<GP>::sum(gm, gtf) + gtf0;
+  movecost = Grp<GP>::sum(gm, movecost);
+  prim = Grp<GP>::max(gm, prim);
+  dual = dmax(Grp<GP>::max(gm, dual), fabs(gtf));
+  cmin = dmin(Grp<GP>::min(gm, cmin), cmin0);
+  cmax = dmax(Grp<GP>::max(gm, cmax), cmax0);
+  const bool anybad = Grp<GP>::any(gm, bad) != 0 || bad0;
+  t.theta = theta;
+  t.fobj = O.obj_scale * tf + wdc * movecost;
+  t.sumlog = anybad ? -1e300 : sumlog;
+  t.prim_inf = prim; t.dual_inf = dual; t.cmin = cmin; t.cmax = cmax; t.sum_lam = slam; t.sum_z = sz;
+  if (anybad || !(theta == theta)) t.theta = 1e300;
+  Grp<GP>::sync(gm);
+}
+
+// ---------------------------------------------------------------------------------------
+// start points
+// ---------------------------------------------------------------------------------------
+LM_HD void coop_zero_node0(const Cws& W) {
+  double zero[XR];
+#pragma unroll
+  for (int i = 0; i < XR; ++i) zero[i] = 0.0;
+  stv<XR>(W.X(0, 0), zero); stv<XR>(W.X(1, 0), zero); stv<DR>(W.D(0), zero);
+}
+
+// one stage of a start point: primal values given, multipliers and slack pair as in dc::init_guess
+LM_HD void coop_store_start(const Params& P, const Options& O, const Cws& W, int k, const double* z6, double u,
+                            double uprev, bool move) {
+  double x[XR], zero[DR];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) x[X_Z + i] = z6[i];
+  x[X_U] = u;
+#pragma unroll
+  for (int i = 0; i < 7; ++i) x[X_LAM + i] = 0.0;
+  x[X_ZLA] = 1.0; x[X_ZUA] = 1.0;
+  // an unbounded control (circular model) starts on the central path of its vacuous bounds
+  x[X_ZLU] = P.coup5 != 0.0 ? 1.0 : O.mu_init / (u + P.u_ub);
+  x[X_ZUU] = P.coup5 != 0.0 ? 1.0 : O.mu_init / (P.u_ub - u);
+  if (move) {
+    // slack pair on its central path for mu_init with lam_6 = 0:  z_p = z_n = w, p + n = t(v), p - n = v
+    const double wd = O.w_dcost, v = u - uprev;
+    const double tt = (O.mu_init + sqrt(O.mu_init * O.mu_init + wd * wd * v * v)) / wd;
+    x[X_PP] = 0.5 * (tt + v); x[X_PN] = 0.5 * (tt - v); x[X_ZPP] = wd; x[X_ZPN] = wd;
+  } else {
+    x[X_PP] = 1.0; x[X_PN] = 1.0; x[X_ZPP] = 0.0; x[X_ZPN] = 0.0;
+  }
+  x[22] = 0.0; x[23] = 0.0;
+  stv<XR>(W.X(0, k), x);
+#pragma unroll
+  for (int i = 0; i < DR; ++i) zero[i] = 0.0;
+  stv<DR>(W.D(k), zero);
+}
+
+LM_HD void coop_start_scalars(Scal& s, double tf0) {
+  s.tf = tf0;
+  s.zLt = 1.0; s.zUt = 1.0;
+  s.sg1 = 1e-2; s.sg2 = 1e-2; s.zs1 = 1.0; s.zs2 = 1.0; s.nu3 = 0.0;
+}
+
+// the bang-bang roll-out of init_guess() (ascent_ipm.cuh); a sequential integration, carried by every lane
+template <int G, bool MOVE>
+LM_NOINLINE void coop_init_guess(const Params& P, const Mesh& M, const Options& O, const Cws& W, Scal& s) {
+  const int N = M.N;
+  const double tf0 = dmin(dmax(O.tf_guess, 1e-2 * P.tf_ub), 0.99 * P.tf_ub);
+  const GuessProfile gp = guess_profile(P);
+  double y = 0, vy = 0, x = 0, vx = 0, a = 0, w = 0, t_prev = 0, u_prev = 0;
+  const double a_lo = 1e-2 * P.a_ub, a_hi = 0.99 * P.a_ub;
+  if (W.g == 0) coop_zero_node0(W);
+  for (int k = 1; k <= N; ++k) {
+    const double t = M.tau[k] * tf0 * P.T;
+    const double dt = t - t_prev;
+    const double tm = 0.5 * (t + t_prev);
+    double u = tm < gp.t1 ? gp.ulev : (tm < gp.t1 + gp.t2 ? -gp.ulev : 0.0);
+    if (P.coup5 != 0.0) {
+      w += dt * P.asc * u;
+      a += dt * w;
+    } else {
+      // circular model: pitch ramps linearly from ~34 deg (PDF p.21 Fig 9); angledot and u follow
+      const double a_new = 0.2 + 0.45 * M.tau[k];
+      w = (a_new - a) / dt;
+      u = w / (dt * P.asc);
+      a = a_new;
+    }
+    const double ac = dmin(dmax(a, a_lo), a_hi);
+    const double m = P.mflow * P.T * M.tau[k] * tf0;
+    double yn = y + dt * vy, xn = x + dt * vx, vyn = vy, vxn = vx;
+    for (int itr = 0; itr < 3; ++itr) {
+      double ay, ax;
+      accel_value(P, yn, xn, ac, m, ay, ax);
+      vyn = vy + dt * ay; vxn = vx + dt * ax;
+      yn = y + dt * vyn;  xn = x + dt * vxn;
+    }
+    y = yn; vy = vyn; x = xn; vx = vxn;
+    if (((k - 1) % G) == W.g) {
+      const double z6[6] = {y, vy, x, vx, ac, w};
+      coop_store_start(P, O, W, k, z6, u, u_prev, MOVE);
+    }
+    u_prev = u;
+    t_prev = t;
+  }
+  coop_start_scalars(s, tf0);
+  Grp<G>::sync(W.mask);
+}
+
+// caller-supplied start point (init_from_guess(), ascent_ipm.cuh), stage-parallel
+template <int G, bool MOVE>
+LM_NOINLINE void coop_init_from_guess(const Params& P, const Mesh& M, const Options& O, const Cws& W, const GuessSrc& Gs,
+                                      Scal& s) {
+  const int N = M.N, nt = N + 1;
+  const double tf0 = dmin(dmax(Gs.tf[Gs.b], 1e-2 * P.tf_ub), 0.99 * P.tf_ub);
+  const double a_lo = 1e-2 * P.a_ub, a_hi = 0.99 * P.a_ub, u_hi = 0.99 * P.u_ub;
+  if (W.g == 0) coop_zero_node0(W);
+  for (int k = 1 + W.g; k <= N; k += G) {
+    const double u = dmin(dmax(Gs.at(GuessSrc::V_U, k, nt), -u_hi), u_hi);
+    const double up = k > 1 ? dmin(dmax(Gs.at(GuessSrc::V_U, k - 1, nt), -u_hi), u_hi) : 0.0;
+    const double z6[6] = {Gs.at(GuessSrc::V_Y, k, nt), Gs.at(GuessSrc::V_YDOT, k, nt), Gs.at(GuessSrc::V_X, k, nt),
+                          Gs.at(GuessSrc::V_XDOT, k, nt), dmin(dmax(Gs.at(GuessSrc::V_ANGLE, k, nt), a_lo), a_hi),
+                          Gs.at(GuessSrc::V_ANGLEDOT, k, nt)};
+    coop_store_start(P, O, W, k, z6, u, up, MOVE);
+  }
+  coop_start_scalars(s, tf0);
+  Grp<G>::sync(W.mask);
+}
+
+// Reference column of the batch warm start, in the layout of ref_store() (ascent_ipm.cuh: the 17 rows of the
+// 7-state iterate, then one row of scalars), so that both kernels can start from a reference produced here.
+template <int G>
+LM_NOINLINE void coop_store_ref(const Params& P, const Mesh& M, const Cws& W, int src, const Scal& c, double mu, bool ok,
+                                double* ref) {
+  const int N1 = M.N + 1;
+  for (int k = 1 + W.g; k <= M.N; k += G) {
+    double x[XR];
+    ldv<XR>(W.X(src, k), x);
+#pragma unroll
+    for (int i = 0; i < 7; ++i) ref[(lmato::F_Z + i) * N1 + k] = x[X_Z + i];        // states, u
+#pragma unroll
+    for (int i = 0; i < 6; ++i) ref[(lmato::F_LAM + i) * N1 + k] = x[X_LAM + i];
+    ref[lmato::F_ZLA * N1 + k] = x[X_ZLA]; ref[lmato::F_ZUA * N1 + k] = x[X_ZUA];
+    ref[lmato::F_ZLU * N1 + k] = x[X_ZLU]; ref[lmato::F_ZUU * N1 + k] = x[X_ZUU];
+  }
+  if (W.g == 0) {
+    double* sc = ref + lmato::N_ITER * N1;
+    sc[REF_OK] = ok ? 1.0 : 0.0; sc[REF_MU] = mu; sc[REF_S] = P.S; sc[REF_TF] = c.tf;
+    sc[REF_ZLT] = c.zLt; sc[REF_ZUT] = c.zUt; sc[REF_SG1] = c.sg1; sc[REF_SG2] = c.sg2;
+    sc[REF_ZS1] = c.zs1; sc[REF_ZS2] = c.zs2; sc[REF_NU3] = c.nu3;
+  }
+}
+
+// start from the reference column (dc::init_from_ref7): the slack pair is put on its central path for the
+// reference's moves and the multiplier of the u row follows from dual feasibility
+template <int G, bool MOVE>
+LM_NOINLINE bool coop_load_ref(const Params& P, const Mesh& M, const Options& O, const Cws& W, const double* ref,
+                               Scal& s, double* mu_out) {
+  const int N1 = M.N + 1;
+  const double* sc = ref + lmato::N_ITER * N1;
+  if (!(sc[REF_OK] > 0.5)) return false;
+  const double r = sc[REF_S] * P.Sinv, ri = P.S / sc[REF_S];
+  const double mu = sc[REF_MU], w = O.w_dcost;
+  if (W.g == 0) coop_zero_node0(W);
+  for (int k = 1 + W.g; k <= M.N; k += G) {
+    double x[XR], zero[DR];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) x[X_Z + i] = ref[(lmato::F_Z + i) * N1 + k] * (i < 4 ? r : 1.0);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) x[X_LAM + i] = ref[(lmato::F_LAM + i) * N1 + k] * (i < 4 ? ri : 1.0);
+    x[X_ZLA] = ref[lmato::F_ZLA * N1 + k]; x[X_ZUA] = ref[lmato::F_ZUA * N1 + k];
+    x[X_ZLU] = ref[lmato::F_ZLU * N1 + k]; x[X_ZUU] = ref[lmato::F_ZUU * N1 + k];
+    if (MOVE) {
+      const double u = x[X_U], up = k > 1 ? ref[lmato::F_U * N1 + k - 1] : 0.0;
+      const double v = u - up;
+      const double tt = (mu + sqrt(mu * mu + w * w * v * v)) / w;
+      const double pp = 0.5 * (tt + v), pn = 0.5 * (tt - v);
+      x[X_PP] = pp; x[X_PN] = pn; x[X_ZPP] = mu / pp; x[X_ZPN] = mu / pn;
+      x[X_LAM + 6] = w - mu / pp;
+    } else {
+      x[X_PP] = 1.0; x[X_PN] = 1.0; x[X_ZPP] = 0.0; x[X_ZPN] = 0.0;
+      x[X_LAM + 6] = 0.0;
+    }
+    x[22] = 0.0; x[23] = 0.0;
+    stv<XR>(W.X(0, k), x);
+#pragma unroll
+    for (int i = 0; i < DR; ++i) zero[i] = 0.0;
+    stv<DR>(W.D(k), zero);
+  }
+  s.tf = dmin(sc[REF_TF], 0.99 * P.tf_ub);
+  s.zLt = sc[REF_ZLT]; s.zUt = sc[REF_ZUT];
+  s.sg1 = sc[REF_SG1]; s.sg2 = sc[REF_SG2]; s.zs1 = sc[REF_ZS1]; s.zs2 = sc[REF_ZS2]; s.nu3 = sc[REF_NU3];
+  *mu_out = mu;
+  Grp<G>::sync(W.mask);
+  return true;
+}
+
+}  // namespace coop
+
+// Sweeps policy of the cooperative formulation for the IPM driver (ipm_iterate_t).
+//   G  lanes carry the sequential phases (cost-to-go distributed by rows: 8/G rows per lane),
+//   GP lanes (a multiple of G, at most a warp) carry the stage-parallel phases of the same problem.
+template <int G, int GP, bool MOVE>
+struct SweepsCoop {
+  enum : int { LANES_PER_PROBLEM = GP };
+  LM_HD static int n_eq(int N) { return (MOVE ? 7 : 6) * N + 3; }
+  LM_HD static int n_bd(int N) { return (MOVE ? 6 : 4) * N + 4; }
+  LM_HD static bool backward(const Params& P, const Mesh& M, const Options& O, const coop::Cws& W, int src, const Scal& c0,
+                             double mu, double dw, bool ls, double* dtf) {
+    // the least-squares multiplier estimate factorises its own model (Hessian := I) of the start point
+    if (ls) coop::coop_build<GP, MOVE>(P, M, O, W, src, c0.tf, true);
+    return coop::coop_backward<G, GP, MOVE>(P, M, O, W, src, c0, mu, dw, ls, dtf);
+  }
+  LM_HD static void forward(const Params& P, const Mesh& M, const Options& O, const coop::Cws& W, int src, const Scal& c0,
+                            double mu, double tau, double dtf, bool ls, TermStep& ts, StepInfo& si) {
+    coop::coop_forward<G, GP, MOVE>(P, M, O, W, src, c0, mu, tau, dtf, ls, ts, si);
+  }
+  LM_HD static void eval(const Params& P, const Mesh& M, const Options& O, const coop::Cws& W, int src, int dst,
+                         const Scal& c0, const TermStep& ts, double mu, double /*dw*/, double alpha, double alpha_z,
+                         double alpha_lam, int /*mode*/, Scal& t, double* pimax) {
+    // (the new multipliers are always read: the adjoint recursion ran at the end of forward())
+    coop::coop_eval<GP, MOVE>(P, M, O, W, src, dst, c0, ts, mu, alpha, alpha_z, alpha_lam, t);
+    if (pimax) *pimax = W.pimax;
+  }
+  LM_HD static void guess(const Params& P, const Mesh& M, const Options& O, const coop::Cws& W, Scal& s) {
+    coop::coop_init_guess<GP, MOVE>(P, M, O, W, s);
+  }
+  LM_HD static void guess_from(const Params& P, const Mesh& M, const Options& O, const coop::Cws& W, const GuessSrc& Gs, Scal& s) {
+    coop::coop_init_from_guess<GP, MOVE>(P, M, O, W, Gs, s);
+  }
+  LM_HD static void store_ref(const Params& P, const Mesh& M, const coop::Cws& W, int src, const Scal& c, double mu, bool ok,
+                              double* ref) { coop::coop_store_ref<GP>(P, M, W, src, c, mu, ok, ref); }
+  LM_HD static bool load_ref(const Params& P, const Mesh& M, const Options& O, const coop::Cws& W, const double* ref,
+                             Scal& s, double* mu) {
+    return coop::coop_load_ref<GP, MOVE>(P, M, O, W, ref, s, mu);
+  }
+  LM_HD static void remerit(const Mesh&, const Options&, const coop::Cws&, int, double, Scal&) {}
+};
+
+}  // namespace lmato

@@ -1208,6 +1208,7 @@ enum : int { PH_LSQ = 0, PH_NEWTON = 1 };
 
 struct IpmState {
   bool warm;        // start point carries its own multipliers (skip the least-squares estimate)
+  bool from_guess;  // start point supplied by the caller (lmato_set_initial_guess)
   Scal cur;
   Ctl ctl;
   TermStep ts;
@@ -1233,6 +1234,7 @@ LM_HD void ipm_begin(const Options& O, IpmState& S) {
   S.polish_left = -1;
   S.polishing = false;
   S.warm = false;
+  S.from_guess = false;
 }
 
 // Sweeps policy of the 7-state formulation (dcost = 0); ascent_ipm_dc.cuh provides the 8-state one.
@@ -1266,8 +1268,8 @@ struct Sweeps7 {
   LM_HD static void remerit(const Mesh&, const Options&, const Ws&, int, double, Scal&) {}
 };
 
-template <class SW>
-LM_HD bool ipm_iterate_t(const Params& P, const Mesh& M, const Options& O, const Ws& W, IpmState& S) {
+template <class SW, class WS>
+LM_HD bool ipm_iterate_t(const Params& P, const Mesh& M, const Options& O, const WS& W, IpmState& S) {
   Ctl& ctl = S.ctl;
   Scal& cur = S.cur;
   const int N = M.N;
