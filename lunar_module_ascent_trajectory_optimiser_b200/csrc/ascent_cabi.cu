@@ -404,8 +404,9 @@ __device__ __noinline__ void coop_write_results(const KArgs& a, const Params& P,
 //   GP = 8 : four problems per warp, for batches that can fill the GPU that way;
 //   GP = 32: the whole warp works on one problem (the stage-parallel phases are four times shorter), for
 //            the latency regime: up to a few problems per SM.
-template <int G, int GP, bool MOVE>
-__global__ void __launch_bounds__(kCoopBlock, (GP == 32 ? 1 : kCoopBlocksPerSM)) ascent_coop_kernel(KArgs a) {
+//   BPS = CTAs per SM: 1 leaves 255 registers per thread (no spills), 2 halves them for twice the problems in flight.
+template <int G, int GP, bool MOVE, int BPS>
+__global__ void __launch_bounds__(kCoopBlock, BPS) ascent_coop_kernel(KArgs a) {
   using SW = SweepsCoop<G, GP, MOVE>;
   constexpr int PPW = 32 / GP;                 // problems per warp
   constexpr int GPB = kCoopBlock / GP;         // groups per block
@@ -487,6 +488,18 @@ __global__ void __launch_bounds__(kCoopBlock, (GP == 32 ? 1 : kCoopBlocksPerSM))
       pending = true;
     }
   }
+}
+
+template <int GP, int BPS>
+static void coop_launch(bool move, long grid, cudaStream_t st, const KArgs& a) {
+  if (move) ascent_coop_kernel<kCoopG, GP, true, BPS><<<(int)grid, kCoopBlock, coop_smem(GP), st>>>(a);
+  else ascent_coop_kernel<kCoopG, GP, false, BPS><<<(int)grid, kCoopBlock, coop_smem(GP), st>>>(a);
+}
+template <int GP, int BPS>
+static cudaError_t coop_optin() {
+  cudaError_t e = cudaFuncSetAttribute(ascent_coop_kernel<kCoopG, GP, true, BPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coop_smem(GP));
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(ascent_coop_kernel<kCoopG, GP, false, BPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coop_smem(GP));
 }
 
 // FP64 FMA peak: 8 independent chains per thread, no memory traffic.
@@ -585,10 +598,10 @@ static lmato_status_t create_device_state(lmato_handle* H, const std::vector<dou
   // the staging tiles need the opt-in shared-memory size (158 KB dynamic + 42 KB static per CTA)
   CUDA_TRY(cudaFuncSetAttribute(ascent_ipm_kernel<Sweeps7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmem));
   CUDA_TRY(cudaFuncSetAttribute(ascent_ipm_kernel<Sweeps8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmem));
-  CUDA_TRY(cudaFuncSetAttribute(ascent_coop_kernel<kCoopG, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coop_smem(8)));
-  CUDA_TRY(cudaFuncSetAttribute(ascent_coop_kernel<kCoopG, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coop_smem(8)));
-  CUDA_TRY(cudaFuncSetAttribute(ascent_coop_kernel<kCoopG, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coop_smem(32)));
-  CUDA_TRY(cudaFuncSetAttribute(ascent_coop_kernel<kCoopG, 32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coop_smem(32)));
+  CUDA_TRY((coop_optin<8, 1>()));
+  CUDA_TRY((coop_optin<8, 2>()));
+  CUDA_TRY((coop_optin<32, 1>()));
+  CUDA_TRY((coop_optin<32, 2>()));
   CUDA_TRY(cudaMalloc(&H->d_h, sizeof(double) * nt));
   CUDA_TRY(cudaMalloc(&H->d_tau, sizeof(double) * nt));
   CUDA_TRY(cudaMemcpy(H->d_h, h.data(), sizeof(double) * nt, cudaMemcpyHostToDevice));
@@ -704,7 +717,7 @@ static bool dcost_active(const lmato_handle* h) { return h->opt.dcost > 0.0 && h
 // the GPU and streams the least HBM traffic per problem; eight lanes per problem fill it with an eighth of that
 // and shorten the critical path of every problem, at ~2.5x the traffic.  Measured cross-over on B200 at nt = 200:
 // between 16 384 and 32 768 problems (profiles/README.md).
-constexpr int64_t kCoopMaxBatch = 24576;
+constexpr int64_t kCoopMaxBatch = 6144;
 static bool use_coop(const lmato_handle* h, int64_t B) {
   if (h->opt.kernel == LMATO_KERNEL_COOP) return true;
   if (h->opt.kernel == LMATO_KERNEL_THREAD) return false;
@@ -724,10 +737,14 @@ static int coop_gp_for(const lmato_handle* h, int64_t B) {
   if (h->opt.coop_lanes == 8 || h->opt.coop_lanes == 32) return h->opt.coop_lanes;
   return B <= (int64_t)h->sm_count * 8 ? 32 : 8;
 }
+// CTAs per SM: one (255 registers per thread) while one CTA per SM holds the whole batch, else two
+static int coop_bps_for(const lmato_handle* h, int64_t B, int gp) {
+  return B <= (int64_t)h->sm_count * (kCoopBlock / gp) ? 1 : kCoopBlocksPerSM;
+}
 // CTAs of 256 threads = 256/GP groups; a warp's chunk is 32/GP problems
 static long coop_grid_for(const lmato_handle* h, int64_t B, int gp) {
   const long chunks = (B + (32 / gp) - 1) / (32 / gp);
-  const long cap = (long)h->sm_count * (gp == 32 ? 1 : kCoopBlocksPerSM);
+  const long cap = (long)h->sm_count * coop_bps_for(h, B, gp);
   return chunks < cap ? (chunks > 0 ? chunks : 1) : cap;
 }
 static size_t coop_ws_bytes(const lmato_handle* h, long grid, int gp) {
@@ -826,20 +843,16 @@ lmato_status_t lmato_solve_batch(lmato_handle* h, const double* params, int64_t 
     r.ref = h->d_ref; r.ref_mode = 1;
     r.O.tol = 10.0 * h->opt.mu_ref; r.O.mu_min_factor = 0.1; r.O.n_polish = 0;
     r.O.w_dcost = 0.0;
-    ascent_coop_kernel<kCoopG, 32, false><<<1, kCoopBlock, coop_smem(32), st>>>(r);
+    coop_launch<32, 1>(false, 1, st, r);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemsetAsync(h->d_counter, 0, sizeof(int), st));
     a.ref = h->d_ref; a.ref_mode = 2;
     h->launches += 2;
   }
   if (coopk) {
-    if (gp == 32) {
-      if (use_dc) ascent_coop_kernel<kCoopG, 32, true><<<(int)cgrid, kCoopBlock, coop_smem(32), st>>>(a);
-      else ascent_coop_kernel<kCoopG, 32, false><<<(int)cgrid, kCoopBlock, coop_smem(32), st>>>(a);
-    } else {
-      if (use_dc) ascent_coop_kernel<kCoopG, 8, true><<<(int)cgrid, kCoopBlock, coop_smem(8), st>>>(a);
-      else ascent_coop_kernel<kCoopG, 8, false><<<(int)cgrid, kCoopBlock, coop_smem(8), st>>>(a);
-    }
+    const int bps = coop_bps_for(h, B, gp);
+    if (gp == 32) { if (bps == 1) coop_launch<32, 1>(use_dc, cgrid, st, a); else coop_launch<32, 2>(use_dc, cgrid, st, a); }
+    else          { if (bps == 1) coop_launch<8, 1>(use_dc, cgrid, st, a); else coop_launch<8, 2>(use_dc, cgrid, st, a); }
   } else {
     const int grid = (int)(slots / kBlock);
     if (use_dc) ascent_ipm_kernel<Sweeps8><<<grid, kBlock, kTileSmem, st>>>(a);

@@ -198,6 +198,14 @@ LM_HD void rg_copy(RingRef r, int off, const double* src, int g) {
     }
   }
 }
+// hint: bring the 128-byte lines of a record that a later stage of a stage-parallel loop will read into L2/L1
+template <int NDBL>
+LM_HD void prefetch_rec(const double* p) {
+#if defined(__CUDA_ARCH__) && defined(LMATO_COOP_PREFETCH)
+#pragma unroll
+  for (int i = 0; i < NDBL; i += 16) asm volatile("prefetch.global.L1 [%0];" ::"l"(p + i));
+#endif
+}
 LM_HD void rg_commit() {
 #if defined(__CUDA_ARCH__)
   asm volatile("cp.async.commit_group;" ::: "memory");
@@ -364,6 +372,7 @@ LM_SWEEP bool coop_backward_seq(const Params& P, const Mesh& M, const Options& O
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const int i = g * R + r;
+      // (selects, not branches: eight different branch bodies would serialise the lanes of the group)
       const bool e0 = (i == 0), e2 = (i == 2), e4 = (i == 4), e7 = (i == 7);
       Pr[r][0] += e0 ? q[Q_00] + dw : e2 ? q[Q_02] : e4 ? q[Q_04] : e7 ? q[Q_T0 + 0] : 0.0;
       Pr[r][2] += e0 ? q[Q_02] : e2 ? q[Q_22] + dw : e4 ? q[Q_24] : e7 ? q[Q_T0 + 2] : 0.0;
@@ -577,6 +586,7 @@ LM_SWEEP void coop_forward(const Params& P, const Mesh& M, const Options& O, con
     terminal_qp(P, O, c0, zn, mu, dw, ls, tq);
   }
   for (int k = 1 + g; k <= N; k += GP) {
+    if (k + GP <= N) { prefetch_rec<XR>(W.X(src, k + GP)); prefetch_rec<8>(W.D(k + GP)); prefetch_rec<QR>(W.Mo(src, k + GP) + M_Q); }
     double x[XR], d[8], q[QR];
     ldv<XR>(W.X(src, k), x);
     ldv<8>(W.D(k), d);
@@ -751,6 +761,7 @@ LM_SWEEP void coop_eval(const Params& P, const Mesh& M, const Options& O, const 
   double theta = 0, prim = 0, dual = 0, sumlog = 0, cmin = 1e300, cmax = 0, slam = 0, sz = 0, gtf = 0, movecost = 0;
   int bad = 0;
   for (int k = 1 + g; k <= N; k += GP) {
+    if (k + GP <= N) { prefetch_rec<XR>(W.X(src, k + GP)); prefetch_rec<DR>(W.D(k + GP)); }
     double xo[XR], d[DR], xm[8], dm[8];
     ldv<XR>(W.X(src, k), xo);
     ldv<DR>(W.D(k), d);

@@ -41,9 +41,12 @@ def run(B, nt=200, model="elliptical", dcost=1e-5, seed=11, reps=2, traj=True, l
 
 
 if __name__ == "__main__":
-    run(1); run(1, lanes=8); run(1, dcost=0.0); run(1, model="circular"); run(1, nt=40)
-    run(37); run(148); run(700); run(700, lanes=8); run(1024); run(1024, lanes=8); run(1184); run(4096)
+    if len(sys.argv) > 1 and sys.argv[1] == "quick":
+        run(1); run(700); run(1184); run(2048); run(4096); run(512, nt=2001, traj=False); run(4096, nt=2001, traj=False, reps=1)
+        sys.exit(0)
+    run(1); run(1, dcost=0.0); run(1, model="circular"); run(1, nt=40)
+    run(37); run(700); run(1184); run(2048); run(4096); run(4736, traj=False)
     if len(sys.argv) > 1:
-        for B in (8192, 16384):
+        for B in (6144, 8192, 16384):
             run(B, traj=False)
-        run(64, nt=2001); run(512, nt=2001, traj=False); run(512, nt=2001, traj=False, lanes=8); run(4096, nt=2001, traj=False, reps=1)
+        run(64, nt=2001); run(512, nt=2001, traj=False); run(4096, nt=2001, traj=False, reps=1)
