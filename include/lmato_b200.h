@@ -161,6 +161,23 @@ lmato_status_t lmato_solve_batch_host(lmato_handle* h, const double* params, int
                                       double* out_traj, double* out_tf, double* out_final_mass,
                                       int32_t* out_status, int32_t* out_iters, double* out_kkt);
 
+/* Device list: one host process, several GPUs.  The batch is index-partitioned (problem i ->
+ * devices[floor(i*ndev/B)], contiguous ranges whose sizes differ by at most one), every device solves its
+ * shard concurrently with its own handle, and each writes its slice of the caller's HOST result arrays
+ * (same shapes as lmato_solve_batch_host; pinned host memory makes the copies asynchronous).  The problems
+ * are independent and the results land on the host, so no collective is involved; the one-process-per-GPU
+ * path (torchrun) with its single NCCL allgather lives in the Python host layer (`sharded_solve`).
+ * A device may be named more than once (each entry gets its own handle and workspace). */
+typedef struct lmato_multi lmato_multi;
+lmato_status_t lmato_multi_create(lmato_multi** out, const int32_t* devices, int32_t ndev, int32_t nt,
+                                  const double* time, int32_t nodes, int32_t model);
+lmato_status_t lmato_multi_destroy(lmato_multi* m);
+lmato_status_t lmato_multi_set_options(lmato_multi* m, const lmato_options* o);
+lmato_status_t lmato_multi_device_count(lmato_multi* m, int32_t* n);
+lmato_status_t lmato_multi_solve_host(lmato_multi* m, const double* params, int64_t B,
+                                      double* out_traj, double* out_tf, double* out_final_mass,
+                                      int32_t* out_status, int32_t* out_iters, double* out_kkt);
+
 /* Start point for the following solves on this handle (accept a previous solution as the guess;
  * the reference's counterpart is the `value=` argument of m.Var / m.MV / m.FV, LO:39, 83-96):
  *   guess_traj [LMATO_NVAR][nt][B]  in the layout of out_traj (the rows of ydoubledot, xdoubledot and mass are

@@ -96,10 +96,16 @@ def lib() -> C.CDLL:
     L.lmato_coast_orbit.argtypes = [vp, vp, i64, C.c_double, C.c_double, i64, vp, vp]
     L.lmato_set_sensitivity_output.argtypes = [vp, vp]
     L.lmato_set_initial_guess.argtypes = [vp, vp, vp]
+    L.lmato_multi_create.argtypes = [C.POINTER(vp), C.POINTER(i32), i32, i32, vp, i32, i32]
+    L.lmato_multi_destroy.argtypes = [vp]
+    L.lmato_multi_set_options.argtypes = [vp, C.POINTER(LmatoOptions)]
+    L.lmato_multi_device_count.argtypes = [vp, C.POINTER(i32)]
+    L.lmato_multi_solve_host.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, vp]
     for name in ("lmato_create", "lmato_destroy", "lmato_set_options", "lmato_solve_batch",
                  "lmato_solve_batch_host", "lmato_workspace_bytes", "lmato_kernel_launches",
                  "lmato_last_kernel_ms", "lmato_measure_fp64_peak", "lmato_selftest_math", "lmato_coast_orbit",
-                 "lmato_set_sensitivity_output", "lmato_set_initial_guess"):
+                 "lmato_set_sensitivity_output", "lmato_set_initial_guess", "lmato_multi_create", "lmato_multi_destroy",
+                 "lmato_multi_set_options", "lmato_multi_device_count", "lmato_multi_solve_host"):
         getattr(L, name).restype = C.c_int
     _lib = L
     return L
@@ -109,7 +115,8 @@ EXPORTED_SYMBOLS = ["lmato_default_options", "lmato_create", "lmato_destroy", "l
                     "lmato_solve_batch", "lmato_solve_batch_host", "lmato_workspace_bytes",
                     "lmato_kernel_launches", "lmato_last_kernel_ms", "lmato_measure_fp64_peak",
                     "lmato_selftest_math", "lmato_coast_orbit", "lmato_set_sensitivity_output", "lmato_set_initial_guess", "lmato_last_error",
-                    "lmato_version"]
+                    "lmato_version", "lmato_multi_create", "lmato_multi_destroy", "lmato_multi_set_options",
+                    "lmato_multi_device_count", "lmato_multi_solve_host"]
 
 
 def check(rc: int, what: str) -> None:

@@ -157,6 +157,9 @@ class AscentBatchSolution:
     # optional: d tf / d parameter, name -> [B] (scaled tf per unit of the raw parameter), for
     # Ft, M0, M_dot, angle_doubledot_max; only with ``sensitivities=True``
     dtf_dparam: Optional[Dict[str, torch.Tensor]] = None
+    # which reference variable `control` is: the MV `angledoubledot` (LO:96) or, for the circular model, the MV
+    # `angle` (PDF p.27 src 69-73)
+    control_name: str = "angledoubledot"
 
     @property
     def converged(self) -> torch.Tensor:
@@ -177,6 +180,7 @@ class AscentSolution:
     iterations: int
     kkt_error: float
     time: torch.Tensor
+    control_name: str = "angledoubledot"
 
 
 class AscentSolver:
@@ -206,13 +210,7 @@ class AscentSolver:
         self.set_options(self.options)
 
     def set_options(self, o: SolverOptions) -> None:
-        co = _cabi.LmatoOptions(tol=o.tol, mu_init=o.mu_init, obj_scale=o.obj_scale, tf_guess=o.tf_guess,
-                                delta_c=o.delta_c, mu_min_factor=o.mu_min_factor, max_iter=int(o.max_iter),
-                                max_ls=int(o.max_ls), n_polish=int(o.n_polish),
-                                warm_start=int(o.warm_start), mu_ref=o.mu_ref,
-                                dcost=float(1e-5 if o.dcost is None else o.dcost),
-                                kappa_eps=float(o.kappa_eps), objective_nodes=int(o.objective_nodes),
-                                kernel=_cabi.KERNEL_IDS[o.kernel], coop_lanes=int(o.coop_lanes), otol=float(o.otol), rtol=float(o.rtol))
+        co = _c_options(o)
         _cabi.check(_cabi.lib().lmato_set_options(self._h, C.byref(co)), "lmato_set_options")
         self.options = o
 
@@ -360,6 +358,78 @@ class AscentSolver:
         return package_solution(raw, rows, self.time, self.model)
 
 
+class AscentMultiSolver:
+    """Owns one ``lmato_multi`` handle of the C ABI: a device list driven by ONE host process
+    (``lmato_multi_create`` / ``lmato_multi_solve_host``).  Host tensors in, pinned host tensors out."""
+
+    def __init__(self, devices: Sequence[int], mesh: Optional[Mesh] = None, options: Optional[SolverOptions] = None,
+                 model: str = "elliptical"):
+        self.mesh = mesh or Mesh()
+        self.options = options or SolverOptions()
+        L = _cabi.lib()
+        if not torch.cuda.is_available():
+            raise _cabi.LmatoError("no CUDA device: the solver has no CPU fallback")
+        self.devices = [int(d) for d in devices]
+        if not self.devices:
+            raise ValueError("`devices` is empty")
+        self.time = self.mesh.grid()
+        self.nt = int(self.time.shape[0])
+        self.model = model
+        model_id = {"elliptical": 0, "circular": 1}.get(model)
+        if model_id is None:
+            raise ValueError(f"unknown model {model!r}")
+        self._h = C.c_void_p()
+        tbuf = (C.c_double * self.nt)(*self.time.tolist())
+        dbuf = (C.c_int32 * len(self.devices))(*self.devices)
+        _cabi.check(L.lmato_multi_create(C.byref(self._h), dbuf, len(self.devices), self.nt, C.cast(tbuf, C.c_void_p),
+                                         int(self.mesh.nodes), model_id), "lmato_multi_create")
+        self.set_options(self.options)
+
+    def set_options(self, o: SolverOptions) -> None:
+        _cabi.check(_cabi.lib().lmato_multi_set_options(self._h, C.byref(_c_options(o))), "lmato_multi_set_options")
+        self.options = o
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _cabi.lib().lmato_multi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def solve_rows(self, rows: torch.Tensor, trajectories: bool = True) -> Dict[str, torch.Tensor]:
+        if rows.is_cuda or rows.dtype != torch.float64 or rows.dim() != 2 or rows.shape[0] != _cabi.NPARAM:
+            raise ValueError("rows must be a CPU float64 tensor [NPARAM, B]")
+        rows = rows.contiguous()
+        B = int(rows.shape[1])
+        kw = dict(pin_memory=True)
+        out = {"traj": torch.empty((_cabi.NVAR, self.nt, B), dtype=torch.float64, **kw) if trajectories else None,
+               "tf": torch.empty(B, dtype=torch.float64, **kw), "final_mass": torch.empty(B, dtype=torch.float64, **kw),
+               "status": torch.empty(B, dtype=torch.int32, **kw), "iterations": torch.empty(B, dtype=torch.int32, **kw),
+               "kkt": torch.empty(B, dtype=torch.float64, **kw)}
+        if B == 0:
+            return out
+        ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p()
+        _cabi.check(_cabi.lib().lmato_multi_solve_host(self._h, ptr(rows), B, ptr(out["traj"]), ptr(out["tf"]),
+                                                       ptr(out["final_mass"]), ptr(out["status"]), ptr(out["iterations"]),
+                                                       ptr(out["kkt"])), "lmato_multi_solve_host")
+        return out
+
+
+def _c_options(o: SolverOptions) -> "_cabi.LmatoOptions":
+    return _cabi.LmatoOptions(tol=o.tol, mu_init=o.mu_init, obj_scale=o.obj_scale, tf_guess=o.tf_guess,
+                              delta_c=o.delta_c, mu_min_factor=o.mu_min_factor, max_iter=int(o.max_iter),
+                              max_ls=int(o.max_ls), n_polish=int(o.n_polish),
+                              warm_start=int(o.warm_start), mu_ref=o.mu_ref,
+                              dcost=float(1e-5 if o.dcost is None else o.dcost),
+                              kappa_eps=float(o.kappa_eps), objective_nodes=int(o.objective_nodes),
+                              kernel=_cabi.KERNEL_IDS[o.kernel], coop_lanes=int(o.coop_lanes), otol=float(o.otol),
+                              rtol=float(o.rtol))
+
+
 def package_solution(raw: Dict[str, torch.Tensor], rows: torch.Tensor, time: torch.Tensor,
                      model: str = "elliptical") -> AscentBatchSolution:
     traj = raw["traj"]
@@ -380,7 +450,8 @@ def package_solution(raw: Dict[str, torch.Tensor], rows: torch.Tensor, time: tor
     return AscentBatchSolution(tf=raw["tf"], tf_seconds=raw["tf"] * T.to(raw["tf"].device), states=states,
                                control=control, final_mass=raw["final_mass"], status=raw["status"],
                                iterations=raw["iterations"], kkt_error=raw["kkt"], time=time,
-                               dtf_dparam=None if dtf is None else {n: dtf[i] for i, n in enumerate(_cabi.SENS_ROWS)})
+                               dtf_dparam=None if dtf is None else {n: dtf[i] for i, n in enumerate(_cabi.SENS_ROWS)},
+                               control_name="angle" if model == "circular" else "angledoubledot")
 
 
 # ---------------------------------------------------------------------------------------
@@ -394,11 +465,13 @@ def shard_bounds(B: int, world: int, rank: int):
 
 
 def sharded_solve(rows: torch.Tensor, solve_fn: Callable[[torch.Tensor], Dict[str, torch.Tensor]],
-                  group=None, gather: bool = True) -> Dict[str, torch.Tensor]:
+                  group=None, gather: bool = True, gather_traj: bool = True) -> Dict[str, torch.Tensor]:
     """Every rank holds the full ``rows`` block; rank r solves its contiguous shard with
     ``solve_fn`` and a single ``all_gather`` (NCCL over NVLink on GPUs, gloo in the CPU tests)
     reassembles the per-problem results on every rank.  No per-iteration collectives: the
-    problems are independent."""
+    problems are independent.  ``gather_traj=False`` gathers the per-problem scalars only (tf, final mass,
+    status, iterations, KKT error: 40 B per problem) and returns the rank's own trajectory shard under
+    ``"traj"`` together with its index range ``"shard"`` (the trajectories are optional)."""
     import torch.distributed as dist
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
@@ -408,7 +481,7 @@ def sharded_solve(rows: torch.Tensor, solve_fn: Callable[[torch.Tensor], Dict[st
     if not gather:
         return local
     per = (B + world - 1) // world
-    keys = [k for k, v in local.items() if v is not None]
+    keys = [k for k, v in local.items() if v is not None and (gather_traj or k != "traj")]
     # pack every result into one float64 buffer [per, width] so that one collective suffices
     cols = []
     for k in keys:
@@ -440,6 +513,9 @@ def sharded_solve(rows: torch.Tensor, solve_fn: Callable[[torch.Tensor], Dict[st
             w = 1
             out[k] = full[:, c].to(v.dtype)
         c += w
+    if not gather_traj:
+        out["traj"] = local.get("traj")
+        out["shard"] = (lo, hi)
     return out
 
 
@@ -570,6 +646,16 @@ def optimise_batch(params: AscentParams, mesh: Optional[Mesh] = None,
         if options.warm_start == 1 and nB >= 1024:
             # the shards belong to one batch: they keep the batch warm start even if a shard alone is small
             options = dataclasses.replace(options, warm_start=2)
+        if not on_dev and not sensitivities:
+            # host tensors: the C ABI's own device-list entry (lmato_multi_solve_host)
+            key = ("multi", tuple(int(d) for d in devices), tuple(mesh.grid().tolist()), mesh.nodes, params.model)
+            ms = _solver_cache.get(key)
+            if ms is None:
+                ms = _solver_cache[key] = AscentMultiSolver(devices, mesh, options, params.model)
+            else:
+                ms.set_options(options)
+            rows = params.rows(batch).pin_memory()
+            return package_solution(ms.solve_rows(rows, trajectories), rows, ms.time, params.model)
         solvers = [_get_solver(mesh, options, d, params.model) for d in devices]
         rows = params.rows(batch, device=solvers[0].device if on_dev else "cpu")
         if not on_dev:
@@ -619,4 +705,5 @@ def optimise(params: Optional[AscentParams] = None, mesh: Optional[Mesh] = None,
     return AscentSolution(tf=float(sol.tf[0]), tf_seconds=float(sol.tf_seconds[0]),
                           states={k: v[0].clone() for k, v in sol.states.items()},
                           control=sol.control[0].clone(), final_mass=float(sol.final_mass[0]), status=st,
-                          iterations=int(sol.iterations[0]), kkt_error=float(sol.kkt_error[0]), time=sol.time)
+                          iterations=int(sol.iterations[0]), kkt_error=float(sol.kkt_error[0]), time=sol.time,
+                          control_name=sol.control_name)

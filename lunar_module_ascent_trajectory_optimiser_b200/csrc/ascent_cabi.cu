@@ -1040,4 +1040,144 @@ lmato_status_t lmato_measure_fp64_peak(lmato_handle* h, double* gflops) {
   return LMATO_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------
+// device list: one host process, several GPUs.  Problem i goes to device floor(i*G/B)
+// (contiguous index ranges); every device solves its shard with its own handle, concurrently (all launches
+// are asynchronous), and writes its slice of the caller's HOST result arrays.  The problems are independent
+// and the results land on the host, so there is no collective to own here; the one-process-per-GPU path with
+// its single NCCL allgather is `sharded_solve` in the Python host layer.
+// ---------------------------------------------------------------------------------------
+struct lmato_multi {
+  std::vector<lmato_handle*> h;
+  std::vector<cudaStream_t> st;
+  std::vector<double*> d_params;   // per device [NPARAM][Bshard]
+  std::vector<double*> d_out;      // per device: traj | tf | fmass | kkt | status | iters
+  std::vector<size_t> params_bytes, out_bytes;
+};
+
+lmato_status_t lmato_multi_destroy(lmato_multi* m) {
+  if (!m) return LMATO_OK;
+  for (size_t g = 0; g < m->h.size(); ++g) {
+    if (m->h[g]) cudaSetDevice(m->h[g]->device);
+    if (g < m->st.size() && m->st[g]) cudaStreamDestroy(m->st[g]);
+    if (g < m->d_params.size()) cudaFree(m->d_params[g]);
+    if (g < m->d_out.size()) cudaFree(m->d_out[g]);
+    lmato_destroy(m->h[g]);
+  }
+  delete m;
+  return LMATO_OK;
+}
+
+lmato_status_t lmato_multi_create(lmato_multi** out, const int32_t* devices, int32_t ndev, int32_t nt,
+                                  const double* time, int32_t nodes, int32_t model) {
+  if (!out) { set_err("lmato_multi_create: out is NULL"); return LMATO_ERR_INVALID; }
+  *out = nullptr;
+  if (!devices || ndev < 1) { set_err("lmato_multi_create: empty device list"); return LMATO_ERR_INVALID; }
+  lmato_multi* m = new (std::nothrow) lmato_multi();
+  if (!m) { set_err("lmato_multi_create: out of host memory"); return LMATO_ERR_INVALID; }
+  m->h.assign(ndev, nullptr); m->st.assign(ndev, nullptr);
+  m->d_params.assign(ndev, nullptr); m->d_out.assign(ndev, nullptr);
+  m->params_bytes.assign(ndev, 0); m->out_bytes.assign(ndev, 0);
+  for (int g = 0; g < ndev; ++g) {
+    lmato_status_t rc = lmato_create(&m->h[g], devices[g], nt, time, nodes, model);
+    if (rc == LMATO_OK && (cudaSetDevice(devices[g]) != cudaSuccess ||
+                           cudaStreamCreateWithFlags(&m->st[g], cudaStreamNonBlocking) != cudaSuccess)) {
+      set_err("lmato_multi_create: could not create a stream on device %s", g == 0 ? "0" : "n");
+      rc = LMATO_ERR_CUDA;
+    }
+    if (rc != LMATO_OK) { lmato_multi_destroy(m); return rc; }
+  }
+  *out = m;
+  return LMATO_OK;
+}
+
+lmato_status_t lmato_multi_set_options(lmato_multi* m, const lmato_options* o) {
+  if (!m || !o) { set_err("lmato_multi_set_options: NULL argument"); return LMATO_ERR_INVALID; }
+  for (lmato_handle* h : m->h) {
+    const lmato_status_t rc = lmato_set_options(h, o);
+    if (rc != LMATO_OK) return rc;
+  }
+  return LMATO_OK;
+}
+
+lmato_status_t lmato_multi_device_count(lmato_multi* m, int32_t* n) {
+  if (!m || !n) { set_err("lmato_multi_device_count: NULL argument"); return LMATO_ERR_INVALID; }
+  *n = (int32_t)m->h.size();
+  return LMATO_OK;
+}
+
+lmato_status_t lmato_multi_solve_host(lmato_multi* m, const double* params, int64_t B,
+                                      double* out_traj, double* out_tf, double* out_final_mass,
+                                      int32_t* out_status, int32_t* out_iters, double* out_kkt) {
+  if (!m) { set_err("lmato_multi_solve_host: NULL handle"); return LMATO_ERR_INVALID; }
+  if (B < 0) { set_err("lmato_multi_solve_host: negative batch"); return LMATO_ERR_INVALID; }
+  if (B == 0) return LMATO_OK;
+  if (!params || !out_tf || !out_final_mass || !out_status || !out_iters) {
+    set_err("lmato_multi_solve_host: NULL buffer");
+    return LMATO_ERR_INVALID;
+  }
+  const int G = (int)m->h.size();
+  const int nt = m->h[0]->nt;
+  struct Shard { int64_t lo, n; double *traj, *tf, *fm, *kkt; int32_t *st, *it; };
+  std::vector<Shard> sh(G);
+  // phase 1: every device gets its parameter columns and its launch (nothing here waits for a device)
+  for (int g = 0; g < G; ++g) {
+    lmato_handle* h = m->h[g];
+    Shard& s = sh[g];
+    s.lo = (B * g) / G;
+    s.n = (B * (g + 1)) / G - s.lo;
+    if (s.n == 0) continue;
+    CUDA_TRY(cudaSetDevice(h->device));
+    // the shards of one batch keep the batch warm start even when a shard alone is small
+    const int32_t ws_saved = h->opt.warm_start;
+    if (ws_saved == 1 && B >= kWarmStartMinBatch) h->opt.warm_start = 2;
+    const size_t pbytes = sizeof(double) * LMATO_NPARAM * (size_t)s.n;
+    if (pbytes > m->params_bytes[g]) {
+      CUDA_TRY(cudaStreamSynchronize(m->st[g]));
+      cudaFree(m->d_params[g]); m->d_params[g] = nullptr; m->params_bytes[g] = 0;
+      CUDA_TRY(cudaMalloc(&m->d_params[g], pbytes));
+      m->params_bytes[g] = pbytes;
+    }
+    const size_t traj_n = out_traj ? (size_t)LMATO_NVAR * nt * (size_t)s.n : 0;
+    const size_t obytes = sizeof(double) * (traj_n + 3 * (size_t)s.n) + sizeof(int32_t) * 2 * (size_t)s.n;
+    if (obytes > m->out_bytes[g]) {
+      CUDA_TRY(cudaStreamSynchronize(m->st[g]));
+      cudaFree(m->d_out[g]); m->d_out[g] = nullptr; m->out_bytes[g] = 0;
+      CUDA_TRY(cudaMalloc(&m->d_out[g], obytes));
+      m->out_bytes[g] = obytes;
+    }
+    s.traj = out_traj ? m->d_out[g] : nullptr;
+    s.tf = m->d_out[g] + traj_n; s.fm = s.tf + s.n; s.kkt = s.fm + s.n;
+    s.st = (int32_t*)(s.kkt + s.n); s.it = s.st + s.n;
+    // columns [lo, lo+n) of the row-major [NPARAM][B] block
+    CUDA_TRY(cudaMemcpy2DAsync(m->d_params[g], sizeof(double) * s.n, params + s.lo, sizeof(double) * B,
+                               sizeof(double) * s.n, LMATO_NPARAM, cudaMemcpyHostToDevice, m->st[g]));
+    const lmato_status_t rc = lmato_solve_batch(h, m->d_params[g], s.n, s.traj, s.tf, s.fm, s.st, s.it, s.kkt, m->st[g]);
+    h->opt.warm_start = ws_saved;
+    if (rc != LMATO_OK) return rc;
+  }
+  // phase 2: every device writes its slice of the host arrays
+  for (int g = 0; g < G; ++g) {
+    const Shard& s = sh[g];
+    if (s.n == 0) continue;
+    CUDA_TRY(cudaSetDevice(m->h[g]->device));
+    cudaStream_t st = m->st[g];
+    if (out_traj)
+      CUDA_TRY(cudaMemcpy2DAsync(out_traj + s.lo, sizeof(double) * B, s.traj, sizeof(double) * s.n, sizeof(double) * s.n,
+                                 (size_t)LMATO_NVAR * nt, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(out_tf + s.lo, s.tf, sizeof(double) * s.n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(out_final_mass + s.lo, s.fm, sizeof(double) * s.n, cudaMemcpyDeviceToHost, st));
+    if (out_kkt) CUDA_TRY(cudaMemcpyAsync(out_kkt + s.lo, s.kkt, sizeof(double) * s.n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(out_status + s.lo, s.st, sizeof(int32_t) * s.n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(out_iters + s.lo, s.it, sizeof(int32_t) * s.n, cudaMemcpyDeviceToHost, st));
+  }
+  for (int g = 0; g < G; ++g) {
+    if (sh[g].n == 0) continue;
+    CUDA_TRY(cudaSetDevice(m->h[g]->device));
+    CUDA_TRY(cudaStreamSynchronize(m->st[g]));
+  }
+  return LMATO_OK;
+}
+
 }  // extern "C"

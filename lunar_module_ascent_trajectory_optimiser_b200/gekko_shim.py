@@ -50,10 +50,12 @@ def _one(sol: Union[AscentSolution, AscentBatchSolution], index: int):
     if isinstance(sol, AscentSolution):
         states = {k: v.cpu().numpy() for k, v in sol.states.items()}
         ctrl = sol.control.cpu().numpy()
+        states[sol.control_name] = ctrl
         return (sol.tf, states, ctrl, sol.time.cpu().numpy(), sol.status, sol.iterations, sol.final_mass,
                 sol.tf_seconds)
     states = {k: v[index].cpu().numpy() for k, v in sol.states.items()}
     ctrl = sol.control[index].cpu().numpy()
+    states[sol.control_name] = ctrl       # the MV: `angledoubledot` (LO:96), or `angle` in the circular model
     return (float(sol.tf[index]), states, ctrl, sol.time.cpu().numpy(), int(sol.status[index]),
             int(sol.iterations[index]), float(sol.final_mass[index]), float(sol.tf_seconds[index]))
 
@@ -63,7 +65,7 @@ def as_gekko(sol: Union[AscentSolution, AscentBatchSolution], index: int = 0) ->
     nt = len(time)
     ns = SimpleNamespace()
     for name in _VAR_ORDER:
-        arr = ctrl if name == "angledoubledot" else states.get(name)
+        arr = states.get(name)         # (the circular model has no angledot / angledoubledot: PDF p.27 src 54-73)
         if arr is None:
             continue
         setattr(ns, name, GKValue(name, [float(v) for v in arr]))

@@ -26,6 +26,22 @@ def _init_worker():
     _build_node_model("elliptical")
 
 
+def solve_one_gekko(args) -> Tuple[float, int, int, float]:
+    """The reference's own stack (only when tools/probe_gekko.py found it usable): GEKKO(remote=False), one
+    problem per process, with the reference's OTOL = RTOL = 1e-3 (LO:31-32)."""
+    col, nt, _tol, _obj_scale, _dcost = args
+    import sys as _sys
+    _sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from tools.probe_gekko import declare_and_solve
+    kw = dict(zip(_ROWS, [float(v) for v in col]))
+    t0 = time.perf_counter()
+    try:
+        m, tf, _v = declare_and_solve(kw, nt=nt)
+        return float(tf.value[0]), 0, int(m.options.ITERATIONS), time.perf_counter() - t0
+    except Exception:
+        return float("nan"), 1, 0, time.perf_counter() - t0
+
+
 def solve_one(args) -> Tuple[float, int, int, float]:
     col, nt, tol, obj_scale, dcost = args
     from oracle.ascent_nlp import AscentNLP, AscentParams
@@ -44,7 +60,8 @@ def solve_one(args) -> Tuple[float, int, int, float]:
 class OraclePool:
     """One worker process per host core, reused across steps."""
 
-    def __init__(self, cores: int = 0):
+    def __init__(self, cores: int = 0, gekko: bool = False):
+        self.gekko = gekko
         self.cores = cores or (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count())
         ctx = mp.get_context("spawn")
         self.pool = ctx.Pool(self.cores, initializer=_init_worker)
@@ -55,7 +72,7 @@ class OraclePool:
         """rows: [NPARAM, n].  Returns (tf[n], status[n], iters[n], wall seconds)."""
         n = rows.shape[1]
         t0 = time.perf_counter()
-        res = self.pool.map(solve_one, [(rows[:, i].copy(), nt, tol, obj_scale, dcost) for i in range(n)], chunksize=1)
+        res = self.pool.map(solve_one_gekko if self.gekko else solve_one, [(rows[:, i].copy(), nt, tol, obj_scale, dcost) for i in range(n)], chunksize=1)
         wall = time.perf_counter() - t0
         tf = np.array([r[0] for r in res])
         st = np.array([r[1] for r in res])

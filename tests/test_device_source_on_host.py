@@ -35,12 +35,12 @@ def hostsim(tmp_path_factory):
     return L
 
 
-def _solve(L, raw, nt=200, time=None, tol=1e-10):
+def _solve(L, raw, nt=200, time=None, tol=1e-10, fn="hostsim_solve"):
     raw = np.ascontiguousarray(raw, dtype=np.float64)
     traj = np.empty((10, nt))
     tf, it, kkt = C.c_double(), C.c_int(), C.c_double()
     tp = None if time is None else np.ascontiguousarray(time, dtype=np.float64).ctypes.data_as(C.c_void_p)
-    st = L.hostsim_solve(raw.ctypes.data_as(C.c_void_p), nt, tp, C.c_double(tol), C.c_double(10.0), C.c_double(1e-3),
+    st = getattr(L, fn)(raw.ctypes.data_as(C.c_void_p), nt, tp, C.c_double(tol), C.c_double(10.0), C.c_double(1e-3),
                          traj.ctypes.data_as(C.c_void_p), C.byref(tf), C.byref(it), C.byref(kkt))
     return st, tf.value, it.value, traj
 
@@ -85,3 +85,40 @@ def test_device_ipm_source_matches_goldens(hostsim, monkeypatch):
     raw = NOMINAL.copy(); raw[8] = raw[9] = 53108.4; raw[11] = 2576.0
     st, tf, it, traj = _solve(hostsim, raw)
     assert st == 0 and abs(tf - float(g["tf"])) / float(g["tf"]) < 1e-8
+
+
+def test_cooperative_sweeps_source_matches_goldens_and_thread_sweeps(hostsim, monkeypatch):
+    """csrc/ascent_coop.cuh run by one lane (G = 1: the group primitives are identities): the stored-model
+    phases, the row-wise congruence with its symmetrisation, the forward / adjoint recursions.  Same optimum
+    and the same number of iterations as the one-thread-per-problem sweeps, on every golden case."""
+    monkeypatch.delenv("WDC", raising=False)
+    monkeypatch.delenv("CIRCULAR", raising=False)
+    monkeypatch.delenv("NPOL", raising=False)
+
+    def both(raw, gold_tf, gold_traj=None, **kw):
+        a = _solve(hostsim, raw, fn="hostsim_solve", **kw)
+        b = _solve(hostsim, raw, fn="hostsim_solve_coop", **kw)
+        assert a[0] == 0 and b[0] == 0
+        assert abs(b[1] - gold_tf) / gold_tf < 1e-8 and abs(a[1] - b[1]) / a[1] < 1e-11
+        assert abs(a[2] - b[2]) <= 1, (a[2], b[2])                    # iterations
+        if gold_traj is not None:
+            err = _rel(b[3], gold_traj)
+            assert err[:9].max() < 1e-4 and err[9] < 2e-4, err
+        assert _rel(b[3], a[3] + 0.0)[:9].max() < 1e-5
+
+    g = np.load(os.path.join(GOLDEN, "elliptical_nominal_nt200.npz"))
+    both(NOMINAL, float(g["tf"]), g["traj"])
+    g = np.load(os.path.join(GOLDEN, "elliptical_nominal_nt40.npz"))
+    both(NOMINAL, float(g["tf"]), g["traj"], nt=40)
+    g = np.load(os.path.join(GOLDEN, "elliptical_nominal_nonuniform60.npz"))
+    both(NOMINAL, float(g["tf"]), g["traj"], nt=60, time=g["time"])
+    g = np.load(os.path.join(GOLDEN, "elliptical_dcost1e-5_disp4_seed11_nt200.npz"))
+    monkeypatch.setenv("WDC", repr(10.0 * 1e-5 / 199))
+    monkeypatch.setenv("NPOL", "2")
+    for b in range(4):
+        both(g["rows"][:, b], g["tf"][b], g["traj"][b])
+    monkeypatch.delenv("WDC"); monkeypatch.delenv("NPOL")
+    g = np.load(os.path.join(GOLDEN, "circular_nominal_nt200.npz"))
+    monkeypatch.setenv("CIRCULAR", "1")
+    raw = NOMINAL.copy(); raw[8] = raw[9] = 53108.4; raw[11] = 2576.0
+    both(raw, float(g["tf"]))

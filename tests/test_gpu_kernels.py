@@ -1,0 +1,152 @@
+"""The two kernel mappings (one thread per problem / eight lanes per problem, csrc/ascent_coop.cuh) must be the
+same solver: same optimum to rounding, same iteration counts up to line-search ties.  Plus the boundary items of
+round 2: OTOL/RTOL rule, solves on different streams of one handle, the C ABI's device-list entry, and the
+reference's own post-processing (LO:187-202) run on a device solution through the GEKKO-shaped shim."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+VAR_ROWS = ["y", "ydot", "ydoubledot", "x", "xdot", "xdoubledot", "angle", "angledot", "mass", "angledoubledot"]
+
+
+@pytest.fixture(scope="module")
+def lm(built_lib):
+    import lunar_module_ascent_trajectory_optimiser_b200 as lm
+    assert torch.cuda.is_available()
+    return lm
+
+
+def _solve(lm, rows, nt=200, model="elliptical", **opt):
+    s = lm.AscentSolver(lm.Mesh(nt=nt), lm.SolverOptions(**opt), device=0, model=model)
+    r = s.solve_rows(rows.cuda())
+    torch.cuda.synchronize()
+    out = {k: (v.cpu() if v is not None else None) for k, v in r.items()}
+    s.close()
+    return out
+
+
+@pytest.mark.parametrize("B,nt,dcost", [(1, 200, 1e-5), (300, 200, 1e-5), (300, 200, 0.0), (1500, 200, 1e-5), (40, 801, 1e-5)])
+def test_thread_and_coop_kernels_agree(lm, B, nt, dcost):
+    rows = (lm.dispersed_params(B, seed=17) if B > 1 else lm.AscentParams()).rows(B)
+    ref = _solve(lm, rows, nt, kernel="thread", dcost=dcost)
+    assert int((ref["status"] != 0).sum()) == 0
+    sc = ref["traj"].abs().amax(dim=1, keepdim=True) + 1e-300
+    for lanes in (8, 32):
+        got = _solve(lm, rows, nt, kernel="coop", coop_lanes=lanes, dcost=dcost)
+        assert int((got["status"] != 0).sum()) == 0, (lanes, torch.bincount(got["status"].long()))
+        assert float(((got["tf"] - ref["tf"]).abs() / ref["tf"]).max()) < 1e-10
+        assert float((got["final_mass"] - ref["final_mass"]).abs().max() / 2600.0) < 1e-10
+        err = ((got["traj"] - ref["traj"]).abs() / sc).amax(dim=(1, 2))
+        assert float(err[:9].max()) < 1e-4 and float(err[9]) < 5e-3, err     # states; MV on the singular arc
+        # the same Newton iteration: iteration counts differ by line-search ties at most
+        assert abs(float(got["iterations"].double().mean()) - float(ref["iterations"].double().mean())) < 1.0
+        assert float(got["kkt"].max()) <= 1e-9
+
+
+def test_coop_kernel_matches_goldens(lm, golden_dir):
+    """The cooperative kernel against the oracle directly (nominal without DCOST, four dispersions with DCOST,
+    circular model), both lane counts."""
+    g = np.load(os.path.join(golden_dir, "elliptical_nominal_nt200.npz"))
+    gd = np.load(os.path.join(golden_dir, "elliptical_dcost1e-5_disp4_seed11_nt200.npz"))
+    gc = np.load(os.path.join(golden_dir, "circular_nominal_nt200.npz"))
+    for lanes in (8, 32):
+        r = _solve(lm, lm.AscentParams().rows(1), kernel="coop", coop_lanes=lanes, dcost=0.0)
+        assert int(r["status"][0]) == 0 and abs(float(r["tf"][0]) - float(g["tf"])) / float(g["tf"]) < 1e-9
+        e = (np.abs(r["traj"][:, :, 0].numpy() - g["traj"]) / (np.abs(g["traj"]).max(axis=1, keepdims=True) + 1e-300)).max(axis=1)
+        assert e[:9].max() < 1e-4 and e[9] < 2e-4, e
+        r = _solve(lm, lm.dispersed_params(4, seed=11).rows(4), kernel="coop", coop_lanes=lanes)
+        for b in range(4):
+            assert abs(float(r["tf"][b]) - gd["tf"][b]) / gd["tf"][b] < 1e-9
+            e = (np.abs(r["traj"][:, :, b].numpy() - gd["traj"][b]) / (np.abs(gd["traj"][b]).max(axis=1, keepdims=True) + 1e-300)).max(axis=1)
+            assert e[:9].max() < 1e-4 and e[9] < 2e-4, e
+        r = _solve(lm, lm.AscentParams.circular().rows(1), model="circular", kernel="coop", coop_lanes=lanes)
+        assert int(r["status"][0]) == 0 and abs(float(r["tf"][0]) - float(gc["tf"])) / float(gc["tf"]) < 1e-9
+
+
+def test_otol_rtol_rule(lm):
+    """LO:31-32: the solve runs to min(tol, otol, rtol).  The reference's 1e-3 never loosens the default 1e-10;
+    a tighter OTOL/RTOL tightens it (include/lmato_b200.h)."""
+    rows = lm.dispersed_params(16, seed=3).rows(16)
+    a = _solve(lm, rows)                                        # otol = rtol = 1e-3 (LO:31-32), tol = 1e-10
+    b = _solve(lm, rows, otol=1e-12, rtol=1e-12)
+    c = _solve(lm, rows, tol=1e-6)                              # an explicitly loose tol is honoured
+    assert float(a["kkt"].max()) <= 1e-10 and float(b["kkt"].max()) <= 1e-12
+    assert float(c["iterations"].double().mean()) < float(a["iterations"].double().mean()) - 2
+    assert float(((b["tf"] - a["tf"]).abs() / a["tf"]).max()) < 1e-9
+    with pytest.raises(lm.LmatoError):
+        lm.AscentSolver(lm.Mesh(nt=20), lm.SolverOptions(otol=-1.0), device=0)
+
+
+def test_two_streams_share_one_handle(lm):
+    """Solves issued back to back on DIFFERENT streams of one handle share its workspace and work queue: the
+    library serialises them on the device (the second waits for the first), results equal the sequential ones."""
+    solver = lm.AscentSolver(lm.Mesh(), lm.SolverOptions(), device=0)
+    r1 = lm.dispersed_params(600, seed=1).rows(600).cuda()
+    r2 = lm.dispersed_params(600, seed=2).rows(600).cuda()
+    want1 = {k: v.clone() for k, v in solver.solve_rows(r1).items()}
+    want2 = {k: v.clone() for k, v in solver.solve_rows(r2).items()}
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    o1, o2 = solver.alloc_outputs(600), solver.alloc_outputs(600)
+    for _ in range(3):
+        with torch.cuda.stream(s1):
+            solver.solve_rows(r1, out=o1)
+        with torch.cuda.stream(s2):
+            solver.solve_rows(r2, out=o2)
+    torch.cuda.synchronize()
+    for k in ("tf", "status", "iterations", "traj"):
+        assert torch.equal(o1[k], want1[k]) and torch.equal(o2[k], want2[k]), k
+
+
+def test_c_abi_device_list(lm):
+    """lmato_multi_*: the C ABI's own device-list entry (host arrays in and out).  One GPU: the list names it
+    twice or three times; two or more: real devices."""
+    B = 333
+    p = lm.dispersed_params(B, seed=23)
+    one = lm.optimise_batch(p)
+    ngpu = torch.cuda.device_count()
+    for devices in ([0], [0, 0], [0, 0, 0]) + (([0, 1],) if ngpu >= 2 else ()):
+        ms = lm.AscentMultiSolver(devices, lm.Mesh(), lm.SolverOptions())
+        raw = ms.solve_rows(p.rows(B))
+        assert int((raw["status"] != 0).sum()) == 0
+        assert torch.equal(raw["tf"], one.tf) and torch.equal(raw["iterations"], one.iterations)
+        assert torch.equal(raw["traj"][0].T, one.states["y"]) and torch.equal(raw["traj"][9].T, one.control)
+        few = ms.solve_rows(p.rows(B)[:, :2].contiguous(), trajectories=False)      # fewer problems than devices
+        assert few["traj"] is None and torch.equal(few["tf"], one.tf[:2])
+        ms.close()
+    many = lm.optimise_batch(p, devices=[0, 0])            # the public API routes host tensors through it
+    assert torch.equal(many.tf, one.tf) and torch.equal(many.states["x"], one.states["x"])
+
+
+def test_reference_postprocessing_runs_on_a_device_solution(lm):
+    """SURVEY 8(f).1 end to end: LO:187-202 (verbatim logic) on as_gekko(optimise()), and the circular model's
+    MV under its reference name `angle` (PDF p.27 src 69-73)."""
+    from lunar_module_ascent_trajectory_optimiser_b200 import gekko_shim
+    g = gekko_shim.as_gekko(lm.optimise())
+    tf, x, y, ydot, xdot, ydoubledot, xdoubledot, angle, m = g.tf, g.x, g.y, g.ydot, g.xdot, g.ydoubledot, g.xdoubledot, g.angle, g.m
+    Rfmin_py, R0_py, final_time = 17703, 1738100, 470
+    ts = m.time * tf.value[0]                                    # LO:187
+    printed = [y.value[-1] * Rfmin_py, x.value[-1] * Rfmin_py, ydot.value[-1] * Rfmin_py, xdot.value[-1] * Rfmin_py,
+               ydoubledot.value[-1] * Rfmin_py, xdoubledot.value[-1] * Rfmin_py, tf.value[0] * final_time]   # LO:188-194
+    y_pos_list = [0] * len(x.value)
+    x_pos_list = [0] * len(x.value)
+    theta_list = [0] * len(x.value)
+    for i in range(len(x.value)):                                # LO:199-202
+        x_pos_list[i] = -x.value[i] * Rfmin_py
+        y_pos_list[i] = y.value[i] * Rfmin_py + R0_py
+        theta_list[i] = 3 * angle.value[i] * (180 / (np.pi))
+    # the reference's published output of exactly these lines (Numerical_results.png), loosely converged there
+    gold = [-6430.82513705478, -290117.041689258, -273.361084935561, -1631.655147319155, -2.38232397650751,
+            -5.52005887268682, 434.03530607609997]
+    for got, want, tol in zip(printed, gold, [1e-3, 1e-4, 1e-4, 1e-4, 2e-3, 1e-4, 1e-4]):
+        assert abs(got - want) / abs(want) < tol, (got, want)
+    assert len(ts) == 200 and abs(math.hypot(x_pos_list[-1], y_pos_list[-1]) - (R0_py + Rfmin_py)) < 1e-3
+    assert 88.4 < theta_list[-1] < 88.6 and g.m.options.APPSTATUS == 1
+    c = gekko_shim.as_gekko(lm.optimise(lm.AscentParams.circular()))
+    assert hasattr(c, "angle") and not hasattr(c, "angledoubledot") and not hasattr(c, "angledot")
+    assert 100.0 < 3 * c.angle.value[-1] * 180 / np.pi < 120.0          # PDF p.21 Fig 9: final pitch ~111 deg

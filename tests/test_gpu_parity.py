@@ -492,9 +492,10 @@ def test_initial_guess(lm):
     zeros = dataclasses.replace(cold, tf=torch.zeros_like(cold.tf),
                                 states={k: torch.zeros_like(v) for k, v in cold.states.items()},
                                 control=torch.zeros_like(cold.control))
+    # (IPOPT reaches the optimum from there through its feasibility restoration phase; this solver has none and
+    #  restarts a problem whose start point leads nowhere from its built-in, dynamically feasible roll-out)
     z = lm.optimise_batch(p, guess=zeros)
-    ok = z.status == 0
-    assert float(((z.tf[ok] - cold.tf[ok]).abs() / cold.tf[ok]).max() if bool(ok.any()) else 0.0) < 1e-8
-    print("all-zero start: converged", int(ok.sum()), "of", B, "iterations", z.iterations.tolist()[:8])
+    assert int((z.status != 0).sum()) == 0, z.status.tolist()
+    assert float(((z.tf - cold.tf).abs() / cold.tf).max()) < 1e-8
     with pytest.raises(ValueError):
         lm.optimise_batch(p, guess=cold, devices=[0])

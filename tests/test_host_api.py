@@ -89,6 +89,11 @@ def _worker(rank, world, port, B, nt, q):
     out = lm.sharded_solve(rows, _stub_solve(nt), None)
     ref = _stub_solve(nt)(rows)
     ok = all(torch.equal(out[k], ref[k]) for k in ref) and out["status"].dtype == torch.int32
+    # scalars gathered, trajectories left sharded (what bench.py's multi-GPU step does)
+    part = lm.sharded_solve(rows, _stub_solve(nt), None, gather_traj=False)
+    lo, hi = lm.shard_bounds(B, world, rank)
+    ok = ok and part["shard"] == (lo, hi) and all(torch.equal(part[k], ref[k]) for k in ref if k != "traj")
+    ok = ok and torch.equal(part["traj"], ref["traj"][:, :, lo:hi])
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 
@@ -113,3 +118,28 @@ def test_package_solution_shapes():
     assert sol.states["y"].shape == (B, nt) and sol.control.shape == (B, nt)
     assert torch.allclose(sol.tf_seconds, sol.tf * 470.0)
     assert len(sol) == B and bool(sol.converged.all())
+
+
+def test_c_abi_default_options_and_kernel_ids():
+    """lmato_default_options through ctypes (no GPU needed): the struct layouts agree and the defaults are the
+    documented ones, incl. the reference's OTOL = RTOL = 1e-3 (LO:31-32) and MAX_ITER = 20000 (LO:28)."""
+    import ctypes as C
+    o = _cabi.LmatoOptions()
+    _cabi.lib().lmato_default_options(C.byref(o))
+    assert (o.tol, o.mu_init, o.obj_scale, o.tf_guess) == (1e-10, 0.1, 10.0, 0.9)
+    assert (o.max_iter, o.max_ls, o.n_polish, o.warm_start) == (20000, 40, -1, 1)
+    assert (o.dcost, o.kappa_eps, o.objective_nodes) == (1e-5, 30.0, 0)
+    assert (o.kernel, o.coop_lanes, o.otol, o.rtol) == (0, 0, 1e-3, 1e-3)
+    assert _cabi.KERNEL_IDS == {"auto": 0, "thread": 1, "coop": 2}
+    s = lm.SolverOptions()
+    assert (s.otol, s.rtol, s.max_iter, s.kernel) == (1e-3, 1e-3, 20000, "auto")
+
+
+def test_circular_solution_names_its_control():
+    nt, B = 5, 2
+    raw = _stub_solve(nt)(lm.dispersed_params(B).rows())
+    sol = package_solution(raw, lm.dispersed_params(B).rows(), torch.linspace(0, 1, nt, dtype=torch.float64), "circular")
+    assert sol.control_name == "angle" and "angle" not in sol.states and "angledot" not in sol.states
+    from lunar_module_ascent_trajectory_optimiser_b200 import gekko_shim
+    g = gekko_shim.as_gekko(sol, 1)
+    assert g.angle.value == sol.control[1].tolist() and not hasattr(g, "angledoubledot")
