@@ -33,6 +33,20 @@ def test_screenshot_self_consistency():
                - p.Ft / m) < 1e-5                                       # thrust acceleration = Ft/m
 
 
+# oracle (converged to 1e-12) minus screenshot, relative to the variable's largest magnitude on the trajectory:
+# the per-variable residuals DESIGN.md section 6 tabulates.  The screenshot is an IPOPT iterate accepted at
+# OTOL = RTOL = 1e-3 (LO:31-32), i.e. a point ON THE WAY to the optimum, not the optimum.
+PNG_RESIDUAL = dict(tf_s=-1.8e-5, y=-2.5e-4, x=-6.1e-5, ydot=-6.1e-5, xdot=+1.7e-6, ydoubledot=-1.1e-3, xdoubledot=+8.7e-5)
+
+
+def _final_state_residuals(nlp, x, S=17703.0):
+    nv = nlp.node_values(x)
+    out = {"tf_s": (x[nlp.i_tf] * 470.0 - PNG["tf_s"]) / PNG["tf_s"]}
+    for k in ("y", "x", "ydot", "xdot", "ydoubledot", "xdoubledot"):
+        out[k] = (nv[k][-1] * S - PNG[k]) / (np.abs(nv[k]).max() * S)
+    return out
+
+
 def test_oracle_reproduces_elliptical_screenshot(golden_dir):
     g = np.load(os.path.join(golden_dir, "elliptical_nominal_nt200.npz"))
     names = list(g["names"])
@@ -44,9 +58,35 @@ def test_oracle_reproduces_elliptical_screenshot(golden_dir):
     for k in ("y", "x", "ydot", "xdot", "ydoubledot", "xdoubledot"):
         val = g["traj"][names.index(k), -1] * S
         scale = np.abs(g["traj"][names.index(k)]).max() * S
-        assert abs(val - PNG[k]) / scale < 1e-4 * 30 if k in ("y", "ydoubledot") else abs(val - PNG[k]) / scale < 1e-4, (k, val, PNG[k])
+        res = (val - PNG[k]) / scale
+        # each variable against its own documented residual (no blanket loosening): x, ydot, xdot, xdoubledot
+        # are inside north_star's 1e-4; y (2.5e-4) and ydoubledot (1.1e-3) are not, see the next test for why
+        assert abs(res - PNG_RESIDUAL[k]) < 0.15 * abs(PNG_RESIDUAL[k]) + 2e-6, (k, res)
+        if k in ("x", "ydot", "xdot", "xdoubledot"):
+            assert abs(res) < 1e-4, (k, res)
     fm = float(g["final_mass"])
     assert abs(fm - (4821 - 5.053 * tf_s)) < 1e-9
+
+
+def test_screenshot_lies_on_the_oracles_central_path():
+    """Why `y` and `ydoubledot` of the converged oracle miss the screenshot by more than 1e-4: the screenshot is
+    not a converged point.  Stopping the oracle's own interior-point iteration early, at a scaled KKT error of
+    3e-5 (barrier parameter 3e-6) on the reference's objective (DCOST included), lands on it: tf to 2e-6, y, x,
+    ydot, xdot, xdoubledot to < 1e-4, and ydoubledot -- which follows the final pitch angle, the weakest
+    determined quantity of this NLP (DESIGN.md "Tolerance") -- to 7e-4, changing sign between 1e-4 and 3e-5.
+    Continuing to 1e-8 moves every quantity monotonically to the converged values of PNG_RESIDUAL."""
+    nlp = AscentNLP(AscentParams(dcost=1e-5), nt=200, obj_scale=10.0)
+    x0 = nlp.initial_guess(0.9)
+    early = _final_state_residuals(nlp, solve_ipm(nlp, x0, IPMOptions(tol=3e-5)).x)
+    assert abs(early["tf_s"]) < 5e-6, early
+    for k in ("y", "x", "ydot", "xdot", "xdoubledot"):
+        assert abs(early[k]) < 1e-4, (k, early)
+    assert abs(early["ydoubledot"]) < 8e-4, early
+    before = _final_state_residuals(nlp, solve_ipm(nlp, x0, IPMOptions(tol=1e-4)).x)
+    late = _final_state_residuals(nlp, solve_ipm(nlp, x0, IPMOptions(tol=1e-8)).x)
+    for k in ("tf_s", "y", "ydoubledot"):
+        assert before[k] > early[k] > late[k], (k, before[k], early[k], late[k])       # the path crosses the screenshot
+        assert abs(late[k] - PNG_RESIDUAL[k]) < 0.15 * abs(PNG_RESIDUAL[k]) + 2e-6, (k, late[k])
 
 
 def test_oracle_reproduces_circular_pdf_output(golden_dir):
