@@ -131,7 +131,9 @@ void lmato_default_options(lmato_options* o);
  *   nt      number of mesh nodes (LO:20, 200)
  *   time    host pointer to nt normalised times in [0,1], strictly increasing, time[0]=0
  *           (LO:21); NULL = linspace(0,1,nt)
- *   nodes   collocation NODES (LO:25); 2 is implemented on the device
+ *   nodes   collocation NODES (LO:25), 2..6.  2 (the reference's value, backward Euler) runs on the two tuned
+ *           kernels; 3..6 (Lobatto collocation with NODES-1 points per step, MV held over the step) run on the
+ *           general collocation kernel: elliptical model, no DCOST term, no warm start / guess / sensitivities
  *   model   lmato_model_t
  * Replaces: GEKKO() + m.time + m.options.* (LO:19-33). */
 lmato_status_t lmato_create(lmato_handle** out, int32_t device, int32_t nt, const double* time,
@@ -202,6 +204,10 @@ typedef enum lmato_sens {
   LMATO_S_ANGLE_DOUBLEDOT_MAX = 3   /* pitch acceleration limit (LO:66) */
 } lmato_sens_t;
 lmato_status_t lmato_set_sensitivity_output(lmato_handle* h, double* out_dtf);
+
+/* The collocation rule used for NODES = 2..6 (host only, no GPU needed): tau[NODES-1] = the non-initial Lobatto
+ * points on (0,1], N[(NODES-1)^2] row-major with  h N f_{1..} = z_{1..} - z_0  (SURVEY Appendix B.2). */
+lmato_status_t lmato_collocation_rule(int32_t nodes, double* tau, double* N);
 
 /* Introspection (for benchmarks and tests). */
 lmato_status_t lmato_workspace_bytes(lmato_handle* h, int64_t B, int64_t* bytes);

@@ -49,7 +49,7 @@ class LmatoError(RuntimeError):
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/ascent_cabi.cu for sm_100a into the in-tree shared library."""
-    srcs = [os.path.join(CSRC, f) for f in ("ascent_cabi.cu", "ascent_ipm.cuh", "ascent_ipm_dc.cuh", "ascent_coop.cuh",
+    srcs = [os.path.join(CSRC, f) for f in ("ascent_cabi.cu", "ascent_ipm.cuh", "ascent_ipm_dc.cuh", "ascent_coop.cuh", "ascent_colloc.cuh",
                                             "ascent_model.cuh")]
     srcs.append(os.path.join(INCLUDE, "lmato_b200.h"))
     if not force and os.path.exists(LIB_PATH):
@@ -96,6 +96,7 @@ def lib() -> C.CDLL:
     L.lmato_coast_orbit.argtypes = [vp, vp, i64, C.c_double, C.c_double, i64, vp, vp]
     L.lmato_set_sensitivity_output.argtypes = [vp, vp]
     L.lmato_set_initial_guess.argtypes = [vp, vp, vp]
+    L.lmato_collocation_rule.argtypes = [i32, vp, vp]
     L.lmato_multi_create.argtypes = [C.POINTER(vp), C.POINTER(i32), i32, i32, vp, i32, i32]
     L.lmato_multi_destroy.argtypes = [vp]
     L.lmato_multi_set_options.argtypes = [vp, C.POINTER(LmatoOptions)]
@@ -105,7 +106,7 @@ def lib() -> C.CDLL:
                  "lmato_solve_batch_host", "lmato_workspace_bytes", "lmato_kernel_launches",
                  "lmato_last_kernel_ms", "lmato_measure_fp64_peak", "lmato_selftest_math", "lmato_coast_orbit",
                  "lmato_set_sensitivity_output", "lmato_set_initial_guess", "lmato_multi_create", "lmato_multi_destroy",
-                 "lmato_multi_set_options", "lmato_multi_device_count", "lmato_multi_solve_host"):
+                 "lmato_multi_set_options", "lmato_multi_device_count", "lmato_multi_solve_host", "lmato_collocation_rule"):
         getattr(L, name).restype = C.c_int
     _lib = L
     return L
@@ -116,7 +117,7 @@ EXPORTED_SYMBOLS = ["lmato_default_options", "lmato_create", "lmato_destroy", "l
                     "lmato_kernel_launches", "lmato_last_kernel_ms", "lmato_measure_fp64_peak",
                     "lmato_selftest_math", "lmato_coast_orbit", "lmato_set_sensitivity_output", "lmato_set_initial_guess", "lmato_last_error",
                     "lmato_version", "lmato_multi_create", "lmato_multi_destroy", "lmato_multi_set_options",
-                    "lmato_multi_device_count", "lmato_multi_solve_host"]
+                    "lmato_multi_device_count", "lmato_multi_solve_host", "lmato_collocation_rule"]
 
 
 def check(rc: int, what: str) -> None:

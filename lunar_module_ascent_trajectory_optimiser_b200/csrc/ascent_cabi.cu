@@ -24,6 +24,7 @@
 #include "../../include/lmato_b200.h"
 #include "ascent_ipm_dc.cuh"
 #include "ascent_coop.cuh"
+#include "ascent_colloc.cuh"
 
 using namespace lmato;
 
@@ -80,6 +81,7 @@ struct KArgs {
   int ref_mode;          // 0 cold start; 1 solve and store the reference (starting from the previous one,
                          // if any); 2 start from the reference
   Options O;
+  colloc::Coll coll;     // collocation rule (NODES >= 3 only)
 };
 
 // Mean of every parameter row over the batch: the reference problem of the warm start.
@@ -502,6 +504,106 @@ static cudaError_t coop_optin() {
   return cudaFuncSetAttribute(ascent_coop_kernel<kCoopG, GP, false, BPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coop_smem(GP));
 }
 
+// ---------------------------------------------------------------------------------------
+// higher-order collocation kernel (NODES = 3..6, ascent_colloc.cuh): GP lanes per problem
+// ---------------------------------------------------------------------------------------
+template <int GP>
+__device__ __noinline__ void colloc_write_results(const KArgs& a, const Params& P, const colloc::Nws& W, const IpmState& S, long b) {
+  SolveOut out;
+  ipm_result(S, out);
+  const int nt = a.N + 1, m = W.L.m;
+  const long B = a.B;
+  if (W.g == 0) {
+    a.tf[b] = out.tf;
+    a.fmass[b] = P.M0 - P.fuel * (P.mflow * P.T * out.tf);
+    a.status[b] = out.status;
+    a.iters[b] = out.iters;
+    if (a.kkt) a.kkt[b] = out.kkt;
+  }
+  double* __restrict__ t = a.traj;
+  if (!t) return;
+  for (int v = W.g; v < LMATO_NVAR; v += GP) t[((long)v * nt) * B + b] = 0.0;   // node 0 pinned
+  for (int k = 1 + W.g; k <= a.N; k += GP) {
+    const double* xr = W.X(out.cur, k);
+    const double* z = xr + 6 * (m - 1);                  // the mesh node is the last collocation point of its step
+    const double ms = P.mflow * P.T * a.tau[k] * out.tf;
+    double ay, ax;
+    accel_value(P, z[0], z[2], z[4], ms, ay, ax);
+    t[((long)LMATO_V_Y * nt + k) * B + b] = z[0];
+    t[((long)LMATO_V_YDOT * nt + k) * B + b] = z[1];
+    t[((long)LMATO_V_YDOUBLEDOT * nt + k) * B + b] = ay;
+    t[((long)LMATO_V_X * nt + k) * B + b] = z[2];
+    t[((long)LMATO_V_XDOT * nt + k) * B + b] = z[3];
+    t[((long)LMATO_V_XDOUBLEDOT * nt + k) * B + b] = ax;
+    t[((long)LMATO_V_ANGLE * nt + k) * B + b] = z[4];
+    t[((long)LMATO_V_ANGLEDOT * nt + k) * B + b] = z[5];
+    t[((long)LMATO_V_MASS * nt + k) * B + b] = ms;
+    t[((long)LMATO_V_ANGLEDOUBLEDOT * nt + k) * B + b] = xr[W.L.x_u];
+  }
+}
+
+template <int GP>
+__global__ void __launch_bounds__(kCoopBlock, 1) ascent_colloc_kernel(KArgs a) {
+  using SW = SweepsColloc<GP>;
+  constexpr int PPW = 32 / GP;
+  constexpr int GPB = kCoopBlock / GP;
+  __shared__ ParamsSlot sP[GPB];
+  __shared__ Options sO;
+  __shared__ Mesh sM;
+  __shared__ colloc::Coll sC;
+  if (threadIdx.x == 0) { sO = a.O; sM = Mesh{a.N, a.h, a.tau}; sC = a.coll; }
+  __syncthreads();
+  const Options& O = sO;
+  const Mesh& M = sM;
+  const int lane = threadIdx.x & 31;
+  const int grp = threadIdx.x / GP;
+  const unsigned gmask = GP == 32 ? 0xffffffffu : (((1u << GP) - 1u) << ((lane / GP) * GP));
+  Params& P = sP[grp].p;
+  const long slot = (long)blockIdx.x * GPB + grp;
+  colloc::Nws W;
+  W.L.init(sC.m);
+  W.base = a.ws + slot * colloc::colloc_doubles_per_problem(a.N + 1, sC.m);
+  W.N1 = a.N + 1; W.C = &sC; W.g = lane % GP; W.mask = gmask; W.dw = 0.0; W.pimax = 0.0; W.ls_flag = 0;
+  IpmState S;
+  bool active = false, pending = false, exhausted = false, first = true;
+  long b = -1;
+  const int warps_per_block = kCoopBlock / 32;
+  while (true) {
+    const bool chunk_done = !__any_sync(0xffffffffu, active);
+    if (chunk_done && __any_sync(0xffffffffu, pending)) {
+      if (pending) colloc_write_results<GP>(a, P, W, S, b);
+      pending = false;
+    }
+    if (!exhausted && chunk_done) {
+      int chunk = 0;
+      if (first) {
+        chunk = (threadIdx.x / 32) * gridDim.x + blockIdx.x;
+        first = false;
+      } else {
+        if (lane == 0) chunk = atomicAdd(a.counter, 1) + gridDim.x * warps_per_block;
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+      }
+      if ((long)chunk * PPW >= a.B) {
+        exhausted = true;
+      } else {
+        b = (long)chunk * PPW + lane / GP;
+        if (b < a.B) {
+          if (W.g == 0) P = derive_params(a.params, a.B, b, a.model);
+          coop::Grp<GP>::sync(gmask);
+          ipm_begin(O, S);
+          SW::guess(P, M, O, W, S.cur);
+          active = true;
+        }
+      }
+    }
+    if (exhausted && !__any_sync(0xffffffffu, active || pending)) break;
+    if (active && ipm_iterate_t<SW>(P, M, O, W, S)) {
+      active = false;
+      pending = true;
+    }
+  }
+}
+
 // FP64 FMA peak: 8 independent chains per thread, no memory traffic.
 __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters) {
   double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
@@ -586,7 +688,49 @@ struct lmato_handle {
   cudaStream_t last_stream = nullptr;
   bool timed = false;
   bool last_coop = false;         // which kernel the last solve used
+  colloc::Coll coll;              // collocation rule for NODES >= 3
 };
+
+// Collocation rule of GEKKO NODES = n: Lobatto points on [0,1] including both ends;
+// h N f_{1..m} = z_{1..m} - z_0 with N_ij = int_0^{tau_i} l_j(s) ds, l_j the Lagrange basis on tau_1..tau_m.
+static bool collocation_rule(int nodes, colloc::Coll* C) {
+  if (nodes < 2 || nodes > 6) return false;
+  const int m = nodes - 1;
+  double pts[6];                         // Lobatto points on [-1, 1]
+  switch (nodes) {
+    case 2: pts[0] = -1; pts[1] = 1; break;
+    case 3: pts[0] = -1; pts[1] = 0; pts[2] = 1; break;
+    case 4: { const double a = sqrt(1.0 / 5.0); pts[0] = -1; pts[1] = -a; pts[2] = a; pts[3] = 1; break; }
+    case 5: { const double a = sqrt(3.0 / 7.0); pts[0] = -1; pts[1] = -a; pts[2] = 0; pts[3] = a; pts[4] = 1; break; }
+    default: {
+      const double a = sqrt(1.0 / 3.0 - 2.0 * sqrt(7.0) / 21.0), b = sqrt(1.0 / 3.0 + 2.0 * sqrt(7.0) / 21.0);
+      pts[0] = -1; pts[1] = -b; pts[2] = -a; pts[3] = a; pts[4] = b; pts[5] = 1; break;
+    }
+  }
+  double tau[6];
+  for (int i = 0; i < nodes; ++i) tau[i] = 0.5 * (pts[i] + 1.0);
+  C->m = m;
+  for (int i = 0; i < colloc::MAXM; ++i) { C->tau[i] = 0.0; for (int j = 0; j < colloc::MAXM; ++j) C->N[i][j] = 0.0; }
+  for (int i = 0; i < m; ++i) C->tau[i] = tau[i + 1];
+  for (int j = 0; j < m; ++j) {
+    double c[6] = {1, 0, 0, 0, 0, 0};    // coefficients of l_j, ascending powers
+    int deg = 0;
+    for (int q = 0; q < m; ++q) {
+      if (q == j) continue;
+      const double den = tau[j + 1] - tau[q + 1];
+      double n[6] = {0, 0, 0, 0, 0, 0};
+      for (int d = 0; d <= deg; ++d) { n[d + 1] += c[d] / den; n[d] -= c[d] * tau[q + 1] / den; }
+      ++deg;
+      for (int d = 0; d <= deg; ++d) c[d] = n[d];
+    }
+    for (int i = 0; i < m; ++i) {
+      double s = 0.0, tp = tau[i + 1];
+      for (int d = 0; d <= deg; ++d) { s += c[d] * tp / (double)(d + 1); tp *= tau[i + 1]; }
+      C->N[i][j] = s;
+    }
+  }
+  return true;
+}
 
 // device-side part of lmato_create (every failure path returns through the caller's lmato_destroy)
 static lmato_status_t create_device_state(lmato_handle* H, const std::vector<double>& h, const std::vector<double>& tau) {
@@ -647,14 +791,14 @@ lmato_status_t lmato_create(lmato_handle** out, int32_t device, int32_t nt, cons
   if (!out) { set_err("lmato_create: out is NULL"); return LMATO_ERR_INVALID; }
   *out = nullptr;
   if (nt < 2) { set_err("lmato_create: nt must be >= 2"); return LMATO_ERR_INVALID; }
-  if (nodes != 2) {
-    set_err("lmato_create: NODES=%s not implemented on the device (only 2 = backward Euler, LO:25)",
-            nodes == 3 ? "3" : "n");
-    return LMATO_ERR_UNSUPPORTED;
-  }
+  if (nodes < 2 || nodes > 6) { set_err("lmato_create: NODES must be 2..6 (GEKKO's range, LO:25)"); return LMATO_ERR_INVALID; }
   if (model != LMATO_MODEL_ELLIPTICAL && model != LMATO_MODEL_CIRCULAR) {
     set_err("lmato_create: unknown model");
     return LMATO_ERR_INVALID;
+  }
+  if (nodes > 2 && model != LMATO_MODEL_ELLIPTICAL) {
+    set_err("lmato_create: NODES > 2 is implemented for the elliptical model (Launch_Optimiser.py) only");
+    return LMATO_ERR_UNSUPPORTED;
   }
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -676,6 +820,7 @@ lmato_status_t lmato_create(lmato_handle** out, int32_t device, int32_t nt, cons
   if (!H) { set_err("lmato_create: out of host memory"); return LMATO_ERR_INVALID; }
   H->device = device; H->nt = nt; H->nodes = nodes; H->model = model;
   lmato_default_options(&H->opt);
+  collocation_rule(nodes, &H->coll);
   const lmato_status_t rc = create_device_state(H, h, tau);
   if (rc != LMATO_OK) { lmato_destroy(H); return rc; }      // frees whatever was allocated before the failure
   *out = H;
@@ -750,7 +895,18 @@ static long coop_grid_for(const lmato_handle* h, int64_t B, int gp) {
 static size_t coop_ws_bytes(const lmato_handle* h, long grid, int gp) {
   return sizeof(double) * (size_t)coop::coop_doubles_per_problem(h->nt) * (size_t)(grid * (kCoopBlock / gp));
 }
+static int colloc_gp_for(const lmato_handle* h, int64_t B) { return B <= (int64_t)h->sm_count * 8 ? 32 : 8; }
+static long colloc_grid_for(const lmato_handle* h, int64_t B, int gp) {
+  const long chunks = (B + (32 / gp) - 1) / (32 / gp);
+  const long cap = (long)h->sm_count;
+  return chunks < cap ? (chunks > 0 ? chunks : 1) : cap;
+}
 static size_t ws_bytes_for(const lmato_handle* h, int64_t B) {
+  if (h->nodes > 2) {
+    const int gp = colloc_gp_for(h, B);
+    return sizeof(double) * (size_t)colloc::colloc_doubles_per_problem(h->nt, h->nodes - 1) *
+           (size_t)(colloc_grid_for(h, B, gp) * (kCoopBlock / gp));
+  }
   if (use_coop(h, B)) { const int gp = coop_gp_for(h, B); return coop_ws_bytes(h, coop_grid_for(h, B, gp), gp); }
   return sizeof(double) * (size_t)fields_for(h) * (size_t)h->nt * (size_t)slots_for(h, B);
 }
@@ -783,12 +939,17 @@ lmato_status_t lmato_solve_batch(lmato_handle* h, const double* params, int64_t 
   // Every solve on a handle shares its workspace, work-queue counter and warm-start reference.  A solve issued on
   // a different stream than the previous one first waits (on the device) for that one to finish.
   if (h->timed && st != h->last_stream) CUDA_TRY(cudaStreamWaitEvent(st, h->ev1, 0));
-  const bool coopk = use_coop(h, B);
+  const bool hi_order = h->nodes > 2;        // NODES >= 3: the general collocation kernel
+  if (hi_order && (h->sens_out || h->guess_traj)) {
+    set_err("lmato_solve_batch: sensitivities and caller-supplied start points are implemented for NODES = 2 only");
+    return LMATO_ERR_UNSUPPORTED;
+  }
+  const bool coopk = !hi_order && use_coop(h, B);
   const long slots = slots_for(h, B);
   const int gp = coop_gp_for(h, B);
   const long cgrid = coop_grid_for(h, B, gp);
-  const bool use_dc = dcost_active(h);
-  const bool warm = !h->guess_traj && (h->opt.warm_start == 2 || (h->opt.warm_start == 1 && B >= kWarmStartMinBatch));
+  const bool use_dc = dcost_active(h) && !hi_order;   // the l1 move term is carried by the NODES = 2 kernels only
+  const bool warm = !hi_order && !h->guess_traj && (h->opt.warm_start == 2 || (h->opt.warm_start == 1 && B >= kWarmStartMinBatch));
   size_t need = ws_bytes_for(h, B);
   if (warm) { const size_t r = coop_ws_bytes(h, 1, 32); if (r > need) need = r; }     // the reference solve: one warp of one CTA
   if (need > h->ws_bytes) {
@@ -849,7 +1010,13 @@ lmato_status_t lmato_solve_batch(lmato_handle* h, const double* params, int64_t 
     a.ref = h->d_ref; a.ref_mode = 2;
     h->launches += 2;
   }
-  if (coopk) {
+  a.coll = h->coll;
+  if (hi_order) {
+    const int cgp = colloc_gp_for(h, B);
+    const int cg = (int)colloc_grid_for(h, B, cgp);
+    if (cgp == 32) ascent_colloc_kernel<32><<<cg, kCoopBlock, 0, st>>>(a);
+    else ascent_colloc_kernel<8><<<cg, kCoopBlock, 0, st>>>(a);
+  } else if (coopk) {
     const int bps = coop_bps_for(h, B, gp);
     if (gp == 32) { if (bps == 1) coop_launch<32, 1>(use_dc, cgrid, st, a); else coop_launch<32, 2>(use_dc, cgrid, st, a); }
     else          { if (bps == 1) coop_launch<8, 1>(use_dc, cgrid, st, a); else coop_launch<8, 2>(use_dc, cgrid, st, a); }
@@ -961,6 +1128,13 @@ lmato_status_t lmato_solve_batch_host(lmato_handle* h, const double* params, int
   CUDA_TRY(cudaMemcpyAsync(out_status, d_st, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaMemcpyAsync(out_iters, d_it, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
+  return LMATO_OK;
+}
+
+lmato_status_t lmato_collocation_rule(int32_t nodes, double* tau, double* N) {
+  colloc::Coll C;
+  if (!tau || !N || !collocation_rule(nodes, &C)) { set_err("lmato_collocation_rule: NODES must be 2..6"); return LMATO_ERR_INVALID; }
+  for (int i = 0; i < C.m; ++i) { tau[i] = C.tau[i]; for (int j = 0; j < C.m; ++j) N[i * C.m + j] = C.N[i][j]; }
   return LMATO_OK;
 }
 

@@ -64,6 +64,7 @@ struct Nws {
   double* base;
   int N1;
   Lay L;
+  const Coll* C;         // the collocation rule (shared by the whole launch)
   int g;                 // lane inside the group (0 .. GP-1)
   unsigned mask;
   mutable double dw;
@@ -672,16 +673,30 @@ LM_NOINLINE void colloc_init_guess(const Params& P, const Mesh& M, const Options
 
 }  // namespace colloc
 
-// Sweeps policy of the higher-order collocation path for the IPM driver.  The collocation rule travels in the
-// workspace view's companion object; the driver passes `W` through untouched.
-struct CollocCtx { colloc::Nws W; const colloc::Coll* C; mutable int ls_flag; };
-
+// Sweeps policy of the higher-order collocation path for the IPM driver (ipm_iterate_t).
 template <int GP>
 struct SweepsColloc {
-  LM_HD static int n_eq(int N, int m) { return 6 * m * N + 3; }
-  LM_HD static int n_bd(int N, int m) { return (2 * m + 2) * N + 4; }
-  // (ipm_iterate_t asks with N only; m is folded in by the caller through Mesh::N being the number of steps)
-  static int m_;
+  LM_HD static int n_eq(const colloc::Nws& W, int N) { return 6 * W.L.m * N + 3; }
+  LM_HD static int n_bd(const colloc::Nws& W, int N) { return (2 * W.L.m + 2) * N + 4; }
+  LM_HD static bool backward(const Params& P, const Mesh& M, const Options& O, const colloc::Nws& W, int src, const Scal& c0,
+                             double mu, double dw, bool ls, double* dtf) {
+    if (ls) colloc::colloc_build<GP>(P, M, *W.C, W, src, c0.tf, true);
+    return colloc::colloc_backward<GP>(P, M, O, W, src, c0, mu, dw, ls, dtf);
+  }
+  LM_HD static void forward(const Params& P, const Mesh& M, const Options& O, const colloc::Nws& W, int src, const Scal& c0,
+                            double mu, double tau, double dtf, bool ls, TermStep& ts, StepInfo& si) {
+    colloc::colloc_forward<GP>(P, M, O, *W.C, W, src, c0, mu, tau, dtf, ls, ts, si);
+  }
+  LM_HD static void eval(const Params& P, const Mesh& M, const Options& O, const colloc::Nws& W, int src, int dst,
+                         const Scal& c0, const TermStep& ts, double mu, double /*dw*/, double alpha, double alpha_z,
+                         double alpha_lam, int /*mode*/, Scal& t, double* pimax) {
+    colloc::colloc_eval<GP>(P, M, O, *W.C, W, src, dst, c0, ts, mu, alpha, alpha_z, alpha_lam, t);
+    if (pimax) *pimax = W.pimax;
+  }
+  LM_HD static void guess(const Params& P, const Mesh& M, const Options& O, const colloc::Nws& W, Scal& s) {
+    colloc::colloc_init_guess<GP>(P, M, O, *W.C, W, s);
+  }
+  LM_HD static void remerit(const Mesh&, const Options&, const colloc::Nws&, int, double, Scal&) {}
 };
 
 }  // namespace lmato

@@ -1095,8 +1095,8 @@ LM_NOINLINE bool coop_load_ref(const Params& P, const Mesh& M, const Options& O,
 template <int G, int GP, bool MOVE>
 struct SweepsCoop {
   enum : int { LANES_PER_PROBLEM = GP };
-  LM_HD static int n_eq(int N) { return (MOVE ? 7 : 6) * N + 3; }
-  LM_HD static int n_bd(int N) { return (MOVE ? 6 : 4) * N + 4; }
+  LM_HD static int n_eq(const coop::Cws&, int N) { return (MOVE ? 7 : 6) * N + 3; }
+  LM_HD static int n_bd(const coop::Cws&, int N) { return (MOVE ? 6 : 4) * N + 4; }
   LM_HD static bool backward(const Params& P, const Mesh& M, const Options& O, const coop::Cws& W, int src, const Scal& c0,
                              double mu, double dw, bool ls, double* dtf) {
     // the least-squares multiplier estimate factorises its own model (Hessian := I) of the start point

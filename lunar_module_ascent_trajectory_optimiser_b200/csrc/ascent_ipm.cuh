@@ -1240,8 +1240,8 @@ LM_HD void ipm_begin(const Options& O, IpmState& S) {
 // Sweeps policy of the 7-state formulation (dcost = 0); ascent_ipm_dc.cuh provides the 8-state one.
 struct Sweeps7 {
   enum : int { NFIELDS = N_FIELDS, NITER = N_ITER, FZ = F_Z, FU = F_U, FLAM = F_LAM, REFROWS = REF_ROWS };
-  LM_HD static int n_eq(int N) { return 6 * N + 3; }
-  LM_HD static int n_bd(int N) { return 4 * N + 4; }
+  LM_HD static int n_eq(const Ws&, int N) { return 6 * N + 3; }
+  LM_HD static int n_bd(const Ws&, int N) { return 4 * N + 4; }
   LM_HD static bool backward(const Params& P, const Mesh& M, const Options& O, const Ws& W, int src, const Scal& c0,
                              double mu, double dw, bool ls, double* dtf) {
     return riccati_backward(P, M, O, W, src, c0, mu, dw, ls, dtf);
@@ -1273,8 +1273,8 @@ LM_HD bool ipm_iterate_t(const Params& P, const Mesh& M, const Options& O, const
   Ctl& ctl = S.ctl;
   Scal& cur = S.cur;
   const int N = M.N;
-  const int n_eq = SW::n_eq(N);
-  const int n_bd = SW::n_bd(N);
+  const int n_eq = SW::n_eq(W, N);
+  const int n_bd = SW::n_bd(W, N);
   const bool ls = (S.phase == PH_LSQ);
   W.ls_flag = ls ? 1 : 0;
   if (!ls) {

@@ -69,7 +69,7 @@ def main():
              final_mass=np.array(fms), traj=np.stack(trajs), names=np.array(VAR_ROWS))
 
 
-if __name__ == "__main__" and not any(a in sys.argv for a in ("--dense", "--dcost", "--sens")):
+if __name__ == "__main__" and not any(a in sys.argv for a in ("--dense", "--dcost", "--sens", "--nodes")):
     main()
 
 
@@ -135,3 +135,30 @@ def sensitivities():
 
 if __name__ == "__main__" and "--sens" in sys.argv:
     sensitivities()
+
+
+def higher_order():
+    """NODES = 3..6 (LO:25): Lobatto collocation with NODES-1 points per step, MV held over the
+    step, no DCOST term.  Nominal case on coarse meshes for every NODES, three seed-11 dispersions for NODES = 3."""
+    import torch  # noqa: F401
+    from lunar_module_ascent_trajectory_optimiser_b200.dispersions import dispersed_params
+    out = {}
+    for nodes, nt in ((3, 40), (4, 30), (5, 24), (6, 20)):
+        s = solve(AscentParams(dcost=0.0), nt=nt, nodes=nodes, tol=1e-11)
+        out[f"tf_n{nodes}"] = s["tf"]; out[f"fm_n{nodes}"] = s["final_mass"]; out[f"traj_n{nodes}"] = s["traj"]
+        out[f"nt_n{nodes}"] = nt
+        print("nodes", nodes, "nt", nt, "tf_s", s["tf"] * 470, "iters", s["iters"], "kkt", s["kkt"])
+    rows = dispersed_params(4, seed=11).rows().numpy()[:, 1:4]
+    tfs, fms, trajs = [], [], []
+    for b in range(rows.shape[1]):
+        p = AscentParams(Ft=rows[3, b], M0=rows[4, b], M_dot=rows[5, b], angle_doubledot_max=rows[7, b],
+                         r_periapsis=rows[8, b], r_apoapsis=rows[9, b], dcost=0.0)
+        s = solve(p, nt=60, nodes=3, tol=1e-11)
+        tfs.append(s["tf"]); fms.append(s["final_mass"]); trajs.append(s["traj"])
+        print("nodes 3 dispersion", b, "tf_s", s["tf"] * 470, "iters", s["iters"])
+    np.savez(os.path.join(HERE, "elliptical_higher_order_nodes3to6.npz"), names=np.array(VAR_ROWS), rows=rows,
+             disp_tf=np.array(tfs), disp_fm=np.array(fms), disp_traj=np.stack(trajs), disp_nt=60, **out)
+
+
+if __name__ == "__main__" and "--nodes" in sys.argv:
+    higher_order()

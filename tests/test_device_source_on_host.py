@@ -122,3 +122,37 @@ def test_cooperative_sweeps_source_matches_goldens_and_thread_sweeps(hostsim, mo
     monkeypatch.setenv("CIRCULAR", "1")
     raw = NOMINAL.copy(); raw[8] = raw[9] = 53108.4; raw[11] = 2576.0
     both(raw, float(g["tf"]))
+
+
+def test_higher_order_collocation_source_matches_goldens(hostsim):
+    """csrc/ascent_colloc.cuh (NODES = 3..6, LO:25) run by one lane against the oracle's fixtures: per-step LU
+    condensation, dense Riccati on the coupling unknowns, multipliers from the stored factors.  The collocation
+    rule comes from the C ABI (lmato_collocation_rule) and must equal the oracle's (APMonitor's tables)."""
+    from lunar_module_ascent_trajectory_optimiser_b200 import _cabi
+    from oracle.ascent_nlp import collocation_matrix
+    g = np.load(os.path.join(GOLDEN, "elliptical_higher_order_nodes3to6.npz"))
+    fn = hostsim.hostsim_solve_colloc
+
+    def solve(raw, nt, nodes):
+        m = nodes - 1
+        tau = np.zeros(m); Nc = np.zeros((m, m))
+        assert _cabi.lib().lmato_collocation_rule(nodes, tau.ctypes.data_as(C.c_void_p), Nc.ctypes.data_as(C.c_void_p)) == 0
+        t_or, N_or = collocation_matrix(nodes)
+        assert np.abs(tau - t_or[1:]).max() < 1e-14 and np.abs(Nc - N_or).max() < 1e-12
+        raw = np.ascontiguousarray(raw, dtype=np.float64)
+        traj = np.empty((10, nt)); tf, it, kkt = C.c_double(), C.c_int(), C.c_double()
+        st = fn(raw.ctypes.data_as(C.c_void_p), nt, None, nodes, Nc.ctypes.data_as(C.c_void_p), tau.ctypes.data_as(C.c_void_p),
+                C.c_double(1e-10), C.c_double(10.0), C.c_double(1e-3), traj.ctypes.data_as(C.c_void_p), C.byref(tf),
+                C.byref(it), C.byref(kkt))
+        return st, tf.value, it.value, traj
+
+    for nodes in (3, 4, 5, 6):
+        nt = int(g[f"nt_n{nodes}"])
+        st, tf, it, traj = solve(NOMINAL, nt, nodes)
+        assert st == 0 and abs(tf - float(g[f"tf_n{nodes}"])) / tf < 1e-9, (nodes, st, tf)
+        err = _rel(traj, g[f"traj_n{nodes}"])
+        assert err[:9].max() < 1e-6 and err[9] < 1e-4, (nodes, err)
+    for b in range(3):
+        st, tf, it, traj = solve(g["rows"][:, b], int(g["disp_nt"]), 3)
+        assert st == 0 and abs(tf - g["disp_tf"][b]) / tf < 1e-9
+        assert _rel(traj, g["disp_traj"][b])[:9].max() < 1e-5

@@ -150,3 +150,41 @@ def test_reference_postprocessing_runs_on_a_device_solution(lm):
     c = gekko_shim.as_gekko(lm.optimise(lm.AscentParams.circular()))
     assert hasattr(c, "angle") and not hasattr(c, "angledoubledot") and not hasattr(c, "angledot")
     assert 100.0 < 3 * c.angle.value[-1] * 180 / np.pi < 120.0          # PDF p.21 Fig 9: final pitch ~111 deg
+
+
+def test_higher_order_collocation_matches_goldens(lm, golden_dir):
+    """NODES = 3..6 on the device (LO:25): the general collocation kernel against the oracle's
+    fixtures at north_star's tolerances (achieved: tf 1e-9, states 1e-6), a dispersed batch through both lane
+    mappings, and the properties every solution must have."""
+    g = np.load(os.path.join(golden_dir, "elliptical_higher_order_nodes3to6.npz"))
+    for nodes in (3, 4, 5, 6):
+        nt = int(g[f"nt_n{nodes}"])
+        sol = lm.optimise(lm.AscentParams(dcost=0.0), lm.Mesh(nt=nt, nodes=nodes))
+        assert sol.status == 0
+        assert abs(sol.tf - float(g[f"tf_n{nodes}"])) / sol.tf < 1e-9
+        assert abs(sol.final_mass - float(g[f"fm_n{nodes}"])) / sol.final_mass < 1e-9
+        traj = torch.stack([sol.control if n == "angledoubledot" else sol.states[n] for n in VAR_ROWS]).numpy()
+        gold = g[f"traj_n{nodes}"]
+        err = (np.abs(traj - gold) / (np.abs(gold).max(axis=1, keepdims=True) + 1e-300)).max(axis=1)
+        assert err[:9].max() < 1e-4 and err[9] < 2e-4, (nodes, err)
+        assert err[:9].max() < 1e-6, (nodes, err)
+        assert np.all(traj[:, 0] == 0.0)
+    # dispersions, NODES = 3, nt = 60: problems 1..3 of the seed-11 draw are the fixture's
+    p = lm.dispersed_params(4, seed=11)
+    sol = lm.optimise_batch(p, lm.Mesh(nt=60, nodes=3), lm.SolverOptions(dcost=0.0))
+    assert int((sol.status != 0).sum()) == 0
+    for b in range(3):
+        assert abs(float(sol.tf[b + 1]) - g["disp_tf"][b]) / g["disp_tf"][b] < 1e-9
+        assert abs(float(sol.states["xdot"][b + 1, -1]) - g["disp_traj"][b][4, -1]) < 1e-8
+    # a batch large enough for the 8-lane mapping (> 8 problems per SM) agrees with the 32-lane one
+    B = 1500
+    pb = lm.dispersed_params(B, seed=5)
+    big = lm.optimise_batch(pb, lm.Mesh(nt=24, nodes=4), trajectories=False)
+    few = lm.optimise_batch(lm.dispersed_params(B, seed=5), lm.Mesh(nt=24, nodes=4), batch=None, trajectories=False)
+    assert int((big.status != 0).sum()) == 0 and torch.equal(big.tf, few.tf)
+    small = lm.optimise_batch(lm.AscentParams(**{k: (v[:64] if isinstance(v, torch.Tensor) else v) for k, v in pb.__dict__.items()}),
+                              lm.Mesh(nt=24, nodes=4), trajectories=False)
+    assert float(((small.tf - big.tf[:64]).abs() / small.tf).max()) < 1e-10
+    # unsupported combinations answer with an error, not a wrong result
+    with pytest.raises(lm.LmatoError):
+        lm.optimise_batch(lm.dispersed_params(4), lm.Mesh(nt=24, nodes=3), sensitivities=True)

@@ -184,7 +184,9 @@ def test_empty_batch_and_errors(lm):
     raw = solver.solve_rows(torch.empty((14, 0), dtype=torch.float64).cuda())
     assert raw["tf"].numel() == 0
     with pytest.raises(lm.LmatoError):
-        lm.AscentSolver(lm.Mesh(nt=20, nodes=3), lm.SolverOptions(), device=0)   # NODES=3 not on device yet
+        lm.AscentSolver(lm.Mesh(nt=20, nodes=7), lm.SolverOptions(), device=0)   # GEKKO's NODES range is 2..6
+    with pytest.raises(lm.LmatoError):
+        lm.AscentSolver(lm.Mesh(nt=20, nodes=3), lm.SolverOptions(), device=0, model="circular")   # NODES > 2: elliptical only
     with pytest.raises(lm.LmatoError):
         lm.AscentSolver(lm.Mesh(time=[0.0, 0.5, 0.4, 1.0]), lm.SolverOptions(), device=0)
     # max_iter exhausted is a per-problem status, not an exception, in the batch API ...

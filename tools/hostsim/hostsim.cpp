@@ -240,3 +240,48 @@ extern "C" int hostsim_solve_coop(const double* raw14, int nt, const double* tim
   }
   return out.status;
 }
+
+// Higher-order collocation (csrc/ascent_colloc.cuh), GP = 1.  Ncol: row-major m x m, tauc: m points.
+#include "ascent_colloc.cuh"
+extern "C" int hostsim_solve_colloc(const double* raw14, int nt, const double* time, int nodes, const double* Ncol,
+                                    const double* tauc, double tol, double obj_scale, double mu_min_factor,
+                                    double* traj /* [10][nt] */, double* tf_out, int* iters, double* kkt) {
+  const int N = nt - 1, m = nodes - 1;
+  std::vector<double> h(N + 1), tau(N + 1);
+  for (int k = 0; k <= N; ++k) { tau[k] = time ? time[k] : (double)k / N; h[k] = k ? tau[k] - tau[k - 1] : 0.0; }
+  Mesh M{N, h.data(), tau.data()};
+  Options O;
+  O.tol = tol; O.mu_init = 0.1; O.obj_scale = obj_scale; O.kappa_eps = 30.0; O.kappa_mu = 0.2; O.theta_mu = 1.5; O.theta_mu_warm = 2.0;
+  O.tau_min = 0.99; O.delta_c = 1e-8; O.tf_guess = 0.9; O.max_iter = 500; O.max_ls = 40; O.mu_min_factor = mu_min_factor; O.n_polish = getenv("NPOL") ? atoi(getenv("NPOL")) : 4;
+  O.w_dcost = 0.0;
+  Params P;
+  const double* r = raw14;
+  P.GM = r[0] * r[1]; P.R0 = r[2]; P.Ft = r[3]; P.M0 = r[4]; P.S = r[8]; P.ms = r[11]; P.mflow = r[5] / r[6];
+  P.asc = r[7] / 3.0; P.T = r[10]; P.a_ub = r[12]; P.u_ub = r[13];
+  const double vt = std::sqrt(P.GM / (P.R0 + 0.5 * (r[8] + r[9])));
+  P.vt2 = (vt / P.S) * (vt / P.S); P.rt = (P.R0 + P.S) / P.S; P.R0S = P.R0 / P.S;
+  P.tf_ub = std::fmin(1.0, 1.0 / (P.mflow * P.T)); P.fuel = r[6]; P.Sinv = 1.0 / P.S; P.coup5 = 1.0; P.mT = P.mflow * P.T;
+  colloc::Coll C;
+  C.m = m;
+  for (int i = 0; i < m; ++i) { C.tau[i] = tauc[i]; for (int j = 0; j < m; ++j) C.N[i][j] = Ncol[i * m + j]; }
+  std::vector<double> ws((size_t)colloc::colloc_doubles_per_problem(nt, m), 0.0);
+  colloc::Nws W;
+  W.base = ws.data(); W.N1 = nt; W.L.init(m); W.C = &C; W.g = 0; W.mask = 1u; W.dw = 0.0; W.pimax = 0.0; W.ls_flag = 0;
+  IpmState S;
+  ipm_begin(O, S);
+  SweepsColloc<1>::guess(P, M, O, W, S.cur);
+  while (!ipm_iterate_t<SweepsColloc<1>>(P, M, O, W, S)) {}
+  SolveOut out;
+  ipm_result(S, out);
+  *tf_out = out.tf; *iters = out.iters; *kkt = out.kkt;
+  for (int v = 0; v < 10; ++v) traj[v * nt] = 0.0;
+  for (int k = 1; k <= N; ++k) {
+    const double* x = W.X(out.cur, k) + 6 * (m - 1);
+    const double ms = P.mflow * P.T * tau[k] * out.tf;
+    double ay, ax;
+    accel_value(P, x[0], x[2], x[4], ms, ay, ax);
+    const double vals[10] = {x[0], x[1], ay, x[2], x[3], ax, x[4], x[5], ms, W.X(out.cur, k)[W.L.x_u]};
+    for (int v = 0; v < 10; ++v) traj[v * nt + k] = vals[v];
+  }
+  return out.status;
+}
