@@ -47,19 +47,27 @@ class LmatoError(RuntimeError):
     pass
 
 
+LAST_BUILD = {"action": None, "seconds": 0.0}     # what the last build_library() call did: "compiled" | "reused"
+
+
 def build_library(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/ascent_cabi.cu for sm_100a into the in-tree shared library."""
+    """Compile csrc/ascent_cabi.cu for sm_100a into the in-tree shared library (or reuse it if it is newer than
+    every source; ``LAST_BUILD`` says which)."""
+    import time as _time
     srcs = [os.path.join(CSRC, f) for f in ("ascent_cabi.cu", "ascent_ipm.cuh", "ascent_ipm_dc.cuh", "ascent_coop.cuh", "ascent_colloc.cuh",
                                             "ascent_model.cuh")]
     srcs.append(os.path.join(INCLUDE, "lmato_b200.h"))
     if not force and os.path.exists(LIB_PATH):
         if all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
+            LAST_BUILD.update(action="reused", seconds=0.0)
             return LIB_PATH
     cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
           ["-o", LIB_PATH, os.path.join(CSRC, "ascent_cabi.cu")]
+    t0 = _time.time()
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise LmatoError("nvcc failed:\n" + r.stdout + r.stderr)
+    LAST_BUILD.update(action="compiled", seconds=_time.time() - t0)
     if verbose:
         sys.stderr.write(r.stderr)
     return LIB_PATH

@@ -565,6 +565,7 @@ __global__ void __launch_bounds__(kCoopBlock, 1) ascent_colloc_kernel(KArgs a) {
   W.base = a.ws + slot * colloc::colloc_doubles_per_problem(a.N + 1, sC.m);
   W.N1 = a.N + 1; W.C = &sC; W.g = lane % GP; W.mask = gmask; W.dw = 0.0; W.pimax = 0.0; W.ls_flag = 0;
   IpmState S;
+  int variant = 0;
   bool active = false, pending = false, exhausted = false, first = true;
   long b = -1;
   const int warps_per_block = kCoopBlock / 32;
@@ -591,13 +592,22 @@ __global__ void __launch_bounds__(kCoopBlock, 1) ascent_colloc_kernel(KArgs a) {
           if (W.g == 0) P = derive_params(a.params, a.B, b, a.model);
           coop::Grp<GP>::sync(gmask);
           ipm_begin(O, S);
-          SW::guess(P, M, O, W, S.cur);
+          variant = 0;
+          SW::guess_variant(P, M, O, W, S.cur, variant);
           active = true;
         }
       }
     }
     if (exhausted && !__any_sync(0xffffffffu, active || pending)) break;
     if (active && ipm_iterate_t<SW>(P, M, O, W, S)) {
+      if (S.ctl.status != ST_CONVERGED && S.ctl.status != ST_MAX_ITER && variant + 1 < (int)SW::N_STARTS) {
+        // no restoration phase: a problem that fails from one start point is restarted from the next
+        const int it_used = S.ctl.iter;
+        ipm_begin(O, S);
+        S.ctl.iter = it_used; S.ctl.iter_best = it_used;      // MAX_ITER (LO:28) bounds the whole ladder
+        SW::guess_variant(P, M, O, W, S.cur, ++variant);
+        continue;
+      }
       active = false;
       pending = true;
     }

@@ -51,7 +51,8 @@ enum : int {
   MR = M_Q + QR,
   K_FF = 8, KR = 10,
   HR = 8,
-  PER_STAGE = 2 * XR + DR + 2 * MR + KR + HR,
+  VR = 72,                                // rows of W_k = P_k + Q_k (64) and g_k = p_k + q_k (8): see VREC below
+  PER_STAGE = 2 * XR + DR + 2 * MR + KR + HR + VR,
   SCR_TR1 = 80, SCR_TR2 = 72,                                    // group scratch: the two transpose tiles of backward()
   // record ring of the sequential phases (cp.async, see rg_*): slots of backward / forward / adjoint
   RING_D = 4,                             // slots (a power of two): records travel RING_D-1 stages ahead
@@ -162,6 +163,7 @@ struct Cws {
   LM_HD double* Mo(int buf, int k) const { return base + (2L * N1) * XR + (long)N1 * DR + ((long)buf * N1 + k) * MR; }
   LM_HD double* K(int k) const { return base + (2L * N1) * XR + (long)N1 * DR + (2L * N1) * MR + (long)k * KR; }
   LM_HD double* H(int k) const { return base + (2L * N1) * XR + (long)N1 * DR + (2L * N1) * MR + (long)N1 * KR + (long)k * HR; }
+  LM_HD double* V(int k) const { return base + (2L * N1) * XR + (long)N1 * DR + (2L * N1) * MR + (long)N1 * (KR + HR) + (long)k * VR; }
 };
 LM_HD long coop_doubles_per_problem(int nt) { return (long)nt * PER_STAGE; }
 static_assert(RING_SF <= RING_SB && RING_SA <= RING_SB, "ring too small");
@@ -311,7 +313,11 @@ LM_SWEEP void coop_build(const Params& P, const Mesh& M, const Options& O, const
 //   condense the move (row / column 6, read from the same tile), P_{k-1} = D (Wt - ...) D
 // identical, up to rounding, to dc::riccati_backward.  Returns false on wrong inertia.
 // ---------------------------------------------------------------------------------------
-template <int G, bool MOVE>
+// VREC: also keep W_k = P_k + Q_k and g_k = p_k + q_k of every stage (72 doubles).  The new multipliers are then
+// pi_k = -E_k^-T (W_k ds_k + g_k)  -- a stage-parallel product in forward() -- instead of the sequential adjoint
+// recursion: one of the three sequential sweeps per iteration disappears, for 1.1 KB more traffic per stage.
+// Used where the sequential sweeps are the critical path (a warp per problem), not where HBM traffic counts.
+template <int G, bool MOVE, bool VREC>
 LM_SWEEP bool coop_backward_seq(const Params& P, const Mesh& M, const Options& O, const Cws& W, int src,
                                 const Scal& c0, double mu, double dw, bool ls, double* dtf_out) {
   constexpr int R = 8 / G;
@@ -386,6 +392,15 @@ LM_SWEEP bool coop_backward_seq(const Params& P, const Mesh& M, const Options& O
       for (int ii = 0; ii < 7; ++ii) t7 = (i == ii) ? q[Q_T0 + ii] : t7;
       Pr[r][7] += t7;
       pr[r] += e4 ? q[Q_G4A] + mu * q[Q_G4B] : (i == 6) ? q[Q_GUA] + mu * q[Q_GUB] : 0.0;
+    }
+    if (VREC) {
+      double* v = W.V(k);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int i = g * R + r;
+        stv<8>(v + 8 * i, Pr[r]);
+        v[64 + i] = pr[r];
+      }
     }
     // ---- X = W E^-1 (row operation), transpose [X | g] across the group ----
 #pragma unroll
@@ -497,13 +512,13 @@ LM_SWEEP bool coop_backward_seq(const Params& P, const Mesh& M, const Options& O
 }
 
 // the G lanes of the sequential group factorise; the result goes to all GP lanes of the group
-template <int G, int GP, bool MOVE>
+template <int G, int GP, bool MOVE, bool VREC>
 LM_SWEEP bool coop_backward(const Params& P, const Mesh& M, const Options& O, const Cws& W, int src,
                             const Scal& c0, double mu, double dw, bool ls, double* dtf_out) {
   W.dw = dw;
   double dtf = 0.0;
   int ok = 0;
-  if (W.g < G) ok = coop_backward_seq<G, MOVE>(P, M, O, W, src, c0, mu, dw, ls, &dtf) ? 1 : 0;
+  if (W.g < G) ok = coop_backward_seq<G, MOVE, VREC>(P, M, O, W, src, c0, mu, dw, ls, &dtf) ? 1 : 0;
   Grp<GP>::sync(W.mask);                     // the feedback law K is read by forward()
   if (GP > G) { ok = Grp<GP>::bcast_int(W.mask, ok, 0); dtf = Grp<GP>::bcast(W.mask, dtf, 0); }
   *dtf_out = dtf;
@@ -516,7 +531,7 @@ LM_SWEEP bool coop_backward(const Params& P, const Mesh& M, const Options& O, co
 // ratios, merit slope, and the right-hand sides Q_k ds_k + q_k of the adjoint recursion; (3) the adjoint
 // recursion E_k^T pi_k = D pi_{k+1} - (Q_k ds_k + q_k) for the new defect multipliers.
 // ---------------------------------------------------------------------------------------
-template <int G, int GP, bool MOVE>
+template <int G, int GP, bool MOVE, bool VREC>
 LM_SWEEP void coop_forward(const Params& P, const Mesh& M, const Options& O, const Cws& W, int src,
                            const Scal& c0, double mu, double tau, double dtf, bool ls, TermStep& ts, StepInfo& si) {
   const int N = M.N;
@@ -576,11 +591,11 @@ LM_SWEEP void coop_forward(const Params& P, const Mesh& M, const Options& O, con
   }
   Grp<GP>::sync(pmk);
   // ---- (2) stage-parallel ----
-  double dphi = 0.0, dxmax = 0.0;
+  double dphi = 0.0, dxmax = 0.0, pimax_par = 0.0;
   RatioMax rp, rz;
   rp.init(); rz.init();
   TermQP tq;
-  if (((N - 1) % GP) == g) {
+  if (!VREC && ((N - 1) % GP) == g) {
     double zn[8];
     ldv<8>(W.X(src, N), zn);
     terminal_qp(P, O, c0, zn, mu, dw, ls, tq);
@@ -618,6 +633,28 @@ LM_SWEEP void coop_forward(const Params& P, const Mesh& M, const Options& O, con
     rz.push(-((mu - zlu * du) * rLu - zlu), zlu);
     rz.push(-((mu + zuu * du) * rUu - zuu), zuu);
     dphi += mu * ((rUa - rLa) * da + (rUu - rLu) * du);
+    if (VREC) {
+      // new multipliers of this stage from the kept rows: pi_k = -E_k^-T (W_k ds_k + g_k)
+      double v[VR], gg[8];
+      ldv<VR>(W.V(k), v);
+#pragma unroll
+      for (int i = 0; i < 7; ++i) {
+        double t = fma(v[8 * i + 7], dtf, v[64 + i]);
+#pragma unroll
+        for (int j = 0; j < 7; ++j) t = fma(v[8 * i + j], d[j], t);
+        gg[i] = -t;
+      }
+      gg[7] = 0.0;
+      StageJac J;
+      jac_load(W.Mo(src, k), J);
+      dc::solveET8(J, gg);
+      gg[7] = 0.0;
+      stv<8>(W.D(k) + D_PI, gg);
+      if (ls) {
+#pragma unroll
+        for (int i = 0; i < 7; ++i) pimax_par = dmax(pimax_par, fabs(gg[i]));
+      }
+    } else {
     // right-hand side of the adjoint recursion (same Hessian as the factorisation, delta_w included)
     const double dd = q[Q_D0] + dw;
     double h[8];
@@ -635,6 +672,7 @@ LM_SWEEP void coop_forward(const Params& P, const Mesh& M, const Options& O, con
         h[i] += tq.H[i][0] * d[0] + tq.H[i][1] * d[1] + tq.H[i][2] * d[2] + tq.H[i][3] * d[3] + tq.g[i];
     }
     stv<HR>(W.H(k), h);
+    }
   }
   dphi = Grp<GP>::sum(pmk, dphi);
   dxmax = dmax(Grp<GP>::max(pmk, dxmax), fabs(dtf));
@@ -677,6 +715,10 @@ LM_SWEEP void coop_forward(const Params& P, const Mesh& M, const Options& O, con
   // ---- (3) adjoint recursion, every lane of the sequential group ----
   double pin[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   double pimax = 0.0;
+  if (VREC) {
+    W.pimax = Grp<GP>::max(pmk, pimax_par);
+    return;
+  }
   if (g < G) {
   const double* pm = W.Mo(src, N) + 2 * g;
   const double* ph = W.H(N) + 2 * g;
@@ -1092,7 +1134,7 @@ LM_NOINLINE bool coop_load_ref(const Params& P, const Mesh& M, const Options& O,
 // Sweeps policy of the cooperative formulation for the IPM driver (ipm_iterate_t).
 //   G  lanes carry the sequential phases (cost-to-go distributed by rows: 8/G rows per lane),
 //   GP lanes (a multiple of G, at most a warp) carry the stage-parallel phases of the same problem.
-template <int G, int GP, bool MOVE>
+template <int G, int GP, bool MOVE, bool VREC = (GP > G)>
 struct SweepsCoop {
   enum : int { LANES_PER_PROBLEM = GP };
   LM_HD static int n_eq(const coop::Cws&, int N) { return (MOVE ? 7 : 6) * N + 3; }
@@ -1101,11 +1143,11 @@ struct SweepsCoop {
                              double mu, double dw, bool ls, double* dtf) {
     // the least-squares multiplier estimate factorises its own model (Hessian := I) of the start point
     if (ls) coop::coop_build<GP, MOVE>(P, M, O, W, src, c0.tf, true);
-    return coop::coop_backward<G, GP, MOVE>(P, M, O, W, src, c0, mu, dw, ls, dtf);
+    return coop::coop_backward<G, GP, MOVE, VREC>(P, M, O, W, src, c0, mu, dw, ls, dtf);
   }
   LM_HD static void forward(const Params& P, const Mesh& M, const Options& O, const coop::Cws& W, int src, const Scal& c0,
                             double mu, double tau, double dtf, bool ls, TermStep& ts, StepInfo& si) {
-    coop::coop_forward<G, GP, MOVE>(P, M, O, W, src, c0, mu, tau, dtf, ls, ts, si);
+    coop::coop_forward<G, GP, MOVE, VREC>(P, M, O, W, src, c0, mu, tau, dtf, ls, ts, si);
   }
   LM_HD static void eval(const Params& P, const Mesh& M, const Options& O, const coop::Cws& W, int src, int dst,
                          const Scal& c0, const TermStep& ts, double mu, double /*dw*/, double alpha, double alpha_z,

@@ -224,8 +224,11 @@ extern "C" int hostsim_solve_coop(const double* raw14, int nt, const double* tim
   coop::Cws W{ws.data(), nt, scr.data(), 0, 1u, 1u, 0.0, 0.0, 0};
   IpmState S;
   ipm_begin(O, S);
-  if (DC) { SweepsCoop<1, 1, true>::guess(P, M, O, W, S.cur); while (!ipm_iterate_t<SweepsCoop<1, 1, true>>(P, M, O, W, S)) {} }
-  else    { SweepsCoop<1, 1, false>::guess(P, M, O, W, S.cur); while (!ipm_iterate_t<SweepsCoop<1, 1, false>>(P, M, O, W, S)) {} }
+  const bool vrec = getenv("VREC") != nullptr;     // the variant that keeps W_k, g_k instead of running the adjoint recursion
+  if (DC && vrec)  { SweepsCoop<1, 1, true, true>::guess(P, M, O, W, S.cur); while (!ipm_iterate_t<SweepsCoop<1, 1, true, true>>(P, M, O, W, S)) {} }
+  else if (DC)     { SweepsCoop<1, 1, true, false>::guess(P, M, O, W, S.cur); while (!ipm_iterate_t<SweepsCoop<1, 1, true, false>>(P, M, O, W, S)) {} }
+  else if (vrec)   { SweepsCoop<1, 1, false, true>::guess(P, M, O, W, S.cur); while (!ipm_iterate_t<SweepsCoop<1, 1, false, true>>(P, M, O, W, S)) {} }
+  else             { SweepsCoop<1, 1, false, false>::guess(P, M, O, W, S.cur); while (!ipm_iterate_t<SweepsCoop<1, 1, false, false>>(P, M, O, W, S)) {} }
   SolveOut out;
   ipm_result(S, out);
   *tf_out = out.tf; *iters = out.iters; *kkt = out.kkt;
@@ -268,11 +271,16 @@ extern "C" int hostsim_solve_colloc(const double* raw14, int nt, const double* t
   colloc::Nws W;
   W.base = ws.data(); W.N1 = nt; W.L.init(m); W.C = &C; W.g = 0; W.mask = 1u; W.dw = 0.0; W.pimax = 0.0; W.ls_flag = 0;
   IpmState S;
-  ipm_begin(O, S);
-  SweepsColloc<1>::guess(P, M, O, W, S.cur);
-  while (!ipm_iterate_t<SweepsColloc<1>>(P, M, O, W, S)) {}
   SolveOut out;
-  ipm_result(S, out);
+  const int v0 = getenv("VARIANT") ? atoi(getenv("VARIANT")) : 0;
+  const int nv = getenv("VARIANT") ? v0 + 1 : (int)SweepsColloc<1>::N_STARTS;
+  for (int variant = v0; variant < nv; ++variant) {        // the kernel's restart ladder
+    ipm_begin(O, S);
+    SweepsColloc<1>::guess_variant(P, M, O, W, S.cur, variant);
+    while (!ipm_iterate_t<SweepsColloc<1>>(P, M, O, W, S)) {}
+    ipm_result(S, out);
+    if (out.status == ST_CONVERGED) break;
+  }
   *tf_out = out.tf; *iters = out.iters; *kkt = out.kkt;
   for (int v = 0; v < 10; ++v) traj[v * nt] = 0.0;
   for (int k = 1; k <= N; ++k) {
