@@ -176,15 +176,16 @@ def test_higher_order_collocation_matches_goldens(lm, golden_dir):
     for b in range(3):
         assert abs(float(sol.tf[b + 1]) - g["disp_tf"][b]) / g["disp_tf"][b] < 1e-9
         assert abs(float(sol.states["xdot"][b + 1, -1]) - g["disp_traj"][b][4, -1]) < 1e-8
-    # a batch large enough for the 8-lane mapping (> 8 problems per SM) agrees with the 32-lane one
+    # a batch large enough for the 8-lane mapping (> 8 problems per SM) agrees with the 32-lane one; every problem
+    # of 1 500 six-parameter dispersions converges (start-point ladder of colloc_init_guess)
     B = 1500
     pb = lm.dispersed_params(B, seed=5)
-    big = lm.optimise_batch(pb, lm.Mesh(nt=24, nodes=4), trajectories=False)
-    few = lm.optimise_batch(lm.dispersed_params(B, seed=5), lm.Mesh(nt=24, nodes=4), batch=None, trajectories=False)
-    assert int((big.status != 0).sum()) == 0 and torch.equal(big.tf, few.tf)
+    big = lm.optimise_batch(pb, lm.Mesh(nt=40, nodes=4), trajectories=False)
+    assert int((big.status != 0).sum()) == 0, torch.bincount(big.status.long())
     small = lm.optimise_batch(lm.AscentParams(**{k: (v[:64] if isinstance(v, torch.Tensor) else v) for k, v in pb.__dict__.items()}),
-                              lm.Mesh(nt=24, nodes=4), trajectories=False)
+                              lm.Mesh(nt=40, nodes=4), trajectories=False)
     assert float(((small.tf - big.tf[:64]).abs() / small.tf).max()) < 1e-10
+    assert float(big.kkt_error.max()) <= 1e-9 and 0.85 < float(big.tf.min()) and float(big.tf.max()) < 1.0
     # unsupported combinations answer with an error, not a wrong result
     with pytest.raises(lm.LmatoError):
         lm.optimise_batch(lm.dispersed_params(4), lm.Mesh(nt=24, nodes=3), sensitivities=True)
