@@ -81,7 +81,7 @@ struct KArgs {
   int ref_mode;          // 0 cold start; 1 solve and store the reference (starting from the previous one,
                          // if any); 2 start from the reference
   Options O;
-  colloc::Coll coll;     // collocation rule (NODES >= 3 only)
+  const colloc::Coll* coll;   // collocation rule in device memory (NODES >= 3 only)
 };
 
 // Mean of every parameter row over the batch: the reference problem of the warm start.
@@ -427,7 +427,9 @@ __global__ void __launch_bounds__(kCoopBlock, BPS) ascent_coop_kernel(KArgs a) {
   Params& P = sP[grp].p;
   const long slot = (long)blockIdx.x * GPB + grp;
   const coop::Cws W{a.ws + slot * coop::coop_doubles_per_problem(a.N + 1), a.N + 1, sScr + grp * kCoopScrStride,
-                    lane % GP, gmask, smask, 0.0, 0.0, 0};
+                    lane % GP, gmask, smask, 0.0, 0.0, 0, 0u};
+  if (W.g == 0) coop::ring_init_barriers(W.bars());      // the mbarriers of this group's record ring
+  __syncthreads();
   IpmState S;
   bool active = false, pending = false, exhausted = false, first = true;
   long b = -1;
@@ -551,7 +553,7 @@ __global__ void __launch_bounds__(kCoopBlock, 1) ascent_colloc_kernel(KArgs a) {
   __shared__ Options sO;
   __shared__ Mesh sM;
   __shared__ colloc::Coll sC;
-  if (threadIdx.x == 0) { sO = a.O; sM = Mesh{a.N, a.h, a.tau}; sC = a.coll; }
+  if (threadIdx.x == 0) { sO = a.O; sM = Mesh{a.N, a.h, a.tau}; sC = *a.coll; }
   __syncthreads();
   const Options& O = sO;
   const Mesh& M = sM;
@@ -698,7 +700,8 @@ struct lmato_handle {
   cudaStream_t last_stream = nullptr;
   bool timed = false;
   bool last_coop = false;         // which kernel the last solve used
-  colloc::Coll coll;              // collocation rule for NODES >= 3
+  colloc::Coll coll;              // collocation rule for NODES >= 3 ...
+  colloc::Coll* d_coll = nullptr; // ... and its device copy
 };
 
 // Collocation rule of GEKKO NODES = n: Lobatto points on [0,1] including both ends;
@@ -764,6 +767,8 @@ static lmato_status_t create_device_state(lmato_handle* H, const std::vector<dou
   CUDA_TRY(cudaMalloc(&H->d_ref, sizeof(double) * (size_t)dc::REF_ROWS * nt));   // dc:: is the larger layout
   CUDA_TRY(cudaMemset(H->d_ref, 0, sizeof(double) * (size_t)dc::REF_ROWS * nt));   // REF_OK = 0: no reference yet
   CUDA_TRY(cudaMalloc(&H->d_refparams, sizeof(double) * (LMATO_NPARAM + 8)));
+  CUDA_TRY(cudaMalloc(&H->d_coll, sizeof(colloc::Coll)));
+  CUDA_TRY(cudaMemcpy(H->d_coll, &H->coll, sizeof(colloc::Coll), cudaMemcpyHostToDevice));
   CUDA_TRY(cudaEventCreate(&H->ev0));
   CUDA_TRY(cudaEventCreate(&H->ev1));
   return LMATO_OK;
@@ -841,7 +846,7 @@ lmato_status_t lmato_destroy(lmato_handle* h) {
   if (!h) return LMATO_OK;
   cudaSetDevice(h->device);
   cudaFree(h->d_h); cudaFree(h->d_tau); cudaFree(h->d_ws); cudaFree(h->d_counter);
-  cudaFree(h->d_params); cudaFree(h->d_out); cudaFree(h->d_ref); cudaFree(h->d_refparams); cudaFree(h->d_guess);
+  cudaFree(h->d_params); cudaFree(h->d_out); cudaFree(h->d_ref); cudaFree(h->d_refparams); cudaFree(h->d_guess); cudaFree(h->d_coll);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   delete h;
@@ -1020,7 +1025,7 @@ lmato_status_t lmato_solve_batch(lmato_handle* h, const double* params, int64_t 
     a.ref = h->d_ref; a.ref_mode = 2;
     h->launches += 2;
   }
-  a.coll = h->coll;
+  a.coll = h->d_coll;
   if (hi_order) {
     const int cgp = colloc_gp_for(h, B);
     const int cg = (int)colloc_grid_for(h, B, cgp);

@@ -60,7 +60,7 @@ enum : int {
   RING_SF = M_Q + KR,                     // forward: J, c of the M record, then the feedback law
   RING_SA = JR + HR,                      // adjoint: J, then the right-hand side
   RING_DOUBLES = RING_D * RING_SB,
-  SCR_DOUBLES = SCR_TR1 + SCR_TR2 + RING_DOUBLES
+  SCR_DOUBLES = SCR_TR1 + SCR_TR2 + RING_DOUBLES + RING_D      // ... + one mbarrier (8 bytes) per ring slot
 };
 
 // 128-bit moves of N (even) doubles
@@ -156,8 +156,10 @@ struct Cws {
   mutable double dw;     // delta_w of the last factorisation (the adjoint recursion uses the same Hessian)
   mutable double pimax;  // largest new defect multiplier of the last adjoint recursion
   mutable int ls_flag;   // set by the driver while the least-squares multiplier estimate runs
+  mutable unsigned rpar; // phase bits of the ring's mbarriers (lanes of the sequential group)
   LM_HD double* ring() const { return scr; }
   LM_HD double* tiles() const { return scr + RING_DOUBLES; }
+  LM_HD double* bars() const { return scr + RING_DOUBLES + SCR_TR1 + SCR_TR2; }
   LM_HD double* X(int buf, int k) const { return base + ((long)buf * N1 + k) * XR; }
   LM_HD double* D(int k) const { return base + (2L * N1) * XR + (long)k * DR; }
   LM_HD double* Mo(int buf, int k) const { return base + (2L * N1) * XR + (long)N1 * DR + ((long)buf * N1 + k) * MR; }
@@ -170,35 +172,123 @@ static_assert(RING_SF <= RING_SB && RING_SA <= RING_SB, "ring too small");
 
 // Record ring.  A sequential phase reads one small record set per stage, at addresses known in advance; without
 // help each stage would start with an exposed L2/HBM round trip (~700 cycles against 100-400 cycles of
-// arithmetic).  The group copies the records DEPTH-1 stages ahead into its shared-memory ring with cp.async
-// (LDGSTS: 16-byte chunks spread over the lanes, no registers), one commit group per stage; a stage waits for
-// its own group, then a group barrier makes every lane's chunks visible.
+// arithmetic).  The group moves the records RING_D-1 stages ahead into its shared-memory ring.  Two back ends:
+//   default          cp.async (LDGSTS): the 16-byte chunks of a record are spread over the lanes, one commit
+//                    group per stage; a stage waits for its own group, then a group barrier makes every lane's
+//                    chunks visible (in the backward sweep that barrier is the symmetrisation tile's).
+//   LMATO_RING_BULK  cp.async.bulk.shared.global (the TMA engine; SASS UBLKCP) issued by ONE lane per record,
+//                    completing on the slot's mbarrier (expect_tx / complete_tx; SASS SYNCS), on which every
+//                    lane of the group waits; records written with ordinary stores in an earlier phase are
+//                    published to the asynchronous proxy by a proxy fence of every writer (ring_publish()).
+// The records are contiguous and 16-byte aligned, i.e. exactly what a bulk copy wants -- but they are 160-416
+// bytes and on the critical path of a single warp: measured on B200 the mbarrier round trip (arrive.expect_tx,
+// UBLKCP through the uniform datapath, try_wait) costs ~350 cycles per stage and phase more than four LDGSTS
+// and a wait_group (single solve 5.7 -> 8.9 ms, config 5 254 -> 320 ms; a ring of 8 slots instead of 4 changes
+// nothing, so it is issue/wait overhead, not uncovered latency).  Hence cp.async by default.
+struct Ring {
+  double* base;          // slot 0 (generic pointer; shared memory on the device)
 #if defined(__CUDA_ARCH__)
-typedef unsigned RingRef;      // shared-space byte address of this lane's first 16-byte chunk of slot 0
-#else
-typedef double* RingRef;
+  unsigned slot_s;       // shared-space byte address of slot 0
+  unsigned bar_s;        // shared-space byte address of the first of RING_D mbarriers
 #endif
-LM_HD RingRef rg_ref(double* ring, int g) {
-#if defined(__CUDA_ARCH__)
-  return (unsigned)__cvta_generic_to_shared(ring) + 16u * (unsigned)g;
+  int g;                 // lane inside the group
+};
+#if defined(LMATO_RING_BULK)
+constexpr bool kRingBulk = true;
 #else
-  return ring + 2 * g;
+constexpr bool kRingBulk = false;
+#endif
+LM_HD void ring_publish() {
+#if defined(__CUDA_ARCH__) && defined(LMATO_RING_BULK)
+  asm volatile("fence.proxy.async.global;" ::: "memory");
 #endif
 }
-// copy a record of NDBL doubles (16-byte chunks, chunk c*G+g by lane g) to offset `off` (doubles) of the ring;
-// `src` already points at this lane's first chunk
-template <int G, int NDBL>
-LM_HD void rg_copy(RingRef r, int off, const double* src, int g) {
-#pragma unroll
-  for (int c = 0; c < (NDBL / 2 + G - 1) / G; ++c) {
-    if (c * G + g < NDBL / 2) {
+LM_HD Ring ring_of(double* base, double* bars, int g) {
+  Ring r;
+  r.base = base; r.g = g;
 #if defined(__CUDA_ARCH__)
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(r + 8u * (unsigned)(off + 2 * c * G)), "l"(src + 2 * c * G) : "memory");
+  r.slot_s = (unsigned)__cvta_generic_to_shared(base);
+  r.bar_s = (unsigned)__cvta_generic_to_shared(bars);
 #else
-      r[off + 2 * c * G] = src[2 * c * G]; r[off + 2 * c * G + 1] = src[2 * c * G + 1];
+  (void)bars;
 #endif
-    }
+  return r;
+}
+// once per kernel, by one lane of the group (followed by a CTA barrier)
+LM_HD void ring_init_barriers(double* bars) {
+#if defined(__CUDA_ARCH__) && defined(LMATO_RING_BULK)
+  const unsigned b = (unsigned)__cvta_generic_to_shared(bars);
+#pragma unroll
+  for (int i = 0; i < RING_D; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b + 8u * i), "r"(1u) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#else
+  (void)bars;
+#endif
+}
+// Fill slot `slot` (stride SLOT doubles) with record A (NA doubles) followed by record B (NB doubles, may be 0);
+// valid = false: the stage does not exist (the commit group is still closed, so that groups and stages stay in step).
+template <int G, int SLOT, int NA, int NB>
+LM_HD void ring_issue(const Ring& r, int slot, const double* a, const double* b, bool valid) {
+#if defined(__CUDA_ARCH__)
+#if defined(LMATO_RING_BULK)
+  if (!valid || r.g != 0) return;
+  const unsigned bar = r.bar_s + 8u * (unsigned)slot;
+  const unsigned dst = r.slot_s + 8u * (unsigned)(slot * SLOT);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(8u * (NA + NB)) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(a), "r"(8u * NA), "r"(bar) : "memory");
+  if (NB > 0)
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst + 8u * NA), "l"(b), "r"(8u * NB), "r"(bar) : "memory");
+#else
+  if (valid) {
+    const unsigned dst = r.slot_s + 8u * (unsigned)(slot * SLOT) + 16u * (unsigned)r.g;
+#pragma unroll
+    for (int c = 0; c < (NA / 2 + G - 1) / G; ++c)
+      if (c * G + r.g < NA / 2)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * (unsigned)(c * G)), "l"(a + 2 * (c * G + r.g)) : "memory");
+#pragma unroll
+    for (int c = 0; c < (NB / 2 + G - 1) / G; ++c)
+      if (c * G + r.g < NB / 2)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 8u * NA + 16u * (unsigned)(c * G)), "l"(b + 2 * (c * G + r.g)) : "memory");
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+#else
+  if (valid && r.g == 0) {
+    double* d = r.base + slot * SLOT;
+    for (int i = 0; i < NA; ++i) d[i] = a[i];
+    for (int i = 0; i < NB; ++i) d[NA + i] = b[i];
+  }
+#endif
+}
+// The copies of slot `slot` have landed.  cp.async: all but the PENDING newest commit groups of this lane are
+// complete (the caller's next group barrier makes the other lanes' chunks visible); bulk: the slot's mbarrier
+// phase is complete (`par` holds one phase bit per slot).
+template <int PENDING>
+LM_HD void ring_wait(const Ring& r, int slot, unsigned& par, bool valid) {
+#if defined(__CUDA_ARCH__)
+#if defined(LMATO_RING_BULK)
+  if (!valid) return;
+  const unsigned bar = r.bar_s + 8u * (unsigned)slot;
+  const unsigned ph = (par >> slot) & 1u;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "RW%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra RD%=;\n\t"
+      "bra RW%=;\n\t"
+      "RD%=:\n\t"
+      "}" ::"r"(bar), "r"(ph) : "memory");
+  par ^= 1u << slot;
+#else
+  asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory");
+  (void)slot; (void)par; (void)valid; (void)r;
+#endif
+#else
+  (void)r; (void)slot; (void)par; (void)valid;
+#endif
 }
 // hint: bring the 128-byte lines of a record that a later stage of a stage-parallel loop will read into L2/L1
 template <int NDBL>
@@ -206,17 +296,6 @@ LM_HD void prefetch_rec(const double* p) {
 #if defined(__CUDA_ARCH__) && defined(LMATO_COOP_PREFETCH)
 #pragma unroll
   for (int i = 0; i < NDBL; i += 16) asm volatile("prefetch.global.L1 [%0];" ::"l"(p + i));
-#endif
-}
-LM_HD void rg_commit() {
-#if defined(__CUDA_ARCH__)
-  asm volatile("cp.async.commit_group;" ::: "memory");
-#endif
-}
-template <int PENDING>
-LM_HD void rg_wait() {
-#if defined(__CUDA_ARCH__)
-  asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory");
 #endif
 }
 
@@ -295,6 +374,7 @@ LM_SWEEP void coop_build(const Params& P, const Mesh& M, const Options& O, const
     build_stage<MOVE>(P, O, M.h[k] * P.T, P.mT * M.tau[k], tf, ls, x + X_Z, x[X_U], xm + X_Z, xm[X_U], x + X_LAM,
                       x[X_ZLA], x[X_ZUA], x[X_ZLU], x[X_ZUU], x[X_PP], x[X_PN], x[X_ZPP], x[X_ZPN], W.Mo(buf, k));
   }
+  ring_publish();
   Grp<GP>::sync(W.mask);
 }
 
@@ -352,21 +432,19 @@ LM_SWEEP bool coop_backward_seq(const Params& P, const Mesh& M, const Options& O
   double* tr2 = W.tiles() + SCR_TR1;    // 8 x 9 : Wt rows
   bool ok = true;
   double* ring = W.ring();
-  const RingRef rr = rg_ref(ring, g);
-  const double* pm = W.Mo(src, N) + 2 * g;     // next record to copy (this lane's first chunk), stepping down
-  int kn = N;
+  const Ring rg = ring_of(ring, W.bars(), g);
+  unsigned par = W.rpar;
+  int ki = N, kw = N;                          // next stage to issue / to wait for (descending)
 #pragma unroll
   for (int d = 0; d < RING_D - 1; ++d) {
-    if (kn >= 1) rg_copy<G, MR>(rr, (kn & (RING_D - 1)) * RING_SB, pm, g);
-    rg_commit();
-    --kn; pm -= MR;
+    ring_issue<G, RING_SB, MR, 0>(rg, ki & (RING_D - 1), W.Mo(src, ki), nullptr, ki >= 1);
+    --ki;
   }
-  rg_wait<RING_D - 2>();                       // stage N has landed; made visible by the barrier below
-  Grp<G>::sync(gm);
+  ring_wait<RING_D - 2>(rg, kw & (RING_D - 1), par, true); --kw;   // stage N has landed
+  if (!kRingBulk) Grp<G>::sync(gm);
   for (int k = N; k >= 1; --k) {
-    if (kn >= 1) rg_copy<G, MR>(rr, (kn & (RING_D - 1)) * RING_SB, pm, g);
-    rg_commit();
-    --kn; pm -= MR;
+    ring_issue<G, RING_SB, MR, 0>(rg, ki & (RING_D - 1), W.Mo(src, ki), nullptr, ki >= 1);
+    --ki;
     const double* m = ring + (k & (RING_D - 1)) * RING_SB;
     StageJac J;
     jac_load(m, J);
@@ -444,8 +522,9 @@ LM_SWEEP bool coop_backward_seq(const Params& P, const Mesh& M, const Options& O
 #pragma unroll
         for (int j = 0; j < 8; ++j) tr2[i * 9 + j] = Pr[r][j];
       }
-      rg_wait<RING_D - 2>();                   // the next stage's record has landed (this lane's chunks) ...
-      Grp<G>::sync(gm);                        // ... and, after the barrier, everyone's
+      ring_wait<RING_D - 2>(rg, kw & (RING_D - 1), par, kw >= 1);   // the next stage's record has landed ...
+      --kw;
+      Grp<G>::sync(gm);                                              // ... and is visible to every lane
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         const int i = g * R + r;
@@ -461,7 +540,8 @@ LM_SWEEP bool coop_backward_seq(const Params& P, const Mesh& M, const Options& O
         for (int j = 0; j < i; ++j) { const double v = 0.5 * (Pr[i % R][j] + Pr[j % R][i]); Pr[i % R][j] = v; Pr[j % R][i] = v; }
 #pragma unroll
       for (int j = 0; j < 8; ++j) w6[j] = Pr[6 % R][j];
-      rg_wait<RING_D - 2>();
+      ring_wait<RING_D - 2>(rg, kw & (RING_D - 1), par, kw >= 1);
+      --kw;
     }
     // ---- condense the move: it enters the u row (index 6) with coefficient 1 ----
     double wc6 = 0.0;
@@ -501,8 +581,16 @@ LM_SWEEP bool coop_backward_seq(const Params& P, const Mesh& M, const Options& O
       for (int j = 0; j < 8; ++j) Pr[r][j] = fma(-w6i, w6s[j], rs * Pr[r][j]);
       pr[r] = fma(-w6i, kff, rs * (gti - cw * wc));
     }
-    if (!ok) return false;
+    if (!ok) {
+      // wrong inertia: leave with the ring drained (every issued copy waited for), the caller retries with delta_w
+      if (kRingBulk) while (kw > ki && kw >= 1) { ring_wait<0>(rg, kw & (RING_D - 1), par, true); --kw; }
+      W.rpar = par;
+      ring_publish();
+      return false;
+    }
   }
+  W.rpar = par;
+  ring_publish();                              // K (and the kept rows) are read through the ring / by other lanes next
   // node 0: everything pinned except tf
   const double P77 = Grp<G>::bcast(gm, Pr[7 % R][7], 7 / R);
   const double p7 = Grp<G>::bcast(gm, pr[7 % R], 7 / R);
@@ -545,23 +633,21 @@ LM_SWEEP void coop_forward(const Params& P, const Mesh& M, const Options& O, con
   // ---- (1) ds_k = E_k^-1 (D ds_{k-1} + e_6 dv_k - c_k),  dv_k = k_k + K_k ds_{k-1} ----
   double ds[8] = {0, 0, 0, 0, 0, 0, 0, dtf};
   double* ring = W.ring();
-  const RingRef rr = rg_ref(ring, g);
+  const Ring rg = ring_of(ring, W.bars(), g);
+  unsigned par = W.rpar;
   if (g < G) {
-    const double* pm = W.Mo(src, 1) + 2 * g;
-    const double* pk = W.K(1) + 2 * g;
-    int kn = 1;
+    int ki = 1;
 #pragma unroll
     for (int d = 0; d < RING_D - 1; ++d) {
-      if (kn <= N) { rg_copy<G, M_Q>(rr, (kn & (RING_D - 1)) * RING_SF, pm, g); rg_copy<G, KR>(rr, (kn & (RING_D - 1)) * RING_SF + M_Q, pk, g); }
-      rg_commit();
-      ++kn; pm += MR; pk += KR;
+      ring_issue<G, RING_SF, M_Q, KR>(rg, ki & (RING_D - 1), W.Mo(src, ki), W.K(ki), ki <= N);
+      ++ki;
     }
     for (int k = 1; k <= N; ++k) {
-      if (kn <= N) { rg_copy<G, M_Q>(rr, (kn & (RING_D - 1)) * RING_SF, pm, g); rg_copy<G, KR>(rr, (kn & (RING_D - 1)) * RING_SF + M_Q, pk, g); }
-      rg_commit();
-      ++kn; pm += MR; pk += KR;
-      rg_wait<RING_D - 1>();
-      Grp<G>::sync(gm);
+      if (kRingBulk) Grp<G>::sync(gm);         // every lane is done with the slot that is re-filled now
+      ring_issue<G, RING_SF, M_Q, KR>(rg, ki & (RING_D - 1), W.Mo(src, ki), W.K(ki), ki <= N);
+      ++ki;
+      ring_wait<RING_D - 1>(rg, k & (RING_D - 1), par, true);
+      if (!kRingBulk) Grp<G>::sync(gm);        // the other lanes' chunks
       const double* m = ring + (k & (RING_D - 1)) * RING_SF;
       StageJac J;
       jac_load(m, J);
@@ -711,30 +797,29 @@ LM_SWEEP void coop_forward(const Params& P, const Mesh& M, const Options& O, con
   si.a_max = (rp.n > tau * rp.d) ? tau * rp.d / rp.n : 1.0;
   si.a_z = (rz.n > tau * rz.d) ? tau * rz.d / rz.n : 1.0;
   si.dphi = dphi; si.dxmax = dxmax;
+  ring_publish();                              // the H records travel through the ring next
   Grp<GP>::sync(pmk);
   // ---- (3) adjoint recursion, every lane of the sequential group ----
   double pin[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   double pimax = 0.0;
   if (VREC) {
+    W.rpar = par;
     W.pimax = Grp<GP>::max(pmk, pimax_par);
     return;
   }
   if (g < G) {
-  const double* pm = W.Mo(src, N) + 2 * g;
-  const double* ph = W.H(N) + 2 * g;
-  int kn = N;
+  int ki = N;
 #pragma unroll
   for (int d = 0; d < RING_D - 1; ++d) {
-    if (kn >= 1) { rg_copy<G, JR>(rr, (kn & (RING_D - 1)) * RING_SA, pm, g); rg_copy<G, HR>(rr, (kn & (RING_D - 1)) * RING_SA + JR, ph, g); }
-    rg_commit();
-    --kn; pm -= MR; ph -= HR;
+    ring_issue<G, RING_SA, JR, HR>(rg, ki & (RING_D - 1), W.Mo(src, ki), W.H(ki), ki >= 1);
+    --ki;
   }
   for (int k = N; k >= 1; --k) {
-    if (kn >= 1) { rg_copy<G, JR>(rr, (kn & (RING_D - 1)) * RING_SA, pm, g); rg_copy<G, HR>(rr, (kn & (RING_D - 1)) * RING_SA + JR, ph, g); }
-    rg_commit();
-    --kn; pm -= MR; ph -= HR;
-    rg_wait<RING_D - 1>();
-    Grp<G>::sync(gm);
+    if (kRingBulk) Grp<G>::sync(gm);
+    ring_issue<G, RING_SA, JR, HR>(rg, ki & (RING_D - 1), W.Mo(src, ki), W.H(ki), ki >= 1);
+    --ki;
+    ring_wait<RING_D - 1>(rg, k & (RING_D - 1), par, true);
+    if (!kRingBulk) Grp<G>::sync(gm);
     const double* m = ring + (k & (RING_D - 1)) * RING_SA;
     StageJac J;
     jac_load(m, J);
@@ -754,6 +839,7 @@ LM_SWEEP void coop_forward(const Params& P, const Mesh& M, const Options& O, con
     if (g == 0) { gg[7] = 0.0; stv<8>(W.D(k) + D_PI, gg); }
   }
   }
+  W.rpar = par;
   Grp<GP>::sync(pmk);
   W.pimax = GP > G ? Grp<GP>::bcast(pmk, pimax, 0) : pimax;
 }
@@ -949,6 +1035,7 @@ LM_SWEEP void coop_eval(const Params& P, const Mesh& M, const Options& O, const 
   t.sumlog = anybad ? -1e300 : sumlog;
   t.prim_inf = prim; t.dual_inf = dual; t.cmin = cmin; t.cmax = cmax; t.sum_lam = slam; t.sum_z = sz;
   if (anybad || !(theta == theta)) t.theta = 1e300;
+  ring_publish();                              // the M records of the trial point travel through the ring next
   Grp<GP>::sync(gm);
 }
 

@@ -221,7 +221,7 @@ extern "C" int hostsim_solve_coop(const double* raw14, int nt, const double* tim
   const bool DC = O.w_dcost > 0;
   std::vector<double> ws((size_t)coop::coop_doubles_per_problem(nt), 0.0);
   std::vector<double> scr(coop::SCR_DOUBLES, 0.0);
-  coop::Cws W{ws.data(), nt, scr.data(), 0, 1u, 1u, 0.0, 0.0, 0};
+  coop::Cws W{ws.data(), nt, scr.data(), 0, 1u, 1u, 0.0, 0.0, 0, 0u};
   IpmState S;
   ipm_begin(O, S);
   const bool vrec = getenv("VREC") != nullptr;     // the variant that keeps W_k, g_k instead of running the adjoint recursion
