@@ -938,6 +938,23 @@ lmato_status_t lmato_kernel_launches(lmato_handle* h, int64_t* n) {
   return LMATO_OK;
 }
 
+// What kind of memory a registered optional buffer (sensitivity output, start point) points at.  The device entry
+// point needs memory the kernel can address (device, managed, or pinned host memory); the host entry point needs
+// memory the host can address.  Answers true when the runtime cannot tell (plain host memory is "unregistered").
+static bool kernel_can_address(const void* p) {
+  if (!p) return true;
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged ||
+         (attr.type == cudaMemoryTypeHost && attr.devicePointer != nullptr);
+}
+static bool host_can_address(const void* p) {
+  if (!p) return true;
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { cudaGetLastError(); return true; }
+  return attr.type != cudaMemoryTypeDevice;
+}
+
 lmato_status_t lmato_solve_batch(lmato_handle* h, const double* params, int64_t B,
                                  double* out_traj, double* out_tf, double* out_final_mass,
                                  int32_t* out_status, int32_t* out_iters, double* out_kkt,
@@ -950,6 +967,11 @@ lmato_status_t lmato_solve_batch(lmato_handle* h, const double* params, int64_t 
     return LMATO_ERR_INVALID;
   }
   CUDA_TRY(cudaSetDevice(h->device));
+  if (!kernel_can_address(h->sens_out) || !kernel_can_address(h->guess_traj) || !kernel_can_address(h->guess_tf)) {
+    set_err("lmato_solve_batch: the registered sensitivity output / start point is not device-addressable memory "
+            "(lmato_solve_batch takes DEVICE pointers; use lmato_solve_batch_host for host buffers)");
+    return LMATO_ERR_INVALID;
+  }
   cudaStream_t st = (cudaStream_t)stream;
   // Every solve on a handle shares its workspace, work-queue counter and warm-start reference.  A solve issued on
   // a different stream than the previous one first waits (on the device) for that one to finish.
@@ -1094,6 +1116,11 @@ lmato_status_t lmato_solve_batch_host(lmato_handle* h, const double* params, int
   double* traj_alias = pinned_alias(out_traj);
   const size_t traj_n = out_traj ? (size_t)LMATO_NVAR * h->nt * (size_t)B : 0;
   const size_t traj_stage = traj_alias ? 0 : traj_n;
+  if (!host_can_address(h->sens_out) || !host_can_address(h->guess_traj) || !host_can_address(h->guess_tf)) {
+    set_err("lmato_solve_batch_host: the registered sensitivity output / start point is device memory "
+            "(lmato_solve_batch_host takes HOST pointers)");
+    return LMATO_ERR_INVALID;
+  }
   double* sens_host = h->sens_out;       // for this entry point the registered pointer is a HOST buffer
   const size_t sens_n = sens_host ? (size_t)LMATO_NSENS * (size_t)B : 0;
   // layout of d_out: traj (only when staged) | sens | tf | fmass | kkt | status | iters

@@ -293,3 +293,75 @@ extern "C" int hostsim_solve_colloc(const double* raw14, int nt, const double* t
   }
   return out.status;
 }
+
+// Batch warm start on the host (what lmato_solve_batch does on the device): the batch-mean problem is solved to
+// mu_ref by the cooperative sweeps without the move term and stored as the reference; every dispersed problem
+// then starts from it.  Returns the mean iteration count; used to study barrier-update strategies on the CPU.
+//   hostsim_warm_batch(nprob, nt, wdc, mu_ref, out_iters[nprob], out_status[nprob], out_tf[nprob])
+extern "C" double hostsim_warm_batch(int nprob, int nt, double wdc, double mu_ref, int* out_iters, int* out_status, double* out_tf) {
+  const int N = nt - 1;
+  std::vector<double> h(N + 1), tau(N + 1);
+  for (int k = 0; k <= N; ++k) { tau[k] = (double)k / N; h[k] = k ? tau[k] - tau[k - 1] : 0.0; }
+  Mesh M{N, h.data(), tau.data()};
+  Options O;
+  O.tol = 1e-10; O.mu_init = 0.1; O.obj_scale = 10.0; O.kappa_eps = 30.0; O.kappa_mu = 0.2; O.theta_mu = 1.5; O.theta_mu_warm = 2.0;
+  O.tau_min = 0.99; O.delta_c = 1e-8; O.tf_guess = 0.9; O.max_iter = 500; O.max_ls = 40; O.mu_min_factor = 1e-3; O.n_polish = 2;
+  O.w_dcost = wdc;
+  if (getenv("THMUW")) O.theta_mu_warm = atof(getenv("THMUW"));
+  if (getenv("KEPS")) O.kappa_eps = atof(getenv("KEPS"));
+  if (getenv("KMU")) O.kappa_mu = atof(getenv("KMU"));
+  if (getenv("NPOL")) O.n_polish = atoi(getenv("NPOL"));
+  if (getenv("MMF")) O.mu_min_factor = atof(getenv("MMF"));
+  std::mt19937_64 rng(11);
+  std::uniform_real_distribution<double> U(0.0, 1.0);
+  std::vector<Params> Ps;
+  double mean[6] = {0, 0, 0, 0, 0, 0};
+  for (int p = 0; p < nprob; ++p) {
+    double u[6];
+    for (int i = 0; i < 6; ++i) u[i] = (p == 0) ? 0.5 : U(rng);
+    const double Ft = 15346.0 * (1 + 0.02 * (2 * u[0] - 1));
+    const double Isp = 309.7 * (1 + 0.01 * (2 * u[1] - 1));
+    const double Mdot = (p == 0) ? 5.053 : Ft / (Isp * 9.807);
+    const double M0 = 4821.0 * (1 + 0.02 * (2 * u[2] - 1));
+    const double addm = 5e-4 * std::pow(2.0, 2 * u[3] - 1);
+    const double rp = 17703.0 * (1 + 0.10 * (2 * u[4] - 1));
+    const double ra = 88615.0 * (1 + 0.10 * (2 * u[5] - 1));
+    Ps.push_back(make_params(Ft, M0, Mdot, addm, rp, ra));
+    const double v[6] = {Ft, M0, Mdot, addm, rp, ra};
+    for (int i = 0; i < 6; ++i) mean[i] += v[i] / nprob;
+  }
+  std::vector<double> ws((size_t)coop::coop_doubles_per_problem(nt), 0.0), scr(coop::SCR_DOUBLES, 0.0);
+  std::vector<double> ref((size_t)dc::REF_ROWS * nt, 0.0);
+  coop::Cws W{ws.data(), nt, scr.data(), 0, 1u, 1u, 0.0, 0.0, 0, 0u};
+  {   // reference solve
+    Params Pm = make_params(mean[0], mean[1], mean[2], mean[3], mean[4], mean[5]);
+    Options R = O;
+    R.tol = 10.0 * mu_ref; R.mu_min_factor = 0.1; R.n_polish = 0; R.w_dcost = 0.0;
+    IpmState S;
+    ipm_begin(R, S);
+    SweepsCoop<1, 1, false, false>::guess(Pm, M, R, W, S.cur);
+    while (!ipm_iterate_t<SweepsCoop<1, 1, false, false>>(Pm, M, R, W, S)) {}
+    SolveOut out; ipm_result(S, out);
+    SweepsCoop<1, 1, false, false>::store_ref(Pm, M, W, out.cur, S.cur, S.ctl.mu, out.status == ST_CONVERGED, ref.data());
+  }
+  double itsum = 0;
+  for (int p = 0; p < nprob; ++p) {
+    IpmState S;
+    ipm_begin(O, S);
+    double mu0 = 0.0;
+    SolveOut out;
+    if (wdc > 0) {
+      SweepsCoop<1, 1, true, false>::load_ref(Ps[p], M, O, W, ref.data(), S.cur, &mu0);
+      S.warm = true; S.ctl.mu = mu0; S.ctl.tau = dmax(O.tau_min, 1.0 - mu0);
+      while (!ipm_iterate_t<SweepsCoop<1, 1, true, false>>(Ps[p], M, O, W, S)) {}
+    } else {
+      SweepsCoop<1, 1, false, false>::load_ref(Ps[p], M, O, W, ref.data(), S.cur, &mu0);
+      S.warm = true; S.ctl.mu = mu0; S.ctl.tau = dmax(O.tau_min, 1.0 - mu0);
+      while (!ipm_iterate_t<SweepsCoop<1, 1, false, false>>(Ps[p], M, O, W, S)) {}
+    }
+    ipm_result(S, out);
+    out_iters[p] = out.iters; out_status[p] = out.status; out_tf[p] = out.tf;
+    itsum += out.iters;
+  }
+  return itsum / nprob;
+}
