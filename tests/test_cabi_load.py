@@ -71,7 +71,8 @@ def test_argument_validation_without_gpu(built_lib):
     h = C.c_void_p()
     assert L.lmato_create(None, 0, 200, None, 2, 0) == 1
     assert L.lmato_create(C.byref(h), 0, 1, None, 2, 0) == 1          # nt < 2
-    assert L.lmato_create(C.byref(h), 0, 200, None, 3, 0) == 4        # NODES=3 unsupported on device
+    assert L.lmato_create(C.byref(h), 0, 200, None, 7, 0) == 1        # NODES outside GEKKO's 2..6 (LO:25)
+    assert L.lmato_create(C.byref(h), 0, 200, None, 3, 1) == 4        # NODES >= 3 with the circular model: unsupported
     assert L.lmato_create(C.byref(h), 0, 200, None, 2, 7) == 1        # unknown model
     assert L.lmato_solve_batch(None, None, 1, None, None, None, None, None, None, None) == 1
     assert L.lmato_destroy(None) == 0
