@@ -73,6 +73,18 @@ struct Params {
 // split every stage body into dozens of small basic blocks (one BSSY/BSYNC pair per rcp / rsqrt /
 // sincos), which starves the two warps per scheduler of instruction-level parallelism.  These
 // versions are straight-line code: hardware seed (MUFU) + Newton, or fdlibm's kernels.
+//
+// The polynomial coefficients of lm_sincos_small (k_sin.c, k_cos.c) and lm_log_pos (e_log.c) are
+// those of fdlibm, the Freely Distributable LIBM -- third-party, not from the reference repository.
+// Its notice, preserved as its licence asks:
+//   ====================================================
+//   Copyright (C) 1993 by Sun Microsystems, Inc. All rights reserved.
+//
+//   Developed at SunSoft, a Sun Microsystems, Inc. business.
+//   Permission to use, copy, modify, and distribute this
+//   software is freely granted, provided that this notice
+//   is preserved.
+//   ====================================================
 // ---------------------------------------------------------------------------------------
 LM_HD double lm_rcp(double x) {
 #if defined(__CUDA_ARCH__)

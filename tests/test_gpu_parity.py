@@ -87,6 +87,32 @@ def test_dispersions_match_golden(lm, golden_dir):
                        float(sol.tf[b]), float(sol.final_mass[b]), _traj(sol, b))
 
 
+def test_config3_matches_oracle_fixture(lm, golden_dir):
+    """Config 3 as BASELINE.json states it (1 024 dispersions over thrust, Isp, initial mass and the angular
+    acceleration limit): EVERY problem of the batch against the oracle's own solve of it -- tf, final mass and
+    all ten variables at every 20th node and the final node (tests/golden/make_golden.py --config3)."""
+    g = np.load(os.path.join(golden_dir, "elliptical_config3_disp1024_seed11_nt200.npz"))
+    B = g["tf"].size
+    p = lm.dispersed_params(B, seed=11, columns=(0, 1, 2, 3))
+    assert np.array_equal(p.rows(B).numpy(), g["rows"])
+    sol = lm.optimise_batch(p, options=lm.SolverOptions(dcost=0.0))
+    assert bool(sol.converged.all())
+    ok = g["kkt"] < 1e-9                      # oracle points that reached the fixture tolerance
+    assert ok.mean() > 0.99, ok.mean()
+    tf = sol.tf.cpu().numpy(); fm = sol.final_mass.cpu().numpy()
+    assert np.max(np.abs(tf - g["tf"])[ok] / g["tf"][ok]) < TF_RTOL
+    assert np.max(np.abs(fm - g["final_mass"])[ok] / g["final_mass"][ok]) < MASS_RTOL
+    traj = _traj(sol).transpose(1, 0, 2)[:, :, g["nodes"]]                 # [B, 10, kept nodes]
+    full = _traj(sol).transpose(1, 0, 2)
+    scale = np.abs(full).max(axis=2, keepdims=True) + 1e-300               # per problem and variable
+    err = (np.abs(traj - g["traj"]) / scale).max(axis=2)                   # [B, 10]
+    assert err[ok][:, :9].max() < STATE_RTOL, err[ok][:, :9].max(axis=0)
+    assert np.quantile(err[ok][:, 9], 0.99) < 5e-3                          # the MV on the singular arc (see CONTROL_RTOL)
+    # what is actually achieved on tf and final mass
+    assert np.max(np.abs(tf - g["tf"])[ok] / g["tf"][ok]) < 1e-7
+    assert np.max(np.abs(fm - g["final_mass"])[ok] / g["final_mass"][ok]) < 1e-7
+
+
 def _defects(lm, p, sol, nt):
     """Recompute the backward-Euler defects and terminal rows from the returned arrays."""
     rows = p.rows(len(sol))

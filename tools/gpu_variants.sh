@@ -5,6 +5,6 @@ cp $LIB /tmp/lib_keep.so
 for v in build_variants/*.so; do
   echo "== $v"
   cp $v $LIB
-  timeout 300 python tools/gpu_variant_probe.py 2>&1 | tail -6
+  timeout 300 python ${PROBE:-tools/gpu_variant_probe.py} 2>&1 | tail -6
 done
 cp /tmp/lib_keep.so $LIB
