@@ -334,6 +334,31 @@ def test_config5_dense_mesh_batch_properties(lm):
     assert abs(float(sol.tf_seconds[0]) - 435.1038) < 2e-3      # nominal on this mesh
 
 
+def test_config5_full_size(lm):
+    """Config 5 as BASELINE.json states it -- 4 096 problems on the nt = 2001 mesh, all six parameters
+    dispersed, the reference's objective (DCOST on) -- on one GPU: every problem converges and every returned
+    trajectory satisfies the transcribed equations, the terminal rows and the bounds (size-independent
+    properties; the oracle's general sparse LU does not finish this mesh)."""
+    B, nt = 4096, 2001
+    p = lm.dispersed_params(B, seed=11)
+    sol = lm.optimise_batch(p, lm.Mesh(nt=nt))
+    assert int((sol.status != 0).sum()) == 0, torch.bincount(sol.status.cpu().long())
+    assert float(sol.kkt_error.max()) <= 1e-8
+    defect, radius, speed, ortho = _defects(lm, p, sol, nt)
+    assert float(defect.max()) < 1e-9
+    assert float(radius.min()) > -1e-8 and float(radius.max()) < 1e-6
+    assert float(speed.min()) > -1e-8 and float(speed.max()) < 1e-6
+    assert float(ortho.abs().max()) < 1e-7
+    assert float(sol.states["angle"].min()) >= 0 and float(sol.states["angle"].max()) <= math.pi / 3
+    assert float(sol.control.abs().max()) <= 1.0 and float(sol.states["mass"].max()) <= 1.0
+    # problem 0 is the nominal case; the refined mesh approaches the continuous-time optimum from below
+    assert abs(float(sol.tf_seconds[0]) - 435.1038) < 2e-3
+    # the same 4 096 parameter sets on the nt = 200 mesh: refining the mesh moves every tf by the same small amount
+    coarse = lm.optimise_batch(p)
+    d = (sol.tf_seconds - coarse.tf_seconds).cpu()
+    assert float(d.min()) > 0.5 and float(d.max()) < 2.0, (float(d.min()), float(d.max()))
+
+
 def test_dcost_matches_golden(lm, golden_dir):
     """The NLP with the reference's move suppression (angledoubledot.DCOST = 1e-5, LO:99) -- the default,
     solved by the 8-state kernel -- against oracle fixtures that carry the term as slack pairs."""
