@@ -333,8 +333,8 @@ constexpr int kCoopG = 8;
 constexpr int kCoopScrStride = coop::SCR_DOUBLES;       // per group: record ring + transpose tiles (even: 16-byte aligned)
 static size_t coop_smem(int gp) { return sizeof(double) * (size_t)(kCoopBlock / gp) * kCoopScrStride; }
 
-template <int G>
-__device__ __noinline__ void coop_write_results(const KArgs& a, const Params& P, const coop::Cws& W, const IpmState& S, long b) {
+template <int G, class CW>
+__device__ __noinline__ void coop_write_results(const KArgs& a, const Params& P, const CW& W, const IpmState& S, long b) {
   SolveOut out;
   ipm_result(S, out);
   const int nt = a.N + 1;
@@ -426,8 +426,9 @@ __global__ void __launch_bounds__(kCoopBlock, BPS) ascent_coop_kernel(KArgs a) {
   const unsigned smask = ((1u << G) - 1u) << ((lane / GP) * GP);
   Params& P = sP[grp].p;
   const long slot = (long)blockIdx.x * GPB + grp;
-  const coop::Cws W{a.ws + slot * coop::coop_doubles_per_problem(a.N + 1), a.N + 1, sScr + grp * kCoopScrStride,
-                    lane % GP, gmask, smask, 0.0, 0.0, 0, 0u};
+  // workspace layout by regime (ascent_coop.cuh, CwsT): stage-major blocks when a whole warp walks one problem
+  const coop::CwsT<(GP == 32)> W{a.ws + slot * coop::coop_doubles_per_problem(a.N + 1), a.N + 1, sScr + grp * kCoopScrStride,
+                                 lane % GP, gmask, smask, 0.0, 0.0, 0, 0u};
   if (W.g == 0) coop::ring_init_barriers(W.bars());      // the mbarriers of this group's record ring
   __syncthreads();
   IpmState S;
