@@ -209,6 +209,9 @@ __device__ __noinline__ void write_results(const KArgs& a, const Params& P, cons
     // per unit of the RAW parameters of include/lmato_b200.h: M_dot = mflow * fuel_mass (LO:65),
     // angle_doubledot_max = 3 * angle_scalar (LO:109); tf in the reference's scaled units (0..1)
     const double inv = 1.0 / a.O.obj_scale;
+    // the mass bound 0 <= mass <= 1 (LO:83) is carried as tf <= tf_ub = 1 / (mflow T): where that is the binding
+    // upper bound on tf, its multiplier contributes  -zUt * d tf_ub / d mflow = zUt / (mflow^2 T)
+    if (P.tf_ub < 1.0) s_mf += S.cur.zUt / (P.mflow * P.mflow * P.T);
     a.sens[(long)LMATO_S_FT * B + b] = s_ft * inv;
     a.sens[(long)LMATO_S_M0 * B + b] = s_m0 * inv;
     a.sens[(long)LMATO_S_M_DOT * B + b] = s_mf * inv / P.fuel;
@@ -389,6 +392,7 @@ __device__ __noinline__ void coop_write_results(const KArgs& a, const Params& P,
   if (a.sens) {
     s_ft = coop::Grp<G>::sum(W.mask, s_ft); s_m0 = coop::Grp<G>::sum(W.mask, s_m0);
     s_mf = coop::Grp<G>::sum(W.mask, s_mf); s_asc = coop::Grp<G>::sum(W.mask, s_asc);
+    if (P.tf_ub < 1.0) s_mf += S.cur.zUt / (P.mflow * P.mflow * P.T);     // see write_results()
     if (W.g == 0) {
       const double inv = 1.0 / a.O.obj_scale;
       a.sens[(long)LMATO_S_FT * B + b] = s_ft * inv;

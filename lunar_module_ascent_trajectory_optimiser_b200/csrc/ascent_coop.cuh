@@ -452,6 +452,13 @@ LM_SWEEP bool coop_backward_seq(const Params& P, const Mesh& M, const Options& O
   }
   const double cw = ls ? 0.0 : 1.0;     // defects are dropped in the least-squares mode
   const double cp = P.coup5;
+  double rmask[R][8], rscale[R];        // rmask[r][j] = 1 if this lane's r-th row is row j;  D = diag(1,1,1,1,1,coup5,1,1)
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) rmask[r][j] = (g * R + r == j) ? 1.0 : 0.0;
+    rscale[r] = (g * R + r == 5) ? cp : 1.0;
+  }
   double* tr1 = W.tiles();              // 8 x 10: X rows with the affine part as ninth column
   double* tr2 = W.tiles() + SCR_TR1;    // 8 x 9 : Wt rows
   bool ok = true;
@@ -477,23 +484,23 @@ LM_SWEEP bool coop_backward_seq(const Params& P, const Mesh& M, const Options& O
     ldv<QR>(m + M_Q, q);
     const double dd = q[Q_D0] + dw;
     // ---- W = Q_k + P_k (owned rows), g = q_k + p_k ----
+    // Row i of the sparse Q_k is assembled with the lane's 0/1 row masks and FMAs: lane-dependent ternaries were
+    // compiled to divergent branches here (BSSY/BSYNC around partially active bodies, 11 % of the loop's stall
+    // samples on a single solve); masked FMAs are straight-line code on a pipe that is idle in this regime.
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      const int i = g * R + r;
-      // (selects, not branches: eight different branch bodies would serialise the lanes of the group)
-      const bool e0 = (i == 0), e2 = (i == 2), e4 = (i == 4), e7 = (i == 7);
-      Pr[r][0] += e0 ? q[Q_00] + dw : e2 ? q[Q_02] : e4 ? q[Q_04] : e7 ? q[Q_T0 + 0] : 0.0;
-      Pr[r][2] += e0 ? q[Q_02] : e2 ? q[Q_22] + dw : e4 ? q[Q_24] : e7 ? q[Q_T0 + 2] : 0.0;
-      Pr[r][4] += e0 ? q[Q_04] : e2 ? q[Q_24] : e4 ? q[Q_44] + dw : e7 ? q[Q_T0 + 4] : 0.0;
-      Pr[r][1] += (i == 1) ? dd : e7 ? q[Q_T0 + 1] : 0.0;
-      Pr[r][3] += (i == 3) ? dd : e7 ? q[Q_T0 + 3] : 0.0;
-      Pr[r][5] += (i == 5) ? dd : e7 ? q[Q_T0 + 5] : 0.0;
-      Pr[r][6] += (i == 6) ? q[Q_RU] + dw : e7 ? q[Q_T0 + 6] : 0.0;
-      double t7 = q[Q_77];
-#pragma unroll
-      for (int ii = 0; ii < 7; ++ii) t7 = (i == ii) ? q[Q_T0 + ii] : t7;
-      Pr[r][7] += t7;
-      pr[r] += e4 ? q[Q_G4A] + mu * q[Q_G4B] : (i == 6) ? q[Q_GUA] + mu * q[Q_GUB] : 0.0;
+      const double* mk = rmask[r];
+      const double q00 = q[Q_00] + dw, q22 = q[Q_22] + dw, q44 = q[Q_44] + dw, qru = q[Q_RU] + dw;
+      Pr[r][0] += mk[0] * q00 + mk[2] * q[Q_02] + (mk[4] * q[Q_04] + mk[7] * q[Q_T0 + 0]);
+      Pr[r][2] += mk[0] * q[Q_02] + mk[2] * q22 + (mk[4] * q[Q_24] + mk[7] * q[Q_T0 + 2]);
+      Pr[r][4] += mk[0] * q[Q_04] + mk[2] * q[Q_24] + (mk[4] * q44 + mk[7] * q[Q_T0 + 4]);
+      Pr[r][1] += mk[1] * dd + mk[7] * q[Q_T0 + 1];
+      Pr[r][3] += mk[3] * dd + mk[7] * q[Q_T0 + 3];
+      Pr[r][5] += mk[5] * dd + mk[7] * q[Q_T0 + 5];
+      Pr[r][6] += mk[6] * qru + mk[7] * q[Q_T0 + 6];
+      Pr[r][7] += (mk[0] * q[Q_T0 + 0] + mk[1] * q[Q_T0 + 1]) + (mk[2] * q[Q_T0 + 2] + mk[3] * q[Q_T0 + 3]) +
+                  ((mk[4] * q[Q_T0 + 4] + mk[5] * q[Q_T0 + 5]) + (mk[6] * q[Q_T0 + 6] + mk[7] * q[Q_77]));
+      pr[r] += mk[4] * (q[Q_G4A] + mu * q[Q_G4B]) + mk[6] * (q[Q_GUA] + mu * q[Q_GUB]);
     }
     if (VREC) {
       double* v = W.V(k);
@@ -591,14 +598,13 @@ LM_SWEEP bool coop_backward_seq(const Params& P, const Mesh& M, const Options& O
     // ---- P_{k-1} = D Wt D - (D w6)(D w6)^T / Ruu ,  p_{k-1} = D (g~ - Wt c) - D w6 ru / Ruu ----
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      const int i = g * R + r;
+      const double* mk = rmask[r];
       double wc = 0.0;
 #pragma unroll
       for (int j = 0; j < 6; ++j) wc = fma(Pr[r][j], c[j], wc);
-      double gti = gt[7];
-#pragma unroll
-      for (int ii = 0; ii < 7; ++ii) gti = (i == ii) ? gt[ii] : gti;
-      const double rs = (i == 5) ? cp : 1.0;
+      const double gti = (mk[0] * gt[0] + mk[1] * gt[1]) + (mk[2] * gt[2] + mk[3] * gt[3]) +
+                         ((mk[4] * gt[4] + mk[5] * gt[5]) + (mk[6] * gt[6] + mk[7] * gt[7]));
+      const double rs = rscale[r];
       const double w6i = rs * Pr[r][6];
       Pr[r][5] *= cp;
 #pragma unroll
