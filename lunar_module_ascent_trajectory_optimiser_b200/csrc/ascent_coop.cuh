@@ -684,9 +684,9 @@ LM_SWEEP void coop_forward(const Params& P, const Mesh& M, const Options& O, con
       double c[8], kk[KR];
       ldv<8>(m + M_C, c);
       ldv<KR>(m + M_Q, kk);
-    double dv = kk[K_FF];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) dv = fma(kk[i], ds[i], dv);
+    // (a tree, not a chain: the move heads the stage's dependency chain)
+    const double dv = ((kk[0] * ds[0] + kk[1] * ds[1]) + (kk[2] * ds[2] + kk[3] * ds[3])) +
+                      ((kk[4] * ds[4] + kk[5] * ds[5]) + (kk[6] * ds[6] + fma(kk[7], ds[7], kk[K_FF])));
     double xi[8];
 #pragma unroll
     for (int i = 0; i < 5; ++i) xi[i] = ds[i] - cw * c[i];
