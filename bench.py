@@ -40,8 +40,8 @@ METRIC = "converged ascent-NLP solves/sec at batch 64K"
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the `ncu --set full`
 # captures summarised under profiles/ (a profiler figure cannot be measured inside an un-profiled run): keyed
 # by (dcost on, problems in the launch, nt) and reported only when the run matches that workload, otherwise null.
-NCU_TRAFFIC = {(True, 65536, 200): (217.488e9 + 123.538e9, "profiles/r01_ncu_ascent_ipm_kernel_metrics.csv"),
-               (True, 4096, 2001): (595.341e9 + 270.463e9, "profiles/r02_ncu_ascent_coop_kernel_cfg5_metrics.csv")}
+NCU_TRAFFIC = {(True, 65536, 200): (217.761e9 + 123.660e9, "profiles/r02_ncu_ascent_ipm_kernel_metrics.csv"),
+               (True, 4096, 2001): (596.359e9 + 265.691e9, "profiles/r02_ncu_ascent_coop_kernel_cfg5_metrics.csv")}
 
 
 def bind_to_gpu_numa_node(index):
