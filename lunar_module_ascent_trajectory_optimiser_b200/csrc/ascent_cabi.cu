@@ -316,13 +316,8 @@ __global__ void __launch_bounds__(kBlock, kBlocksPerSM) ascent_ipm_kernel(KArgs 
         continue;
       }
       active = false;
-      if (a.ref_mode == 1) {
-        SolveOut out;
-        ipm_result(S, out);
-        SW::store_ref(P, M, W, out.cur, S.cur, S.ctl.mu, out.status == ST_CONVERGED, a.ref);
-        continue;
-      }
       pending = true;      // results are written when the whole chunk is done (see above)
+      // (the reference solve of the batch warm start, ref_mode 1, runs on the cooperative kernel)
     }
   }
 }

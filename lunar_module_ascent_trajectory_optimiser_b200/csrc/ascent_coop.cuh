@@ -1180,7 +1180,7 @@ LM_NOINLINE void coop_init_from_guess(const Params& P, const Mesh& M, const Opti
   Grp<G>::sync(W.mask);
 }
 
-// Reference column of the batch warm start, in the layout of ref_store() (ascent_ipm.cuh: the 17 rows of the
+// Reference column of the batch warm start, in the layout init_from_ref() reads (ascent_ipm.cuh: the 17 rows of the
 // 7-state iterate, then one row of scalars), so that both kernels can start from a reference produced here.
 template <int G, class CW>
 LM_NOINLINE void coop_store_ref(const Params& P, const Mesh& M, const CW& W, int src, const Scal& c, double mu, bool ok,

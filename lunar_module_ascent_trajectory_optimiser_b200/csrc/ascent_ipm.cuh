@@ -341,19 +341,62 @@ LM_HD GuessProfile guess_profile(const Params& P) {
   return g;
 }
 
-LM_NOINLINE void init_guess(const Params& P, const Mesh& M, const Options& O, const Ws& W, Scal& s) {
+// Row layout of an iterate in the workspace, for the start-point code shared by the 7-state sweeps (below) and
+// the 8-state sweeps with the move term (ascent_ipm_dc.cuh: Layout8).
+struct Layout7 {
+  enum : int { FZ = F_Z, FU = F_U, FLAM = F_LAM, NLAM = 6, FZLA = F_ZLA, FZUA = F_ZUA, FZLU = F_ZLU, FZUU = F_ZUU,
+               NITER = N_ITER, FDS = F_DS, FDU = F_DU, RSTEP = R_STEP, NSTEP = N_STEP,
+               MOVE = 0, FPP = 0, FPN = 0, FZPP = 0, FZPN = 0 };
+};
+
+// node 0 is pinned at zero (LO:145-151): its state / step rows are literal zeros so that the sweeps can read
+// "node k-1" without a special case at k = 1 (with the move term also MV(0) = 0)
+template <class L>
+LM_HD void start_zero_node0(const Ws& W) {
+  double* s0 = W.stage(0);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) { WS_AT(s0, L::FZ + i) = 0.0; WS_AT(s0, L::NITER + L::FZ + i) = 0.0; WS_AT(s0, L::FDS + i) = 0.0; }
+  if (L::MOVE) { WS_AT(s0, L::FU) = 0.0; WS_AT(s0, L::NITER + L::FU) = 0.0; WS_AT(s0, L::FDU) = 0.0; }
+}
+
+// start values of one stage: primal values as given, multipliers zero, bound multipliers 1 (an unbounded control
+// -- circular model -- starts exactly on the central path of its vacuous bounds), the move slack pair on its
+// central path for mu_init with lam_6 = 0 (z_p = z_n = w, p + n = t(v), p - n = v), step rows zero
+template <class L>
+LM_HD void start_store_stage(const Params& P, const Options& O, double* sp, const double* z6, double u, double u_prev) {
+#pragma unroll
+  for (int i = 0; i < 6; ++i) WS_AT(sp, L::FZ + i) = z6[i];
+  WS_AT(sp, L::FU) = u;
+#pragma unroll
+  for (int i = 0; i < L::NLAM; ++i) WS_AT(sp, L::FLAM + i) = 0.0;
+  WS_AT(sp, L::FZLA) = 1.0; WS_AT(sp, L::FZUA) = 1.0;
+  const bool bounded = L::MOVE || P.coup5 != 0.0;
+  WS_AT(sp, L::FZLU) = bounded ? 1.0 : O.mu_init / (u + P.u_ub);
+  WS_AT(sp, L::FZUU) = bounded ? 1.0 : O.mu_init / (P.u_ub - u);
+  if (L::MOVE) {
+    const double wd = O.w_dcost, v = u - u_prev;
+    const double tt = (O.mu_init + sqrt(O.mu_init * O.mu_init + wd * wd * v * v)) / wd;
+    WS_AT(sp, L::FPP) = 0.5 * (tt + v); WS_AT(sp, L::FPN) = 0.5 * (tt - v);
+    WS_AT(sp, L::FZPP) = wd; WS_AT(sp, L::FZPN) = wd;
+  }
+#pragma unroll
+  for (int i = 0; i < L::NSTEP; ++i) WS_AT(sp, L::RSTEP + i) = 0.0;
+}
+
+LM_HD void start_scalars(Scal& s, double tf0) {
+  s.tf = tf0;
+  s.zLt = 1.0; s.zUt = 1.0;
+  s.sg1 = 1e-2; s.sg2 = 1e-2; s.zs1 = 1.0; s.zs2 = 1.0; s.nu3 = 0.0;
+}
+
+template <class L>
+LM_HD void init_guess_t(const Params& P, const Mesh& M, const Options& O, const Ws& W, Scal& s) {
   const int N = M.N;
   const double tf0 = dmin(dmax(O.tf_guess, 1e-2 * P.tf_ub), 0.99 * P.tf_ub);
   const GuessProfile g = guess_profile(P);
-  double y = 0, vy = 0, x = 0, vx = 0, a = 0, w = 0, t_prev = 0;
+  double y = 0, vy = 0, x = 0, vx = 0, a = 0, w = 0, t_prev = 0, u_prev = 0;
   const double a_lo = 1e-2 * P.a_ub, a_hi = 0.99 * P.a_ub;
-  {
-    // node 0 is pinned at zero (LO:145-151): keep its state / step rows as literal zeros so that
-    // the sweeps can read "node k-1" without a special case at k = 1
-    double* s0 = W.stage(0);
-#pragma unroll
-    for (int i = 0; i < 6; ++i) { WS_AT(s0, F_Z + i) = 0.0; WS_AT(s0, N_ITER + F_Z + i) = 0.0; WS_AT(s0, F_DS + i) = 0.0; }
-  }
+  start_zero_node0<L>(W);
   for (int k = 1; k <= N; ++k) {
     const double t = M.tau[k] * tf0 * P.T;
     const double dt = t - t_prev;
@@ -380,24 +423,16 @@ LM_NOINLINE void init_guess(const Params& P, const Mesh& M, const Options& O, co
       yn = y + dt * vyn;  xn = x + dt * vxn;
     }
     y = yn; vy = vyn; x = xn; vx = vxn;
-    double* sp = W.stage(k);
-    WS_AT(sp, F_Z + 0) = y;  WS_AT(sp, F_Z + 1) = vy;
-    WS_AT(sp, F_Z + 2) = x;  WS_AT(sp, F_Z + 3) = vx;
-    WS_AT(sp, F_Z + 4) = ac; WS_AT(sp, F_Z + 5) = w;
-    WS_AT(sp, F_U) = u;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) WS_AT(sp, F_LAM + i) = 0.0;
-    WS_AT(sp, F_ZLA) = 1.0; WS_AT(sp, F_ZUA) = 1.0;
-    // an unbounded control (circular model) starts exactly on the central path of its vacuous bounds
-    WS_AT(sp, F_ZLU) = P.coup5 != 0.0 ? 1.0 : O.mu_init / (u + P.u_ub);
-    WS_AT(sp, F_ZUU) = P.coup5 != 0.0 ? 1.0 : O.mu_init / (P.u_ub - u);
-#pragma unroll
-    for (int i = 0; i < N_STEP; ++i) WS_AT(sp, R_STEP + i) = 0.0;
+    const double z6[6] = {y, vy, x, vx, ac, w};
+    start_store_stage<L>(P, O, W.stage(k), z6, u, u_prev);
+    u_prev = u;
     t_prev = t;
   }
-  s.tf = tf0;
-  s.zLt = 1.0; s.zUt = 1.0;
-  s.sg1 = 1e-2; s.sg2 = 1e-2; s.zs1 = 1.0; s.zs2 = 1.0; s.nu3 = 0.0;
+  start_scalars(s, tf0);
+}
+
+LM_NOINLINE void init_guess(const Params& P, const Mesh& M, const Options& O, const Ws& W, Scal& s) {
+  init_guess_t<Layout7>(P, M, O, W, s);
 }
 
 // Caller-supplied start point: trajectories in the OUTPUT layout of the solver,
@@ -413,35 +448,27 @@ struct GuessSrc {
 // The primal values are taken as given and only pushed into the interior of their bounds (IPOPT's
 // bound_push); multipliers and slacks start as in the cold start, so iteration 0 is again the
 // least-squares multiplier estimate.  Node 0 is pinned whatever the guess says (LO:145-151).
-LM_NOINLINE void init_from_guess(const Params& P, const Mesh& M, const Options& O, const Ws& W, const GuessSrc& G,
-                                 Scal& s) {
+template <class L>
+LM_HD void init_from_guess_t(const Params& P, const Mesh& M, const Options& O, const Ws& W, const GuessSrc& G, Scal& s) {
   const int N = M.N, nt = N + 1;
   const double tf0 = dmin(dmax(G.tf[G.b], 1e-2 * P.tf_ub), 0.99 * P.tf_ub);
   const double a_lo = 1e-2 * P.a_ub, a_hi = 0.99 * P.a_ub, u_hi = 0.99 * P.u_ub;
-  {
-    double* s0 = W.stage(0);
-#pragma unroll
-    for (int i = 0; i < 6; ++i) { WS_AT(s0, F_Z + i) = 0.0; WS_AT(s0, N_ITER + F_Z + i) = 0.0; WS_AT(s0, F_DS + i) = 0.0; }
-  }
+  start_zero_node0<L>(W);
+  double u_prev = 0.0;
   for (int k = 1; k <= N; ++k) {
-    double* sp = W.stage(k);
     const double u = dmin(dmax(G.at(GuessSrc::V_U, k, nt), -u_hi), u_hi);
-    WS_AT(sp, F_Z + 0) = G.at(GuessSrc::V_Y, k, nt);  WS_AT(sp, F_Z + 1) = G.at(GuessSrc::V_YDOT, k, nt);
-    WS_AT(sp, F_Z + 2) = G.at(GuessSrc::V_X, k, nt);  WS_AT(sp, F_Z + 3) = G.at(GuessSrc::V_XDOT, k, nt);
-    WS_AT(sp, F_Z + 4) = dmin(dmax(G.at(GuessSrc::V_ANGLE, k, nt), a_lo), a_hi);
-    WS_AT(sp, F_Z + 5) = G.at(GuessSrc::V_ANGLEDOT, k, nt);
-    WS_AT(sp, F_U) = u;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) WS_AT(sp, F_LAM + i) = 0.0;
-    WS_AT(sp, F_ZLA) = 1.0; WS_AT(sp, F_ZUA) = 1.0;
-    WS_AT(sp, F_ZLU) = P.coup5 != 0.0 ? 1.0 : O.mu_init / (u + P.u_ub);
-    WS_AT(sp, F_ZUU) = P.coup5 != 0.0 ? 1.0 : O.mu_init / (P.u_ub - u);
-#pragma unroll
-    for (int i = 0; i < N_STEP; ++i) WS_AT(sp, R_STEP + i) = 0.0;
+    const double z6[6] = {G.at(GuessSrc::V_Y, k, nt), G.at(GuessSrc::V_YDOT, k, nt), G.at(GuessSrc::V_X, k, nt),
+                          G.at(GuessSrc::V_XDOT, k, nt), dmin(dmax(G.at(GuessSrc::V_ANGLE, k, nt), a_lo), a_hi),
+                          G.at(GuessSrc::V_ANGLEDOT, k, nt)};
+    start_store_stage<L>(P, O, W.stage(k), z6, u, u_prev);
+    u_prev = u;
   }
-  s.tf = tf0;
-  s.zLt = 1.0; s.zUt = 1.0;
-  s.sg1 = 1e-2; s.sg2 = 1e-2; s.zs1 = 1.0; s.zs2 = 1.0; s.nu3 = 0.0;
+  start_scalars(s, tf0);
+}
+
+LM_NOINLINE void init_from_guess(const Params& P, const Mesh& M, const Options& O, const Ws& W, const GuessSrc& G,
+                                 Scal& s) {
+  init_from_guess_t<Layout7>(P, M, O, W, G, s);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -553,21 +580,7 @@ LM_HD void stage_hessian(const Params& P, const Accel1& f, const StageJac& J, do
 enum : int { REF_ROWS = N_ITER + 1, REF_OK = 0, REF_MU = 1, REF_S = 2, REF_TF = 3, REF_ZLT = 4, REF_ZUT = 5,
              REF_SG1 = 6, REF_SG2 = 7, REF_ZS1 = 8, REF_ZS2 = 9, REF_NU3 = 10, REF_NSCAL = 11 };
 
-// ref[(row * (N+1)) + k]
-LM_NOINLINE void ref_store(const Params& P, const Mesh& M, const Ws& W, int src, const Scal& c, double mu,
-                           bool ok, double* ref) {
-  const int N1 = M.N + 1;
-  for (int k = 1; k <= M.N; ++k) {
-    const double* sp = W.stage(k);
-#pragma unroll
-    for (int f = 0; f < N_ITER; ++f) ref[f * N1 + k] = WS_AT(sp, src * N_ITER + f);
-  }
-  double* sc = ref + N_ITER * N1;
-  sc[REF_OK] = ok ? 1.0 : 0.0; sc[REF_MU] = mu; sc[REF_S] = P.S; sc[REF_TF] = c.tf;
-  sc[REF_ZLT] = c.zLt; sc[REF_ZUT] = c.zUt; sc[REF_SG1] = c.sg1; sc[REF_SG2] = c.sg2;
-  sc[REF_ZS1] = c.zs1; sc[REF_ZS2] = c.zs2; sc[REF_NU3] = c.nu3;
-}
-
+// ref[(row * (N+1)) + k]; written by the cooperative kernel's reference solve (coop_store_ref)
 // Start point of one problem from the reference column (lengths are stored divided by the
 // reference's distance scale S_ref = r_periapsis, LO:107, so they are rescaled to this problem's).
 LM_NOINLINE bool init_from_ref(const Params& P, const Mesh& M, const Ws& W, const double* ref, Scal& s,
@@ -1259,8 +1272,6 @@ struct Sweeps7 {
   LM_HD static void guess_from(const Params& P, const Mesh& M, const Options& O, const Ws& W, const GuessSrc& G, Scal& s) {
     init_from_guess(P, M, O, W, G, s);
   }
-  LM_HD static void store_ref(const Params& P, const Mesh& M, const Ws& W, int src, const Scal& c, double mu, bool ok,
-                              double* ref) { ref_store(P, M, W, src, c, mu, ok, ref); }
   LM_HD static bool load_ref(const Params& P, const Mesh& M, const Options&, const Ws& W, const double* ref, Scal& s,
                              double* mu) {
     return init_from_ref(P, M, W, ref, s, mu);

@@ -82,103 +82,15 @@ LM_HD void solveET8(const StageJac& J, double* g) {
 }
 
 // ---------------------------------------------------------------------------------------
+// start points: the code shared with the 7-state sweeps (ascent_ipm.cuh: init_guess_t / init_from_guess_t), on
+// this layout
+struct Layout8 {
+  enum : int { FZ = F_Z, FU = F_U, FLAM = F_LAM, NLAM = 7, FZLA = F_ZLA, FZUA = F_ZUA, FZLU = F_ZLU, FZUU = F_ZUU,
+               NITER = N_ITER, FDS = F_DS, FDU = F_DU, RSTEP = R_STEP, NSTEP = N_STEP,
+               MOVE = 1, FPP = F_PP, FPN = F_PN, FZPP = F_ZPP, FZPN = F_ZPN };
+};
 LM_NOINLINE void init_guess(const Params& P, const Mesh& M, const Options& O, const Ws& W, Scal& s) {
-  const int N = M.N;
-  const double tf0 = dmin(dmax(O.tf_guess, 1e-2 * P.tf_ub), 0.99 * P.tf_ub);
-  const GuessProfile g = guess_profile(P);
-  double y = 0, vy = 0, x = 0, vx = 0, a = 0, w = 0, t_prev = 0, u_prev = 0;
-  const double a_lo = 1e-2 * P.a_ub, a_hi = 0.99 * P.a_ub;
-  {
-    double* s0 = W.stage(0);
-#pragma unroll
-    for (int i = 0; i < 6; ++i) { WS_AT(s0, F_Z + i) = 0.0; WS_AT(s0, N_ITER + F_Z + i) = 0.0; WS_AT(s0, F_DS + i) = 0.0; }
-    WS_AT(s0, F_U) = 0.0; WS_AT(s0, N_ITER + F_U) = 0.0; WS_AT(s0, F_DU) = 0.0;      // MV(0) = 0 is pinned
-  }
-  for (int k = 1; k <= N; ++k) {
-    const double t = M.tau[k] * tf0 * P.T;
-    const double dt = t - t_prev;
-    const double tm = 0.5 * (t + t_prev);
-    const double u = tm < g.t1 ? g.ulev : (tm < g.t1 + g.t2 ? -g.ulev : 0.0);
-    w += dt * P.asc * u;
-    a += dt * w;
-    const double ac = dmin(dmax(a, a_lo), a_hi);
-    const double m = P.mflow * P.T * M.tau[k] * tf0;
-    double yn = y + dt * vy, xn = x + dt * vx, vyn = vy, vxn = vx;
-    for (int itr = 0; itr < 3; ++itr) {
-      double ay, ax;
-      accel_value(P, yn, xn, ac, m, ay, ax);
-      vyn = vy + dt * ay; vxn = vx + dt * ax;
-      yn = y + dt * vyn;  xn = x + dt * vxn;
-    }
-    y = yn; vy = vyn; x = xn; vx = vxn;
-    double* sp = W.stage(k);
-    WS_AT(sp, F_Z + 0) = y;  WS_AT(sp, F_Z + 1) = vy;
-    WS_AT(sp, F_Z + 2) = x;  WS_AT(sp, F_Z + 3) = vx;
-    WS_AT(sp, F_Z + 4) = ac; WS_AT(sp, F_Z + 5) = w;
-    WS_AT(sp, F_U) = u;
-#pragma unroll
-    for (int i = 0; i < 7; ++i) WS_AT(sp, F_LAM + i) = 0.0;
-    WS_AT(sp, F_ZLA) = 1.0; WS_AT(sp, F_ZUA) = 1.0; WS_AT(sp, F_ZLU) = 1.0; WS_AT(sp, F_ZUU) = 1.0;
-    {
-      // slack pair on its central path for mu_init with lam_6 = 0:  z_p = z_n = w, p + n = t(v), p - n = v
-      const double wd = O.w_dcost, v = u - u_prev;
-      const double tt = (O.mu_init + sqrt(O.mu_init * O.mu_init + wd * wd * v * v)) / wd;
-      WS_AT(sp, F_PP) = 0.5 * (tt + v); WS_AT(sp, F_PN) = 0.5 * (tt - v);
-      WS_AT(sp, F_ZPP) = wd; WS_AT(sp, F_ZPN) = wd;
-      u_prev = u;
-    }
-#pragma unroll
-    for (int i = 0; i < N_STEP; ++i) WS_AT(sp, R_STEP + i) = 0.0;
-    t_prev = t;
-  }
-  s.tf = tf0;
-  s.zLt = 1.0; s.zUt = 1.0;
-  s.sg1 = 1e-2; s.sg2 = 1e-2; s.zs1 = 1.0; s.zs2 = 1.0; s.nu3 = 0.0;
-}
-
-LM_NOINLINE void ref_store(const Params& P, const Mesh& M, const Ws& W, int src, const Scal& c, double mu,
-                           bool ok, double* ref) {
-  const int N1 = M.N + 1;
-  for (int k = 1; k <= M.N; ++k) {
-    const double* sp = W.stage(k);
-#pragma unroll
-    for (int f = 0; f < N_ITER; ++f) ref[f * N1 + k] = WS_AT(sp, src * N_ITER + f);
-  }
-  double* sc = ref + N_ITER * N1;
-  sc[REF_OK] = ok ? 1.0 : 0.0; sc[REF_MU] = mu; sc[REF_S] = P.S; sc[REF_TF] = c.tf;
-  sc[REF_ZLT] = c.zLt; sc[REF_ZUT] = c.zUt; sc[REF_SG1] = c.sg1; sc[REF_SG2] = c.sg2;
-  sc[REF_ZS1] = c.zs1; sc[REF_ZS2] = c.zs2; sc[REF_NU3] = c.nu3;
-}
-
-LM_NOINLINE bool init_from_ref(const Params& P, const Mesh& M, const Ws& W, const double* ref, Scal& s,
-                               double* mu_out) {
-  const int N1 = M.N + 1;
-  const double* sc = ref + N_ITER * N1;
-  if (!(sc[REF_OK] > 0.5)) return false;
-  const double r = sc[REF_S] * P.Sinv, ri = P.S / sc[REF_S];
-  {
-    double* s0 = W.stage(0);
-#pragma unroll
-    for (int i = 0; i < 6; ++i) { WS_AT(s0, F_Z + i) = 0.0; WS_AT(s0, N_ITER + F_Z + i) = 0.0; WS_AT(s0, F_DS + i) = 0.0; }
-    WS_AT(s0, F_U) = 0.0; WS_AT(s0, N_ITER + F_U) = 0.0; WS_AT(s0, F_DU) = 0.0;
-  }
-  for (int k = 1; k <= M.N; ++k) {
-    double* sp = W.stage(k);
-#pragma unroll
-    for (int f = 0; f < N_ITER; ++f) {
-      double v = ref[f * N1 + k];
-      if (f < 4) v *= r;
-      else if (f >= F_LAM && f < F_LAM + 4) v *= ri;
-      WS_AT(sp, f) = v;
-    }
-#pragma unroll
-    for (int i = 0; i < N_STEP; ++i) WS_AT(sp, R_STEP + i) = 0.0;
-  }
-  s.tf = dmin(sc[REF_TF], 0.99 * P.tf_ub);
-  s.zLt = sc[REF_ZLT]; s.zUt = sc[REF_ZUT];
-  s.sg1 = sc[REF_SG1]; s.sg2 = sc[REF_SG2]; s.zs1 = sc[REF_ZS1]; s.zs2 = sc[REF_ZS2]; s.nu3 = sc[REF_NU3];
-  *mu_out = sc[REF_MU];
-  return true;
+  init_guess_t<Layout8>(P, M, O, W, s);
 }
 
 // Start from a reference column produced by the (cheaper) 7-state solve of the batch-mean problem without
@@ -230,40 +142,7 @@ LM_NOINLINE bool init_from_ref7(const Params& P, const Mesh& M, const Options& O
 // is put on its central path for the guess's control moves.
 LM_NOINLINE void init_from_guess(const Params& P, const Mesh& M, const Options& O, const Ws& W, const GuessSrc& G,
                                  Scal& s) {
-  const int N = M.N, nt = N + 1;
-  const double tf0 = dmin(dmax(G.tf[G.b], 1e-2 * P.tf_ub), 0.99 * P.tf_ub);
-  const double a_lo = 1e-2 * P.a_ub, a_hi = 0.99 * P.a_ub, u_hi = 0.99 * P.u_ub;
-  {
-    double* s0 = W.stage(0);
-#pragma unroll
-    for (int i = 0; i < 6; ++i) { WS_AT(s0, F_Z + i) = 0.0; WS_AT(s0, N_ITER + F_Z + i) = 0.0; WS_AT(s0, F_DS + i) = 0.0; }
-    WS_AT(s0, F_U) = 0.0; WS_AT(s0, N_ITER + F_U) = 0.0; WS_AT(s0, F_DU) = 0.0;
-  }
-  double u_prev = 0.0;
-  for (int k = 1; k <= N; ++k) {
-    double* sp = W.stage(k);
-    const double u = dmin(dmax(G.at(GuessSrc::V_U, k, nt), -u_hi), u_hi);
-    WS_AT(sp, F_Z + 0) = G.at(GuessSrc::V_Y, k, nt);  WS_AT(sp, F_Z + 1) = G.at(GuessSrc::V_YDOT, k, nt);
-    WS_AT(sp, F_Z + 2) = G.at(GuessSrc::V_X, k, nt);  WS_AT(sp, F_Z + 3) = G.at(GuessSrc::V_XDOT, k, nt);
-    WS_AT(sp, F_Z + 4) = dmin(dmax(G.at(GuessSrc::V_ANGLE, k, nt), a_lo), a_hi);
-    WS_AT(sp, F_Z + 5) = G.at(GuessSrc::V_ANGLEDOT, k, nt);
-    WS_AT(sp, F_U) = u;
-#pragma unroll
-    for (int i = 0; i < 7; ++i) WS_AT(sp, F_LAM + i) = 0.0;
-    WS_AT(sp, F_ZLA) = 1.0; WS_AT(sp, F_ZUA) = 1.0; WS_AT(sp, F_ZLU) = 1.0; WS_AT(sp, F_ZUU) = 1.0;
-    {
-      const double wd = O.w_dcost, v = u - u_prev;
-      const double tt = (O.mu_init + sqrt(O.mu_init * O.mu_init + wd * wd * v * v)) / wd;
-      WS_AT(sp, F_PP) = 0.5 * (tt + v); WS_AT(sp, F_PN) = 0.5 * (tt - v);
-      WS_AT(sp, F_ZPP) = wd; WS_AT(sp, F_ZPN) = wd;
-      u_prev = u;
-    }
-#pragma unroll
-    for (int i = 0; i < N_STEP; ++i) WS_AT(sp, R_STEP + i) = 0.0;
-  }
-  s.tf = tf0;
-  s.zLt = 1.0; s.zUt = 1.0;
-  s.sg1 = 1e-2; s.sg2 = 1e-2; s.zs1 = 1.0; s.zs2 = 1.0; s.nu3 = 0.0;
+  init_from_guess_t<Layout8>(P, M, O, W, G, s);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -897,8 +776,6 @@ struct Sweeps8 {
   LM_HD static void guess_from(const Params& P, const Mesh& M, const Options& O, const Ws& W, const GuessSrc& G, Scal& s) {
     dc::init_from_guess(P, M, O, W, G, s);
   }
-  LM_HD static void store_ref(const Params& P, const Mesh& M, const Ws& W, int src, const Scal& c, double mu, bool ok,
-                              double* ref) { dc::ref_store(P, M, W, src, c, mu, ok, ref); }
   LM_HD static bool load_ref(const Params& P, const Mesh& M, const Options& O, const Ws& W, const double* ref,
                              Scal& s, double* mu) {
     return dc::init_from_ref7(P, M, O, W, ref, s, mu);      // the reference is produced by the 7-state solve
