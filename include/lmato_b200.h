@@ -100,7 +100,9 @@ typedef struct {
                          starts from it. */
   double mu_ref;     /* barrier parameter at which the reference solve stops; default 1e-3 */
   double dcost;      /* LO:99 angledoubledot.DCOST: l1 move suppression dcost*sum|MV_k - MV_{k-1}|; default
-                        1e-5 (the reference's value); 0 switches the term off (7-state fast path) */
+                        1e-5 (the reference's value); 0 switches the term off (7-state fast path).  For
+                        LMATO_MODEL_CIRCULAR the MV is the pitch angle (PDF p.27 src 69-73, DCOST = 1e-5 there too);
+                        that model with the term runs on the cooperative kernel at every batch size */
   double kappa_eps;  /* barrier sub-problem tolerance factor (IPOPT barrier_tol_factor, default there 10): mu is
                         reduced once E_mu <= kappa_eps*mu; default 30 (2.4 fewer iterations, same answers) */
   int32_t objective_nodes; /* APMonitor sums the objective over the horizon: minimise objective_nodes*tf +

@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(256) mean_params_kernel(const double* __restri
   if (threadIdx.x == 0) out[row] = red[0] / (double)B;
 }
 
-__device__ __forceinline__ Params derive_params(const double* __restrict__ p, long B, long b, int model) {
+__device__ __forceinline__ Params derive_params(const double* __restrict__ p, long B, long b, int model, bool move = false) {
   // LO:50-75, 107-109
   Params P;
   const double G = p[LMATO_P_G * B + b], Mm = p[LMATO_P_M * B + b];
@@ -129,7 +129,7 @@ __device__ __forceinline__ Params derive_params(const double* __restrict__ p, lo
   if (model == LMATO_MODEL_CIRCULAR) {
     // PDF p.27 src 69-73: the MV is the pitch angle itself; no rate or acceleration limit exists
     P.coup5 = 0.0;
-    P.asc = 1.0;
+    P.asc = move ? 0.0 : 1.0;     // with the move term the MV slot holds the pitch angle itself (mv_is_angle())
     P.u_ub = 1e20;
   }
   return P;
@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(kCoopBlock, BPS) ascent_coop_kernel(KArgs a) {
       } else {
         b = (long)chunk * PPW + lane / GP;
         if (b < a.B) {
-          if (W.g == 0) P = derive_params(a.params, a.B, b, a.model);
+          if (W.g == 0) P = derive_params(a.params, a.B, b, a.model, MOVE);
           coop::Grp<GP>::sync(gmask);
           ipm_begin(O, S);
           double mu0 = 0.0;
@@ -869,9 +869,10 @@ lmato_status_t lmato_set_options(lmato_handle* h, const lmato_options* o) {
   return LMATO_OK;
 }
 
-// The move-suppression term (LO:99) applies to the MV angledoubledot of the elliptical model; the
-// circular model's MV is the angle itself and runs without it.
-static bool dcost_active(const lmato_handle* h) { return h->opt.dcost > 0.0 && h->model == LMATO_MODEL_ELLIPTICAL; }
+// The move-suppression term: DCOST on the MV angledoubledot of the elliptical model (LO:99), on the MV angle of the
+// circular model (PDF p.27 src 69-73).  The circular model with the term is carried by the cooperative kernel only.
+static bool dcost_active(const lmato_handle* h) { return h->opt.dcost > 0.0; }
+static bool circular_move(const lmato_handle* h) { return h->model == LMATO_MODEL_CIRCULAR && dcost_active(h); }
 
 // Which kernel solves a batch of B problems.  One thread per problem needs ~1 wave (SMs x 256 problems) to fill
 // the GPU and streams the least HBM traffic per problem; eight lanes per problem fill it with an eighth of that
@@ -879,6 +880,7 @@ static bool dcost_active(const lmato_handle* h) { return h->opt.dcost > 0.0 && h
 // between 16 384 and 32 768 problems (profiles/README.md).
 constexpr int64_t kCoopMaxBatch = 6144;
 static bool use_coop(const lmato_handle* h, int64_t B) {
+  if (circular_move(h)) return true;
   if (h->opt.kernel == LMATO_KERNEL_COOP) return true;
   if (h->opt.kernel == LMATO_KERNEL_THREAD) return false;
   return B <= kCoopMaxBatch;
@@ -986,7 +988,10 @@ lmato_status_t lmato_solve_batch(lmato_handle* h, const double* params, int64_t 
   const int gp = coop_gp_for(h, B);
   const long cgrid = coop_grid_for(h, B, gp);
   const bool use_dc = dcost_active(h) && !hi_order;   // the l1 move term is carried by the NODES = 2 kernels only
-  const bool warm = !hi_order && !h->guess_traj && (h->opt.warm_start == 2 || (h->opt.warm_start == 1 && B >= kWarmStartMinBatch));
+  // (no batch warm start for the circular model with its move term: the reference column of the 7-state solve
+  //  carries a different MV)
+  const bool warm = !hi_order && !h->guess_traj && !circular_move(h) &&
+                    (h->opt.warm_start == 2 || (h->opt.warm_start == 1 && B >= kWarmStartMinBatch));
   size_t need = ws_bytes_for(h, B);
   if (warm) { const size_t r = coop_ws_bytes(h, 1, 32); if (r > need) need = r; }     // the reference solve: one warp of one CTA
   if (need > h->ws_bytes) {

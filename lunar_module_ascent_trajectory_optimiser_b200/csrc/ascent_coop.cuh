@@ -43,7 +43,7 @@ enum : int {
   D_DS = 0 /* ds[0..5], du */, D_DV = 7, D_PI = 8 /* 7 */, DR = 16,
   // M record: stage Jacobian with its structured inverse, defects, Hessian and gradient pieces
   J_AL = 0, J_ALA, J_ALB, J_ALC, J_ALD, J_M11, J_M13, J_M31, J_M33, J_GA1, J_GA3,
-  J_E0, J_E1, J_E2, J_E3, J_E4, J_E5, J_BETA, JR = 20,
+  J_E0, J_E1, J_E2, J_E3, J_E4, J_E5, J_BETA, J_A46, JR = 20,
   M_J = 0, M_C = JR /* 6 defects */, M_Q = JR + 8,
   Q_00 = 0, Q_02, Q_22, Q_04, Q_24, Q_44, Q_T0 /* tf column, rows 0..6 */, Q_77 = Q_T0 + 7, Q_RU, Q_D0,
   Q_G4A, Q_G4B /* gradient of angle = A + mu*B */, Q_GUA, Q_GUB /* gradient of u */,
@@ -331,6 +331,35 @@ LM_HD void jac_load(const double* m, StageJac& J) {
   J.ga1 = j[J_GA1]; J.ga3 = j[J_GA3];
   J.e0 = j[J_E0]; J.e1 = j[J_E1]; J.e2 = j[J_E2]; J.e3 = j[J_E3]; J.e4 = j[J_E4]; J.e5 = j[J_E5];
   J.beta = j[J_BETA];
+  J.a46 = j[J_A46];
+}
+
+// E^{-1} v and E^{-T} g of the 8-state stage Jacobian (dc::solveE8 / dc::solveET8) with the extra entry
+// d defect_4 / d u = -a46 of the circular model with its move term (mv_is_angle(): angle_k - u_k = 0)
+LM_HD void solveE8x(const StageJac& J, double* v) {
+  const double v7 = v[7], v6 = v[6];
+  const double v5 = v[5] + J.beta * v6 + J.e5 * v7;
+  const double v4 = v[4] + J.al * v5 + J.a46 * v6 + J.e4 * v7;
+  const double r0 = fma(J.e0, v7, v[0]);
+  const double r2 = fma(J.e2, v7, v[2]);
+  const double r1 = v[1] + J.ga1 * v4 + J.e1 * v7;
+  const double r3 = v[3] + J.ga3 * v4 + J.e3 * v7;
+  const double t1 = r1 + J.ala * r0 + J.alb * r2;
+  const double t3 = r3 + J.alc * r0 + J.ald * r2;
+  const double v1 = J.m11 * t1 + J.m13 * t3;
+  const double v3 = J.m31 * t1 + J.m33 * t3;
+  v[0] = fma(J.al, v1, r0); v[1] = v1; v[2] = fma(J.al, v3, r2); v[3] = v3; v[4] = v4; v[5] = v5;
+}
+LM_HD void solveET8x(const StageJac& J, double* g) {
+  double w0 = g[0], w1 = g[1], w2 = g[2], w3 = g[3];
+  applyA11T(J, w0, w1, w2, w3);
+  const double gaw = J.ga1 * w1 + J.ga3 * w3;
+  const double gew = J.e0 * w0 + J.e1 * w1 + J.e2 * w2 + J.e3 * w3;
+  const double w4 = g[4] + gaw;
+  const double w5 = g[5] + J.al * w4;
+  const double w6 = g[6] + J.beta * w5 + J.a46 * w4;
+  const double w7 = g[7] + gew + J.e4 * w4 + J.e5 * w5;
+  g[0] = w0; g[1] = w1; g[2] = w2; g[3] = w3; g[4] = w4; g[5] = w5; g[6] = w6; g[7] = w7;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -349,12 +378,13 @@ LM_HD void build_stage(const Params& P, const Options& O, double kap, double tau
   StageJac J;
   stagejac_build(P, kap, tf, taum, f, z[1], z[3], z[5], u, J);
   stagejac_invert(J);
+  J.a46 = mv_is_angle(P);
   double j[JR];
   j[J_AL] = J.al; j[J_ALA] = J.ala; j[J_ALB] = J.alb; j[J_ALC] = J.alc; j[J_ALD] = J.ald;
   j[J_M11] = J.m11; j[J_M13] = J.m13; j[J_M31] = J.m31; j[J_M33] = J.m33;
   j[J_GA1] = J.ga1; j[J_GA3] = J.ga3;
   j[J_E0] = J.e0; j[J_E1] = J.e1; j[J_E2] = J.e2; j[J_E3] = J.e3; j[J_E4] = J.e4; j[J_E5] = J.e5;
-  j[J_BETA] = J.beta; j[18] = 0.0; j[19] = 0.0;
+  j[J_BETA] = J.beta; j[J_A46] = J.a46; j[19] = 0.0;
   stv<JR>(mrec + M_J, j);
   const double al = J.al;
   double c[8];
@@ -362,7 +392,7 @@ LM_HD void build_stage(const Params& P, const Options& O, double kap, double tau
   c[1] = z[1] - zp[1] - al * f.ay;
   c[2] = z[2] - zp[2] - al * z[3];
   c[3] = z[3] - zp[3] - al * f.ax;
-  c[4] = z[4] - zp[4] - al * z[5];
+  c[4] = z[4] - (1.0 - J.a46) * zp[4] - al * z[5] - J.a46 * u;      // (a46 = 1: angle_k - u_k = 0, angledot = 0)
   c[5] = z[5] - P.coup5 * zp[5] - J.beta * u;
   c[6] = 0.0; c[7] = 0.0;
   stv<8>(mrec + M_C, c);
@@ -451,13 +481,13 @@ LM_SWEEP bool coop_backward_seq(const Params& P, const Mesh& M, const Options& O
     }
   }
   const double cw = ls ? 0.0 : 1.0;     // defects are dropped in the least-squares mode
-  const double cp = P.coup5;
-  double rmask[R][8], rscale[R];        // rmask[r][j] = 1 if this lane's r-th row is row j;  D = diag(1,1,1,1,1,coup5,1,1)
+  const double cp = P.coup5, cq4 = 1.0 - mv_is_angle(P);
+  double rmask[R][8], rscale[R];        // rmask[r][j] = 1 if this lane's r-th row is row j;  D = diag(1,1,1,1,cq4,coup5,1,1)
 #pragma unroll
   for (int r = 0; r < R; ++r) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) rmask[r][j] = (g * R + r == j) ? 1.0 : 0.0;
-    rscale[r] = (g * R + r == 5) ? cp : 1.0;
+    rscale[r] = (g * R + r == 5) ? cp : (g * R + r == 4) ? cq4 : 1.0;
   }
   double* tr1 = W.tiles();              // 8 x 10: X rows with the affine part as ninth column
   double* tr2 = W.tiles() + SCR_TR1;    // 8 x 9 : Wt rows
@@ -513,7 +543,7 @@ LM_SWEEP bool coop_backward_seq(const Params& P, const Mesh& M, const Options& O
     }
     // ---- X = W E^-1 (row operation), transpose [X | g] across the group ----
 #pragma unroll
-    for (int r = 0; r < R; ++r) dc::solveET8(J, Pr[r]);
+    for (int r = 0; r < R; ++r) solveET8x(J, Pr[r]);
     double gt[8];
     if (G > 1) {
 #pragma unroll
@@ -542,8 +572,8 @@ LM_SWEEP bool coop_backward_seq(const Params& P, const Mesh& M, const Options& O
     }
     // ---- Wt = X^T E^-1,  g~ = E^-T g (every lane) ----
 #pragma unroll
-    for (int r = 0; r < R; ++r) dc::solveET8(J, Pr[r]);
-    dc::solveET8(J, gt);
+    for (int r = 0; r < R; ++r) solveET8x(J, Pr[r]);
+    solveET8x(J, gt);
     // ---- symmetrise; row 6 (= column 6) of Wt to every lane ----
     double w6[8];
     if (G > 1) {
@@ -583,7 +613,7 @@ LM_SWEEP bool coop_backward_seq(const Params& P, const Mesh& M, const Options& O
     const double ru = q[Q_MVA] + mu * q[Q_MVB] + rx6;
     if (!(Ruu > 0.0) || !(Ruu < 1e300)) ok = false;
     const double Rinv = lm_rcp(Ruu);
-    w6[5] *= cp;                          // d defect_k / d s_{k-1} = -D, D = diag(1,1,1,1,1,coup5,1,1)
+    w6[5] *= cp; w6[4] *= cq4;            // d defect_k / d s_{k-1} = -D, D = diag(1,1,1,1,cq4,coup5,1,1)
     double w6s[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) w6s[j] = w6[j] * Rinv;
@@ -606,7 +636,7 @@ LM_SWEEP bool coop_backward_seq(const Params& P, const Mesh& M, const Options& O
                          ((mk[4] * gt[4] + mk[5] * gt[5]) + (mk[6] * gt[6] + mk[7] * gt[7]));
       const double rs = rscale[r];
       const double w6i = rs * Pr[r][6];
-      Pr[r][5] *= cp;
+      Pr[r][5] *= cp; Pr[r][4] *= cq4;
 #pragma unroll
       for (int j = 0; j < 8; ++j) Pr[r][j] = fma(-w6i, w6s[j], rs * Pr[r][j]);
       pr[r] = fma(-w6i, kff, rs * (gti - cw * wc));
@@ -657,7 +687,7 @@ LM_SWEEP void coop_forward(const Params& P, const Mesh& M, const Options& O, con
   const unsigned gm = W.smask;       // sequential group
   const unsigned pmk = W.mask;       // parallel group
   const double cw = ls ? 0.0 : 1.0;
-  const double cp = P.coup5;
+  const double cp = P.coup5, cq4 = 1.0 - mv_is_angle(P);
   const double dw = W.dw;
   const double wdc = O.w_dcost;
   // ---- (1) ds_k = E_k^-1 (D ds_{k-1} + e_6 dv_k - c_k),  dv_k = k_k + K_k ds_{k-1} ----
@@ -689,11 +719,12 @@ LM_SWEEP void coop_forward(const Params& P, const Mesh& M, const Options& O, con
                       ((kk[4] * ds[4] + kk[5] * ds[5]) + (kk[6] * ds[6] + fma(kk[7], ds[7], kk[K_FF])));
     double xi[8];
 #pragma unroll
-    for (int i = 0; i < 5; ++i) xi[i] = ds[i] - cw * c[i];
+    for (int i = 0; i < 4; ++i) xi[i] = ds[i] - cw * c[i];
+    xi[4] = cq4 * ds[4] - cw * c[4];
     xi[5] = cp * ds[5] - cw * c[5];
     xi[6] = ds[6] + dv;
     xi[7] = dtf;
-    dc::solveE8(J, xi);
+    solveE8x(J, xi);
 #pragma unroll
     for (int i = 0; i < 7; ++i) ds[i] = xi[i];
       if (g == 0) {
@@ -763,7 +794,7 @@ LM_SWEEP void coop_forward(const Params& P, const Mesh& M, const Options& O, con
       gg[7] = 0.0;
       StageJac J;
       jac_load(W.Mo(src, k), J);
-      dc::solveET8(J, gg);
+      solveET8x(J, gg);
       gg[7] = 0.0;
       stv<8>(W.D(k) + D_PI, gg);
       if (ls) {
@@ -857,9 +888,10 @@ LM_SWEEP void coop_forward(const Params& P, const Mesh& M, const Options& O, con
     ldv<HR>(m + JR, h);
 #pragma unroll
     for (int i = 0; i < 7; ++i) gg[i] = pin[i] - h[i];
+    gg[4] = cq4 * pin[4] - h[4];
     gg[5] = cp * pin[5] - h[5];
     gg[7] = 0.0;
-    dc::solveET8(J, gg);
+    solveET8x(J, gg);
 #pragma unroll
     for (int i = 0; i < 7; ++i) pin[i] = gg[i];
     if (ls) {        // only the least-squares multiplier estimate looks at the size of the multipliers
@@ -889,7 +921,7 @@ LM_SWEEP void coop_eval(const Params& P, const Mesh& M, const Options& O, const 
   const double tf0 = c0.tf, dtf = ts.dtf;
   const double tf = tf0 + alpha * dtf;
   const double wdc = O.w_dcost;
-  const double cp = P.coup5;
+  const double cp = P.coup5, cq4 = 1.0 - mv_is_angle(P);
   t.tf = tf;
   // ---- terminal scalars of the trial point (every lane) ----
   t.sg1 = c0.sg1 + alpha * ts.dsg1;
@@ -1013,7 +1045,7 @@ LM_SWEEP void coop_eval(const Params& P, const Mesh& M, const Options& O, const 
     double res[7];
     applyET6(J, lam, res);
     res[4] += zua - zla;
-    res[6] = -J.beta * lam[5] + lam[6] - zlu + zuu;
+    res[6] = -J.beta * lam[5] - J.a46 * lam[4] + lam[6] - zlu + zuu;
     if (k == N) {
       Terminal T;
       terminal_eval(P, z[0], z[1], z[2], z[3], T);
@@ -1032,7 +1064,7 @@ LM_SWEEP void coop_eval(const Params& P, const Mesh& M, const Options& O, const 
 #pragma unroll
       for (int i = 0; i < 7; ++i) {
         const double ln = fma(alpha_lam, pn8[i] - xn[1 + i], xn[1 + i]);
-        res[i] -= (i == 5 ? cp : 1.0) * ln;
+        res[i] -= (i == 5 ? cp : i == 4 ? cq4 : 1.0) * ln;
       }
     }
 #pragma unroll
@@ -1135,8 +1167,8 @@ LM_NOINLINE void coop_init_guess(const Params& P, const Mesh& M, const Options& 
     } else {
       // circular model: pitch ramps linearly from ~34 deg (PDF p.21 Fig 9); angledot and u follow
       const double a_new = 0.2 + 0.45 * M.tau[k];
-      w = (a_new - a) / dt;
-      u = w / (dt * P.asc);
+      if (mv_is_angle(P) != 0.0) { w = 0.0; u = dmin(dmax(a_new, a_lo), a_hi); }    // the MV is the pitch angle
+      else { w = (a_new - a) / dt; u = w / (dt * P.asc); }
       a = a_new;
     }
     const double ac = dmin(dmax(a, a_lo), a_hi);
@@ -1168,12 +1200,14 @@ LM_NOINLINE void coop_init_from_guess(const Params& P, const Mesh& M, const Opti
   const double tf0 = dmin(dmax(Gs.tf[Gs.b], 1e-2 * P.tf_ub), 0.99 * P.tf_ub);
   const double a_lo = 1e-2 * P.a_ub, a_hi = 0.99 * P.a_ub, u_hi = 0.99 * P.u_ub;
   if (W.g == 0) coop_zero_node0(W);
+  const bool mva = mv_is_angle(P) != 0.0;       // the MV is the pitch angle: its slot follows the angle row
   for (int k = 1 + W.g; k <= N; k += G) {
-    const double u = dmin(dmax(Gs.at(GuessSrc::V_U, k, nt), -u_hi), u_hi);
-    const double up = k > 1 ? dmin(dmax(Gs.at(GuessSrc::V_U, k - 1, nt), -u_hi), u_hi) : 0.0;
+    const double ak = dmin(dmax(Gs.at(GuessSrc::V_ANGLE, k, nt), a_lo), a_hi);
+    const double u = mva ? ak : dmin(dmax(Gs.at(GuessSrc::V_U, k, nt), -u_hi), u_hi);
+    const double up = k > 1 ? (mva ? dmin(dmax(Gs.at(GuessSrc::V_ANGLE, k - 1, nt), a_lo), a_hi)
+                                   : dmin(dmax(Gs.at(GuessSrc::V_U, k - 1, nt), -u_hi), u_hi)) : 0.0;
     const double z6[6] = {Gs.at(GuessSrc::V_Y, k, nt), Gs.at(GuessSrc::V_YDOT, k, nt), Gs.at(GuessSrc::V_X, k, nt),
-                          Gs.at(GuessSrc::V_XDOT, k, nt), dmin(dmax(Gs.at(GuessSrc::V_ANGLE, k, nt), a_lo), a_hi),
-                          Gs.at(GuessSrc::V_ANGLEDOT, k, nt)};
+                          Gs.at(GuessSrc::V_XDOT, k, nt), ak, mva ? 0.0 : Gs.at(GuessSrc::V_ANGLEDOT, k, nt)};
     coop_store_start(P, O, W, k, z6, u, up, MOVE);
   }
   coop_start_scalars(s, tf0);

@@ -61,10 +61,17 @@ struct Params {
   // coup5 = 0: the circular "IB-document" model (PDF p.27 src 69-73), where the pitch angle itself
   // is the MV: the angledot row loses its link to the previous node (angledot_k = beta*u_k with u
   // unbounded), which makes angle_k = angle_{k-1} + alpha*angledot_k a free variable per step.
+  // coup5 = 0 AND asc = 0: the circular model WITH its move-suppression term (PDF p.27 src 69-73: DCOST on the
+  // MV `angle`), cooperative kernel only: the MV slot of the 8-state formulation IS the pitch angle
+  // (angle_k - u_k = 0 instead of angle_k - angle_{k-1} - alpha*angledot_k = 0, angledot pinned at 0), so that the
+  // slack pair of the move u_k - u_{k-1} carries |angle_k - angle_{k-1}|.  See mv_is_angle().
   double coup5;
   double mT;      // mflow * T: mass(tau) = mT * tau * tf (LO:123); read per stage, kept here so that it is a
                   // shared-memory load and not a spilled register
 };
+
+// 1 in the circular model with the move term (the MV slot holds the pitch angle), else 0
+LM_HD double mv_is_angle(const Params& P) { return (P.coup5 == 0.0 && P.asc == 0.0) ? 1.0 : 0.0; }
 
 // ---------------------------------------------------------------------------------------
 // Branch-free FP64 math for the inner loops.  Every argument in the sweeps is a normal, positive,

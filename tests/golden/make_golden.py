@@ -69,7 +69,7 @@ def main():
              final_mass=np.array(fms), traj=np.stack(trajs), names=np.array(VAR_ROWS))
 
 
-if __name__ == "__main__" and not any(a in sys.argv for a in ("--dense", "--dcost", "--sens", "--nodes", "--config3")):
+if __name__ == "__main__" and not any(a in sys.argv for a in ("--dense", "--dcost", "--sens", "--nodes", "--config3", "--circular-dcost")):
     main()
 
 
@@ -205,3 +205,23 @@ def config3(B=1024, stride=20):
 
 if __name__ == "__main__" and "--config3" in sys.argv:
     config3()
+
+
+def circular_dcost():
+    """The circular IB-document model WITH its move suppression (PDF p.27 src 69-73: DCOST = 1e-5 on the MV `angle`),
+    objective summed over the nt-1 steps as for the elliptical model."""
+    import dataclasses
+    p = dataclasses.replace(AscentParams.circular(), dcost=1e-5)
+    nlp = AscentNLP(p, nt=200, obj_scale=10.0)
+    r = solve_ipm(nlp, nlp.initial_guess(0.9), IPMOptions(tol=1e-12, max_iter=500))
+    assert r.status == 0 or r.kkt_error < 1e-9, (r.status, r.kkt_error)
+    nv = nlp.node_values(r.x)
+    names = [n for n in VAR_ROWS if n in nv]
+    np.savez(os.path.join(HERE, "circular_dcost1e-5_nt200.npz"), tf=nv["tf"], final_mass=p.M0 - p.fuel_mass * nv["mass"][-1],
+             traj=np.stack([nv[n] for n in names]), names=np.array(names), iters=r.iterations, kkt=r.kkt_error,
+             dcost=1e-5, objective_nodes=199)
+    print("circular with DCOST: tf_s", nv["tf"] * 470, "iters", r.iterations, "kkt", r.kkt_error)
+
+
+if __name__ == "__main__" and "--circular-dcost" in sys.argv:
+    circular_dcost()

@@ -122,6 +122,18 @@ def test_cooperative_sweeps_source_matches_goldens_and_thread_sweeps(hostsim, mo
     monkeypatch.setenv("CIRCULAR", "1")
     raw = NOMINAL.copy(); raw[8] = raw[9] = 53108.4; raw[11] = 2576.0
     both(raw, float(g["tf"]))
+    # the circular model WITH its move suppression (PDF p.27 src 69-73: DCOST = 1e-5 on the MV `angle`): the MV slot
+    # of the 8-state cooperative sweeps holds the pitch angle; the oracle carries the term as slack pairs on the MV
+    g = np.load(os.path.join(GOLDEN, "circular_dcost1e-5_nt200.npz"))
+    monkeypatch.setenv("WDC", repr(10.0 * 1e-5 / 199)); monkeypatch.setenv("NPOL", "2")
+    st, tf, it, traj = _solve(hostsim, raw, fn="hostsim_solve_coop")
+    assert st == 0 and abs(tf - float(g["tf"])) / float(g["tf"]) < 1e-10
+    names = list(g["names"])
+    for n in names:
+        ref = g["traj"][names.index(n)]
+        mine = traj[["y", "ydot", "ydoubledot", "x", "xdot", "xdoubledot", "angle", "angledot", "mass"].index(n)]
+        assert np.abs(mine - ref).max() / np.abs(ref).max() < 1e-7, n
+    assert np.array_equal(traj[9], traj[6]) and np.abs(traj[7]).max() == 0.0     # MV slot == angle, angledot pinned at 0
 
 
 def test_higher_order_collocation_source_matches_goldens(hostsim):

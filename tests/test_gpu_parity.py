@@ -4,6 +4,7 @@ Tolerances are north_star's: tf within 1e-4 relative, final mass within 1e-6 rel
 mesh-node state within 1e-4 (relative to that state's largest magnitude on the trajectory).
 The solver is in fact much closer than that; the tighter asserts below document by how much.
 """
+import dataclasses
 import math
 import os
 
@@ -249,6 +250,18 @@ def test_circular_model_matches_golden_and_pdf(lm, golden_dir):
     tf = 0.92616537474 (435.2977 s)."""
     g = np.load(os.path.join(golden_dir, "circular_nominal_nt200.npz"))
     names = list(g["names"])
+    # with the model's own move suppression (PDF p.27 src 69-73: DCOST = 1e-5 on the MV `angle`; the default) against
+    # the oracle fixture that carries the term as slack pairs, and without it against the plain fixture
+    gd = np.load(os.path.join(golden_dir, "circular_dcost1e-5_nt200.npz"))
+    for params, gold in ((lm.AscentParams.circular(), gd), (dataclasses.replace(lm.AscentParams.circular(), dcost=0.0), g)):
+        s2 = lm.optimise(params, lm.Mesh(nt=200))
+        assert s2.status == 0 and abs(s2.tf - float(gold["tf"])) / float(gold["tf"]) < 1e-10
+        gn = list(gold["names"])
+        for n in s2.states:
+            ref = gold["traj"][gn.index(n)]
+            assert np.abs(s2.states[n].numpy() - ref).max() / np.abs(ref).max() < 1e-6, (params.dcost, n)
+        ref = gold["traj"][gn.index("angle")]
+        assert np.abs(s2.control.numpy() - ref).max() / np.abs(ref).max() < 1e-6, params.dcost
     sol = lm.optimise(lm.AscentParams.circular(), lm.Mesh(nt=200))
     assert sol.status == 0
     assert abs(sol.tf - float(g["tf"])) / float(g["tf"]) < 1e-9

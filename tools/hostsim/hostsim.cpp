@@ -219,6 +219,7 @@ extern "C" int hostsim_solve_coop(const double* raw14, int nt, const double* tim
   P.tf_ub = std::fmin(1.0, 1.0 / (P.mflow * P.T)); P.fuel = r[6]; P.Sinv = 1.0 / P.S; P.coup5 = 1.0; P.mT = P.mflow * P.T;
   if (getenv("CIRCULAR")) { P.coup5 = 0.0; P.asc = 1.0; P.u_ub = 1e20; }
   const bool DC = O.w_dcost > 0;
+  if (getenv("CIRCULAR") && DC) P.asc = 0.0;       // the circular model with its move term: the MV slot is the pitch angle
   std::vector<double> ws((size_t)coop::coop_doubles_per_problem(nt), 0.0);
   std::vector<double> scr(coop::SCR_DOUBLES, 0.0);
   coop::Cws W{ws.data(), nt, scr.data(), 0, 1u, 1u, 0.0, 0.0, 0, 0u};
