@@ -406,7 +406,7 @@ __device__ __noinline__ void coop_write_results(const KArgs& a, const Params& P,
 //   GP = 32: the whole warp works on one problem (the stage-parallel phases are four times shorter), for
 //            the latency regime: up to a few problems per SM.
 //   BPS = CTAs per SM: 1 leaves 255 registers per thread (no spills), 2 halves them for twice the problems in flight.
-template <int G, int GP, bool MOVE, int BPS>
+template <int G, int GP, int MOVE, int BPS>      // MOVE: 0 no move term, 1 move term (LO:99), 2 the circular model's (MV = angle)
 __global__ void __launch_bounds__(kCoopBlock, BPS) ascent_coop_kernel(KArgs a) {
   using SW = SweepsCoop<G, GP, MOVE>;
   constexpr int PPW = 32 / GP;                 // problems per warp
@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(kCoopBlock, BPS) ascent_coop_kernel(KArgs a) {
       } else {
         b = (long)chunk * PPW + lane / GP;
         if (b < a.B) {
-          if (W.g == 0) P = derive_params(a.params, a.B, b, a.model, MOVE);
+          if (W.g == 0) P = derive_params(a.params, a.B, b, a.model, MOVE == 2);
           coop::Grp<GP>::sync(gmask);
           ipm_begin(O, S);
           double mu0 = 0.0;
@@ -495,15 +495,18 @@ __global__ void __launch_bounds__(kCoopBlock, BPS) ascent_coop_kernel(KArgs a) {
 }
 
 template <int GP, int BPS>
-static void coop_launch(bool move, long grid, cudaStream_t st, const KArgs& a) {
-  if (move) ascent_coop_kernel<kCoopG, GP, true, BPS><<<(int)grid, kCoopBlock, coop_smem(GP), st>>>(a);
-  else ascent_coop_kernel<kCoopG, GP, false, BPS><<<(int)grid, kCoopBlock, coop_smem(GP), st>>>(a);
+static void coop_launch(int move, long grid, cudaStream_t st, const KArgs& a) {
+  if (move == 2) ascent_coop_kernel<kCoopG, GP, 2, BPS><<<(int)grid, kCoopBlock, coop_smem(GP), st>>>(a);
+  else if (move == 1) ascent_coop_kernel<kCoopG, GP, 1, BPS><<<(int)grid, kCoopBlock, coop_smem(GP), st>>>(a);
+  else ascent_coop_kernel<kCoopG, GP, 0, BPS><<<(int)grid, kCoopBlock, coop_smem(GP), st>>>(a);
 }
 template <int GP, int BPS>
 static cudaError_t coop_optin() {
-  cudaError_t e = cudaFuncSetAttribute(ascent_coop_kernel<kCoopG, GP, true, BPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coop_smem(GP));
+  cudaError_t e = cudaFuncSetAttribute(ascent_coop_kernel<kCoopG, GP, 2, BPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coop_smem(GP));
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(ascent_coop_kernel<kCoopG, GP, false, BPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coop_smem(GP));
+  e = cudaFuncSetAttribute(ascent_coop_kernel<kCoopG, GP, 1, BPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coop_smem(GP));
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(ascent_coop_kernel<kCoopG, GP, 0, BPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coop_smem(GP));
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1046,7 +1049,7 @@ lmato_status_t lmato_solve_batch(lmato_handle* h, const double* params, int64_t 
     r.ref = h->d_ref; r.ref_mode = 1;
     r.O.tol = 10.0 * h->opt.mu_ref; r.O.mu_min_factor = 0.1; r.O.n_polish = 0;
     r.O.w_dcost = 0.0;
-    coop_launch<32, 1>(false, 1, st, r);
+    coop_launch<32, 1>(0, 1, st, r);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemsetAsync(h->d_counter, 0, sizeof(int), st));
     a.ref = h->d_ref; a.ref_mode = 2;
@@ -1060,8 +1063,9 @@ lmato_status_t lmato_solve_batch(lmato_handle* h, const double* params, int64_t 
     else ascent_colloc_kernel<8><<<cg, kCoopBlock, 0, st>>>(a);
   } else if (coopk) {
     const int bps = coop_bps_for(h, B, gp);
-    if (gp == 32) { if (bps == 1) coop_launch<32, 1>(use_dc, cgrid, st, a); else coop_launch<32, 2>(use_dc, cgrid, st, a); }
-    else          { if (bps == 1) coop_launch<8, 1>(use_dc, cgrid, st, a); else coop_launch<8, 2>(use_dc, cgrid, st, a); }
+    const int mv = !use_dc ? 0 : circular_move(h) ? 2 : 1;
+    if (gp == 32) { if (bps == 1) coop_launch<32, 1>(mv, cgrid, st, a); else coop_launch<32, 2>(mv, cgrid, st, a); }
+    else          { if (bps == 1) coop_launch<8, 1>(mv, cgrid, st, a); else coop_launch<8, 2>(mv, cgrid, st, a); }
   } else {
     const int grid = (int)(slots / kBlock);
     if (use_dc) ascent_ipm_kernel<Sweeps8><<<grid, kBlock, kTileSmem, st>>>(a);

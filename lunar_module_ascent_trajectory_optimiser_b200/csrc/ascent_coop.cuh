@@ -43,7 +43,7 @@ enum : int {
   D_DS = 0 /* ds[0..5], du */, D_DV = 7, D_PI = 8 /* 7 */, DR = 16,
   // M record: stage Jacobian with its structured inverse, defects, Hessian and gradient pieces
   J_AL = 0, J_ALA, J_ALB, J_ALC, J_ALD, J_M11, J_M13, J_M31, J_M33, J_GA1, J_GA3,
-  J_E0, J_E1, J_E2, J_E3, J_E4, J_E5, J_BETA, J_A46, JR = 20,
+  J_E0, J_E1, J_E2, J_E3, J_E4, J_E5, J_BETA, JR = 20,
   M_J = 0, M_C = JR /* 6 defects */, M_Q = JR + 8,
   Q_00 = 0, Q_02, Q_22, Q_04, Q_24, Q_44, Q_T0 /* tf column, rows 0..6 */, Q_77 = Q_T0 + 7, Q_RU, Q_D0,
   Q_G4A, Q_G4B /* gradient of angle = A + mu*B */, Q_GUA, Q_GUB /* gradient of u */,
@@ -331,15 +331,18 @@ LM_HD void jac_load(const double* m, StageJac& J) {
   J.ga1 = j[J_GA1]; J.ga3 = j[J_GA3];
   J.e0 = j[J_E0]; J.e1 = j[J_E1]; J.e2 = j[J_E2]; J.e3 = j[J_E3]; J.e4 = j[J_E4]; J.e5 = j[J_E5];
   J.beta = j[J_BETA];
-  J.a46 = j[J_A46];
 }
 
-// E^{-1} v and E^{-T} g of the 8-state stage Jacobian (dc::solveE8 / dc::solveET8) with the extra entry
-// d defect_4 / d u = -a46 of the circular model with its move term (mv_is_angle(): angle_k - u_k = 0)
+// MOVE as a template argument of the sweeps: 0 no move term (u is free per stage), 1 the move term on the MV
+// angledoubledot (LO:99), 2 the move term of the circular model, where the MV slot IS the pitch angle (mv_is_angle()).
+// E^{-1} v and E^{-T} g of the 8-state stage Jacobian (dc::solveE8 / dc::solveET8); MVA: with the extra entry
+// d defect_4 / d u = -1 of that last case (angle_k - u_k = 0), a compile-time flag so that it costs the other
+// cases nothing on their dependency chains.
+template <bool MVA>
 LM_HD void solveE8x(const StageJac& J, double* v) {
   const double v7 = v[7], v6 = v[6];
   const double v5 = v[5] + J.beta * v6 + J.e5 * v7;
-  const double v4 = v[4] + J.al * v5 + J.a46 * v6 + J.e4 * v7;
+  const double v4 = (MVA ? v[4] + v6 : v[4]) + J.al * v5 + J.e4 * v7;
   const double r0 = fma(J.e0, v7, v[0]);
   const double r2 = fma(J.e2, v7, v[2]);
   const double r1 = v[1] + J.ga1 * v4 + J.e1 * v7;
@@ -350,6 +353,7 @@ LM_HD void solveE8x(const StageJac& J, double* v) {
   const double v3 = J.m31 * t1 + J.m33 * t3;
   v[0] = fma(J.al, v1, r0); v[1] = v1; v[2] = fma(J.al, v3, r2); v[3] = v3; v[4] = v4; v[5] = v5;
 }
+template <bool MVA>
 LM_HD void solveET8x(const StageJac& J, double* g) {
   double w0 = g[0], w1 = g[1], w2 = g[2], w3 = g[3];
   applyA11T(J, w0, w1, w2, w3);
@@ -357,7 +361,7 @@ LM_HD void solveET8x(const StageJac& J, double* g) {
   const double gew = J.e0 * w0 + J.e1 * w1 + J.e2 * w2 + J.e3 * w3;
   const double w4 = g[4] + gaw;
   const double w5 = g[5] + J.al * w4;
-  const double w6 = g[6] + J.beta * w5 + J.a46 * w4;
+  const double w6 = (MVA ? g[6] + w4 : g[6]) + J.beta * w5;
   const double w7 = g[7] + gew + J.e4 * w4 + J.e5 * w5;
   g[0] = w0; g[1] = w1; g[2] = w2; g[3] = w3; g[4] = w4; g[5] = w5; g[6] = w6; g[7] = w7;
 }
@@ -368,7 +372,7 @@ LM_HD void solveET8x(const StageJac& J, double* g) {
 // consumers, so a record stays valid when mu or delta_w change.  ls: the least-squares multiplier
 // estimate of IPOPT section 3.6 (Hessian := I, gradient := grad f - zL + zU), as in stage_hessian().
 // ---------------------------------------------------------------------------------------
-template <bool MOVE>
+template <int MOVE>
 LM_HD void build_stage(const Params& P, const Options& O, double kap, double taum, double tf, bool ls,
                        const double* z, double u, const double* zp, double up, const double* lam,
                        double zla, double zua, double zlu, double zuu,
@@ -378,13 +382,12 @@ LM_HD void build_stage(const Params& P, const Options& O, double kap, double tau
   StageJac J;
   stagejac_build(P, kap, tf, taum, f, z[1], z[3], z[5], u, J);
   stagejac_invert(J);
-  J.a46 = mv_is_angle(P);
   double j[JR];
   j[J_AL] = J.al; j[J_ALA] = J.ala; j[J_ALB] = J.alb; j[J_ALC] = J.alc; j[J_ALD] = J.ald;
   j[J_M11] = J.m11; j[J_M13] = J.m13; j[J_M31] = J.m31; j[J_M33] = J.m33;
   j[J_GA1] = J.ga1; j[J_GA3] = J.ga3;
   j[J_E0] = J.e0; j[J_E1] = J.e1; j[J_E2] = J.e2; j[J_E3] = J.e3; j[J_E4] = J.e4; j[J_E5] = J.e5;
-  j[J_BETA] = J.beta; j[J_A46] = J.a46; j[19] = 0.0;
+  j[J_BETA] = J.beta; j[18] = 0.0; j[19] = 0.0;
   stv<JR>(mrec + M_J, j);
   const double al = J.al;
   double c[8];
@@ -392,7 +395,8 @@ LM_HD void build_stage(const Params& P, const Options& O, double kap, double tau
   c[1] = z[1] - zp[1] - al * f.ay;
   c[2] = z[2] - zp[2] - al * z[3];
   c[3] = z[3] - zp[3] - al * f.ax;
-  c[4] = z[4] - (1.0 - J.a46) * zp[4] - al * z[5] - J.a46 * u;      // (a46 = 1: angle_k - u_k = 0, angledot = 0)
+  c[4] = (MOVE == 2) ? z[4] - u - al * z[5]                  // the MV slot is the angle: angle_k - u_k = 0 (angledot = 0)
+                     : z[4] - zp[4] - al * z[5];
   c[5] = z[5] - P.coup5 * zp[5] - J.beta * u;
   c[6] = 0.0; c[7] = 0.0;
   stv<8>(mrec + M_C, c);
@@ -418,7 +422,7 @@ LM_HD void build_stage(const Params& P, const Options& O, double kap, double tau
 }
 
 // (re)build the M records of buffer `buf` from its X records (start point; least-squares phase)
-template <int GP, bool MOVE, class CW>
+template <int GP, int MOVE, class CW>
 LM_SWEEP void coop_build(const Params& P, const Mesh& M, const Options& O, const CW& W, int buf, double tf, bool ls) {
   const int N = M.N;
   for (int k = 1 + W.g; k <= N; k += GP) {
@@ -451,7 +455,7 @@ LM_SWEEP void coop_build(const Params& P, const Mesh& M, const Options& O, const
 // pi_k = -E_k^-T (W_k ds_k + g_k)  -- a stage-parallel product in forward() -- instead of the sequential adjoint
 // recursion: one of the three sequential sweeps per iteration disappears, for 1.1 KB more traffic per stage.
 // Used where the sequential sweeps are the critical path (a warp per problem), not where HBM traffic counts.
-template <int G, bool MOVE, bool VREC, class CW>
+template <int G, int MOVE, bool VREC, class CW>
 LM_SWEEP bool coop_backward_seq(const Params& P, const Mesh& M, const Options& O, const CW& W, int src,
                                 const Scal& c0, double mu, double dw, bool ls, double* dtf_out) {
   constexpr int R = 8 / G;
@@ -481,7 +485,7 @@ LM_SWEEP bool coop_backward_seq(const Params& P, const Mesh& M, const Options& O
     }
   }
   const double cw = ls ? 0.0 : 1.0;     // defects are dropped in the least-squares mode
-  const double cp = P.coup5, cq4 = 1.0 - mv_is_angle(P);
+  const double cp = P.coup5, cq4 = (MOVE == 2) ? 0.0 : 1.0;
   double rmask[R][8], rscale[R];        // rmask[r][j] = 1 if this lane's r-th row is row j;  D = diag(1,1,1,1,cq4,coup5,1,1)
 #pragma unroll
   for (int r = 0; r < R; ++r) {
@@ -543,7 +547,7 @@ LM_SWEEP bool coop_backward_seq(const Params& P, const Mesh& M, const Options& O
     }
     // ---- X = W E^-1 (row operation), transpose [X | g] across the group ----
 #pragma unroll
-    for (int r = 0; r < R; ++r) solveET8x(J, Pr[r]);
+    for (int r = 0; r < R; ++r) solveET8x<(MOVE == 2)>(J, Pr[r]);
     double gt[8];
     if (G > 1) {
 #pragma unroll
@@ -572,8 +576,8 @@ LM_SWEEP bool coop_backward_seq(const Params& P, const Mesh& M, const Options& O
     }
     // ---- Wt = X^T E^-1,  g~ = E^-T g (every lane) ----
 #pragma unroll
-    for (int r = 0; r < R; ++r) solveET8x(J, Pr[r]);
-    solveET8x(J, gt);
+    for (int r = 0; r < R; ++r) solveET8x<(MOVE == 2)>(J, Pr[r]);
+    solveET8x<(MOVE == 2)>(J, gt);
     // ---- symmetrise; row 6 (= column 6) of Wt to every lane ----
     double w6[8];
     if (G > 1) {
@@ -613,7 +617,7 @@ LM_SWEEP bool coop_backward_seq(const Params& P, const Mesh& M, const Options& O
     const double ru = q[Q_MVA] + mu * q[Q_MVB] + rx6;
     if (!(Ruu > 0.0) || !(Ruu < 1e300)) ok = false;
     const double Rinv = lm_rcp(Ruu);
-    w6[5] *= cp; w6[4] *= cq4;            // d defect_k / d s_{k-1} = -D, D = diag(1,1,1,1,cq4,coup5,1,1)
+    w6[5] *= cp; if (MOVE == 2) w6[4] = 0.0;            // d defect_k / d s_{k-1} = -D, D = diag(1,1,1,1,cq4,coup5,1,1)
     double w6s[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) w6s[j] = w6[j] * Rinv;
@@ -636,7 +640,7 @@ LM_SWEEP bool coop_backward_seq(const Params& P, const Mesh& M, const Options& O
                          ((mk[4] * gt[4] + mk[5] * gt[5]) + (mk[6] * gt[6] + mk[7] * gt[7]));
       const double rs = rscale[r];
       const double w6i = rs * Pr[r][6];
-      Pr[r][5] *= cp; Pr[r][4] *= cq4;
+      Pr[r][5] *= cp; if (MOVE == 2) Pr[r][4] = 0.0;
 #pragma unroll
       for (int j = 0; j < 8; ++j) Pr[r][j] = fma(-w6i, w6s[j], rs * Pr[r][j]);
       pr[r] = fma(-w6i, kff, rs * (gti - cw * wc));
@@ -660,7 +664,7 @@ LM_SWEEP bool coop_backward_seq(const Params& P, const Mesh& M, const Options& O
 }
 
 // the G lanes of the sequential group factorise; the result goes to all GP lanes of the group
-template <int G, int GP, bool MOVE, bool VREC, class CW>
+template <int G, int GP, int MOVE, bool VREC, class CW>
 LM_SWEEP bool coop_backward(const Params& P, const Mesh& M, const Options& O, const CW& W, int src,
                             const Scal& c0, double mu, double dw, bool ls, double* dtf_out) {
   W.dw = dw;
@@ -679,7 +683,7 @@ LM_SWEEP bool coop_backward(const Params& P, const Mesh& M, const Options& O, co
 // ratios, merit slope, and the right-hand sides Q_k ds_k + q_k of the adjoint recursion; (3) the adjoint
 // recursion E_k^T pi_k = D pi_{k+1} - (Q_k ds_k + q_k) for the new defect multipliers.
 // ---------------------------------------------------------------------------------------
-template <int G, int GP, bool MOVE, bool VREC, class CW>
+template <int G, int GP, int MOVE, bool VREC, class CW>
 LM_SWEEP void coop_forward(const Params& P, const Mesh& M, const Options& O, const CW& W, int src,
                            const Scal& c0, double mu, double tau, double dtf, bool ls, TermStep& ts, StepInfo& si) {
   const int N = M.N;
@@ -687,7 +691,7 @@ LM_SWEEP void coop_forward(const Params& P, const Mesh& M, const Options& O, con
   const unsigned gm = W.smask;       // sequential group
   const unsigned pmk = W.mask;       // parallel group
   const double cw = ls ? 0.0 : 1.0;
-  const double cp = P.coup5, cq4 = 1.0 - mv_is_angle(P);
+  const double cp = P.coup5, cq4 = (MOVE == 2) ? 0.0 : 1.0;
   const double dw = W.dw;
   const double wdc = O.w_dcost;
   // ---- (1) ds_k = E_k^-1 (D ds_{k-1} + e_6 dv_k - c_k),  dv_k = k_k + K_k ds_{k-1} ----
@@ -720,11 +724,11 @@ LM_SWEEP void coop_forward(const Params& P, const Mesh& M, const Options& O, con
     double xi[8];
 #pragma unroll
     for (int i = 0; i < 4; ++i) xi[i] = ds[i] - cw * c[i];
-    xi[4] = cq4 * ds[4] - cw * c[4];
+    xi[4] = (MOVE == 2 ? 0.0 : ds[4]) - cw * c[4];
     xi[5] = cp * ds[5] - cw * c[5];
     xi[6] = ds[6] + dv;
     xi[7] = dtf;
-    solveE8x(J, xi);
+    solveE8x<(MOVE == 2)>(J, xi);
 #pragma unroll
     for (int i = 0; i < 7; ++i) ds[i] = xi[i];
       if (g == 0) {
@@ -794,7 +798,7 @@ LM_SWEEP void coop_forward(const Params& P, const Mesh& M, const Options& O, con
       gg[7] = 0.0;
       StageJac J;
       jac_load(W.Mo(src, k), J);
-      solveET8x(J, gg);
+      solveET8x<(MOVE == 2)>(J, gg);
       gg[7] = 0.0;
       stv<8>(W.D(k) + D_PI, gg);
       if (ls) {
@@ -888,10 +892,10 @@ LM_SWEEP void coop_forward(const Params& P, const Mesh& M, const Options& O, con
     ldv<HR>(m + JR, h);
 #pragma unroll
     for (int i = 0; i < 7; ++i) gg[i] = pin[i] - h[i];
-    gg[4] = cq4 * pin[4] - h[4];
+    gg[4] = (MOVE == 2 ? 0.0 : pin[4]) - h[4];
     gg[5] = cp * pin[5] - h[5];
     gg[7] = 0.0;
-    solveET8x(J, gg);
+    solveET8x<(MOVE == 2)>(J, gg);
 #pragma unroll
     for (int i = 0; i < 7; ++i) pin[i] = gg[i];
     if (ls) {        // only the least-squares multiplier estimate looks at the size of the multipliers
@@ -911,7 +915,7 @@ LM_SWEEP void coop_forward(const Params& P, const Mesh& M, const Options& O, con
 // KKT-error terms, and the M records of the trial point (the model of the next Newton system).
 // The per-stage arithmetic is that of dc::eval_pass.
 // ---------------------------------------------------------------------------------------
-template <int GP, bool MOVE, class CW>
+template <int GP, int MOVE, class CW>
 LM_SWEEP void coop_eval(const Params& P, const Mesh& M, const Options& O, const CW& W, int src, int dst,
                         const Scal& c0, const TermStep& ts, double mu, double alpha, double alpha_z,
                         double alpha_lam, Scal& t) {
@@ -921,7 +925,7 @@ LM_SWEEP void coop_eval(const Params& P, const Mesh& M, const Options& O, const 
   const double tf0 = c0.tf, dtf = ts.dtf;
   const double tf = tf0 + alpha * dtf;
   const double wdc = O.w_dcost;
-  const double cp = P.coup5, cq4 = 1.0 - mv_is_angle(P);
+  const double cp = P.coup5, cq4 = (MOVE == 2) ? 0.0 : 1.0;
   t.tf = tf;
   // ---- terminal scalars of the trial point (every lane) ----
   t.sg1 = c0.sg1 + alpha * ts.dsg1;
@@ -1045,7 +1049,7 @@ LM_SWEEP void coop_eval(const Params& P, const Mesh& M, const Options& O, const 
     double res[7];
     applyET6(J, lam, res);
     res[4] += zua - zla;
-    res[6] = -J.beta * lam[5] - J.a46 * lam[4] + lam[6] - zlu + zuu;
+    res[6] = -J.beta * lam[5] - (MOVE == 2 ? lam[4] : 0.0) + lam[6] - zlu + zuu;
     if (k == N) {
       Terminal T;
       terminal_eval(P, z[0], z[1], z[2], z[3], T);
@@ -1148,7 +1152,7 @@ LM_HD void coop_start_scalars(Scal& s, double tf0) {
 }
 
 // the bang-bang roll-out of init_guess() (ascent_ipm.cuh); a sequential integration, carried by every lane
-template <int G, bool MOVE, class CW>
+template <int G, int MOVE, class CW>
 LM_NOINLINE void coop_init_guess(const Params& P, const Mesh& M, const Options& O, const CW& W, Scal& s) {
   const int N = M.N;
   const double tf0 = dmin(dmax(O.tf_guess, 1e-2 * P.tf_ub), 0.99 * P.tf_ub);
@@ -1193,7 +1197,7 @@ LM_NOINLINE void coop_init_guess(const Params& P, const Mesh& M, const Options& 
 }
 
 // caller-supplied start point (init_from_guess(), ascent_ipm.cuh), stage-parallel
-template <int G, bool MOVE, class CW>
+template <int G, int MOVE, class CW>
 LM_NOINLINE void coop_init_from_guess(const Params& P, const Mesh& M, const Options& O, const CW& W, const GuessSrc& Gs,
                                       Scal& s) {
   const int N = M.N, nt = N + 1;
@@ -1240,7 +1244,7 @@ LM_NOINLINE void coop_store_ref(const Params& P, const Mesh& M, const CW& W, int
 
 // start from the reference column (dc::init_from_ref7): the slack pair is put on its central path for the
 // reference's moves and the multiplier of the u row follows from dual feasibility
-template <int G, bool MOVE, class CW>
+template <int G, int MOVE, class CW>
 LM_NOINLINE bool coop_load_ref(const Params& P, const Mesh& M, const Options& O, const CW& W, const double* ref,
                                Scal& s, double* mu_out) {
   const int N1 = M.N + 1;
@@ -1287,7 +1291,7 @@ LM_NOINLINE bool coop_load_ref(const Params& P, const Mesh& M, const Options& O,
 // Sweeps policy of the cooperative formulation for the IPM driver (ipm_iterate_t).
 //   G  lanes carry the sequential phases (cost-to-go distributed by rows: 8/G rows per lane),
 //   GP lanes (a multiple of G, at most a warp) carry the stage-parallel phases of the same problem.
-template <int G, int GP, bool MOVE, bool VREC = (GP > G)>
+template <int G, int GP, int MOVE, bool VREC = (GP > G)>
 struct SweepsCoop {
   enum : int { LANES_PER_PROBLEM = GP };
   template <class CW>

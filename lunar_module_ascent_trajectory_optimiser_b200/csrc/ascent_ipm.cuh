@@ -241,7 +241,6 @@ struct StageJac {
   double ga1, ga3;            // alpha * (ay_a, ax_a)
   double e0, e1, e2, e3, e4, e5;  // tf column (negated entries of E)
   double beta;                // alpha * asc
-  double a46;                 // -d defect_4 / d u: 0, or 1 where the MV slot is the pitch angle (cooperative kernel only)
 };
 
 LM_HD void stagejac_build(const Params& P, double kap, double tf, double taum /* d mass/d tf */,
@@ -258,7 +257,6 @@ LM_HD void stagejac_build(const Params& P, double kap, double tf, double taum /*
   J.e4 = kap * w;
   J.e5 = kap * P.asc * u;
   J.beta = al * P.asc;
-  J.a46 = 0.0;
 }
 
 LM_HD void stagejac_invert(StageJac& J) {

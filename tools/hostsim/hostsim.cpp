@@ -226,7 +226,8 @@ extern "C" int hostsim_solve_coop(const double* raw14, int nt, const double* tim
   IpmState S;
   ipm_begin(O, S);
   const bool vrec = getenv("VREC") != nullptr;     // the variant that keeps W_k, g_k instead of running the adjoint recursion
-  if (DC && vrec)  { SweepsCoop<1, 1, true, true>::guess(P, M, O, W, S.cur); while (!ipm_iterate_t<SweepsCoop<1, 1, true, true>>(P, M, O, W, S)) {} }
+  if (DC && getenv("CIRCULAR")) { SweepsCoop<1, 1, 2, false>::guess(P, M, O, W, S.cur); while (!ipm_iterate_t<SweepsCoop<1, 1, 2, false>>(P, M, O, W, S)) {} }
+  else if (DC && vrec)  { SweepsCoop<1, 1, true, true>::guess(P, M, O, W, S.cur); while (!ipm_iterate_t<SweepsCoop<1, 1, true, true>>(P, M, O, W, S)) {} }
   else if (DC)     { SweepsCoop<1, 1, true, false>::guess(P, M, O, W, S.cur); while (!ipm_iterate_t<SweepsCoop<1, 1, true, false>>(P, M, O, W, S)) {} }
   else if (vrec)   { SweepsCoop<1, 1, false, true>::guess(P, M, O, W, S.cur); while (!ipm_iterate_t<SweepsCoop<1, 1, false, true>>(P, M, O, W, S)) {} }
   else             { SweepsCoop<1, 1, false, false>::guess(P, M, O, W, S.cur); while (!ipm_iterate_t<SweepsCoop<1, 1, false, false>>(P, M, O, W, S)) {} }
