@@ -397,7 +397,7 @@ LM_HD void build_stage(const Params& P, const Options& O, double kap, double tau
   c[3] = z[3] - zp[3] - al * f.ax;
   c[4] = (MOVE == 2) ? z[4] - u - al * z[5]                  // the MV slot is the angle: angle_k - u_k = 0 (angledot = 0)
                      : z[4] - zp[4] - al * z[5];
-  c[5] = z[5] - P.coup5 * zp[5] - J.beta * u;
+  c[5] = z[5] - ((MOVE == 1) ? zp[5] : (MOVE == 2) ? 0.0 : P.coup5 * zp[5]) - J.beta * u;
   c[6] = 0.0; c[7] = 0.0;
   stv<8>(mrec + M_C, c);
   StageQ q;
@@ -485,7 +485,7 @@ LM_SWEEP bool coop_backward_seq(const Params& P, const Mesh& M, const Options& O
     }
   }
   const double cw = ls ? 0.0 : 1.0;     // defects are dropped in the least-squares mode
-  const double cp = P.coup5, cq4 = (MOVE == 2) ? 0.0 : 1.0;
+  const double cp = (MOVE == 1) ? 1.0 : (MOVE == 2) ? 0.0 : P.coup5, cq4 = (MOVE == 2) ? 0.0 : 1.0;   // (compile-time with the move term)
   double rmask[R][8], rscale[R];        // rmask[r][j] = 1 if this lane's r-th row is row j;  D = diag(1,1,1,1,cq4,coup5,1,1)
 #pragma unroll
   for (int r = 0; r < R; ++r) {
@@ -691,7 +691,7 @@ LM_SWEEP void coop_forward(const Params& P, const Mesh& M, const Options& O, con
   const unsigned gm = W.smask;       // sequential group
   const unsigned pmk = W.mask;       // parallel group
   const double cw = ls ? 0.0 : 1.0;
-  const double cp = P.coup5, cq4 = (MOVE == 2) ? 0.0 : 1.0;
+  const double cp = (MOVE == 1) ? 1.0 : (MOVE == 2) ? 0.0 : P.coup5, cq4 = (MOVE == 2) ? 0.0 : 1.0;   // (compile-time with the move term)
   const double dw = W.dw;
   const double wdc = O.w_dcost;
   // ---- (1) ds_k = E_k^-1 (D ds_{k-1} + e_6 dv_k - c_k),  dv_k = k_k + K_k ds_{k-1} ----
@@ -925,7 +925,7 @@ LM_SWEEP void coop_eval(const Params& P, const Mesh& M, const Options& O, const 
   const double tf0 = c0.tf, dtf = ts.dtf;
   const double tf = tf0 + alpha * dtf;
   const double wdc = O.w_dcost;
-  const double cp = P.coup5, cq4 = (MOVE == 2) ? 0.0 : 1.0;
+  const double cp = (MOVE == 1) ? 1.0 : (MOVE == 2) ? 0.0 : P.coup5, cq4 = (MOVE == 2) ? 0.0 : 1.0;   // (compile-time with the move term)
   t.tf = tf;
   // ---- terminal scalars of the trial point (every lane) ----
   t.sg1 = c0.sg1 + alpha * ts.dsg1;
