@@ -597,14 +597,14 @@ LM_SWEEP bool coop_backward_seq(const Params& P, const Mesh& M, const Options& O
         for (int j = 0; j < 8; ++j) Pr[r][j] = 0.5 * (Pr[r][j] + tr2[j * 9 + i]);
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) w6[j] = 0.5 * (tr2[6 * 9 + j] + tr2[j * 9 + 6]);
+      for (int j = 0; j < 8; ++j) w6[j] = tr2[6 * 9 + j] + tr2[j * 9 + 6];     // TWICE row 6: the halves are folded in below
     } else {
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < i; ++j) { const double v = 0.5 * (Pr[i % R][j] + Pr[j % R][i]); Pr[i % R][j] = v; Pr[j % R][i] = v; }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) w6[j] = Pr[6 % R][j];
+      for (int j = 0; j < 8; ++j) w6[j] = 2.0 * Pr[6 % R][j];
       ring_wait<RING_D - 2>(rg, kw & (RING_D - 1), par, kw >= 1);
       --kw;
     }
@@ -612,21 +612,24 @@ LM_SWEEP bool coop_backward_seq(const Params& P, const Mesh& M, const Options& O
     double wc6 = 0.0;
 #pragma unroll
     for (int j = 0; j < 6; ++j) wc6 = fma(w6[j], c[j], wc6);
-    const double rx6 = gt[6] - cw * wc6;
-    const double Ruu = q[Q_MVR] + (MOVE && !ls ? dw : 0.0) + w6[6];
+    const double rx6 = gt[6] - (0.5 * cw) * wc6;                  // (w6 holds twice the symmetrised row 6)
+    const double Ruu = q[Q_MVR] + (MOVE && !ls ? dw : 0.0) + 0.5 * w6[6];
     const double ru = q[Q_MVA] + mu * q[Q_MVB] + rx6;
     if (!(Ruu > 0.0) || !(Ruu < 1e300)) ok = false;
     const double Rinv = lm_rcp(Ruu);
     w6[5] *= cp; if (MOVE == 2) w6[4] = 0.0;            // d defect_k / d s_{k-1} = -D, D = diag(1,1,1,1,cq4,coup5,1,1)
-    double w6s[8];
+    // the feedback law K_k = -w6 / Ruu, k_k = -ru / Ruu, computed with its sign: it is what gets stored, and the
+    // update below subtracts w6_i * w6 / Ruu = adds w6_i * K (no separate negations in the one-lane store branch)
+    const double nRinv = -Rinv, nhRinv = -0.5 * Rinv;
+    double w6n[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) w6s[j] = w6[j] * Rinv;
-    const double kff = ru * Rinv;
+    for (int j = 0; j < 8; ++j) w6n[j] = w6[j] * nhRinv;
+    const double kffn = ru * nRinv;
     if (g == 6 / R) {
       double kk[KR];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) kk[j] = -w6s[j];
-      kk[K_FF] = -kff; kk[9] = 0.0;
+      for (int j = 0; j < 8; ++j) kk[j] = w6n[j];
+      kk[K_FF] = kffn; kk[9] = 0.0;
       stv<KR>(W.K(k), kk);
     }
     // ---- P_{k-1} = D Wt D - (D w6)(D w6)^T / Ruu ,  p_{k-1} = D (g~ - Wt c) - D w6 ru / Ruu ----
@@ -642,8 +645,8 @@ LM_SWEEP bool coop_backward_seq(const Params& P, const Mesh& M, const Options& O
       const double w6i = rs * Pr[r][6];
       Pr[r][5] *= cp; if (MOVE == 2) Pr[r][4] = 0.0;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) Pr[r][j] = fma(-w6i, w6s[j], rs * Pr[r][j]);
-      pr[r] = fma(-w6i, kff, rs * (gti - cw * wc));
+      for (int j = 0; j < 8; ++j) Pr[r][j] = fma(w6i, w6n[j], rs * Pr[r][j]);
+      pr[r] = fma(w6i, kffn, rs * (gti - cw * wc));
     }
     if (!ok) {
       // wrong inertia: leave with the ring drained (every issued copy waited for), the caller retries with delta_w
