@@ -282,7 +282,7 @@ LM_SWEEP void eval_pass(const Params& P, const Mesh& M, const Options& O, const 
       g[2] = pi_next[2] - (q.q02 * ds[0] + q.q22 * ds[2] + q.q24 * ds[4] + q.q26 * dtf);
       g[3] = pi_next[3] - (q.d * ds[3] + q.q36 * dtf);
       g[4] = pi_next[4] - (q.q04 * ds[0] + q.q24 * ds[2] + q.q44 * ds[4] + q.q46 * dtf + q.q4);
-      g[5] = P.coup5 * pi_next[5] - (q.d * ds[5] + q.q56 * dtf);
+      g[5] = pi_next[5] - (q.d * ds[5] + q.q56 * dtf);
       // u as a state: bound barrier (q.R - dw, q.r hold Sigma_u and its gradient), u-tf cross term
       g[6] = pi_next[6] - (q.R * du + q.sig * dtf + q.r);
       g[7] = 0.0;
@@ -368,7 +368,7 @@ LM_SWEEP void eval_pass(const Params& P, const Mesh& M, const Options& O, const 
     c[2] = z[2] - zp[2] - al * z[3];
     c[3] = z[3] - zp[3] - al * f.ax;
     c[4] = z[4] - zp[4] - al * z[5];
-    c[5] = z[5] - P.coup5 * zp[5] - J.beta * u;
+    c[5] = z[5] - zp[5] - J.beta * u;
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
       const double ac = fabs(c[i]);
@@ -401,7 +401,7 @@ LM_SWEEP void eval_pass(const Params& P, const Mesh& M, const Options& O, const 
     } else {
 #pragma unroll
       for (int i = 0; i < 5; ++i) res[i] -= lam_next[i];
-      res[5] -= P.coup5 * lam_next[5];
+      res[5] -= lam_next[5];
       res[6] -= lam_next[6];
     }
 #pragma unroll
@@ -518,7 +518,7 @@ LM_SWEEP bool riccati_backward(const Params& P, const Mesh& M, const Options& O,
       c[2] = zn[2] - zm[2] - al * zn[3];
       c[3] = zn[3] - zm[3] - al * f.ax;
       c[4] = zn[4] - zm[4] - al * zn[5];
-      c[5] = zn[5] - P.coup5 * zm[5] - J.beta * u;
+      c[5] = zn[5] - zm[5] - J.beta * u;
     } else {
 #pragma unroll
       for (int i = 0; i < 6; ++i) c[i] = 0.0;
@@ -592,13 +592,8 @@ LM_SWEEP bool riccati_backward(const Params& P, const Mesh& M, const Options& O,
     for (int j = 0; j < 4; ++j)
       rx[4 + j] = pv[4 + j] - (Bm[0][j] * c[0] + Bm[1][j] * c[1] + Bm[2][j] * c[2] + Bm[3][j] * c[3] + C[j][0] * c[4] + C[j][1] * c[5]);
     const double ru = r + rx[6];
-    // previous node sees the angledot column scaled by coup5
-    const double cp = P.coup5;
-    Rux[5] *= cp; rx[5] *= cp;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) Bm[i][1] *= cp;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { C[1][j] *= cp; C[j][1] *= cp; }
+    // (these sweeps serve the elliptical model only -- coup5 = 1, d defect_k / d s_{k-1} = -I: the circular model
+    //  runs the 7-state sweeps, and with its move term the cooperative kernel)
     if (!(Ruu > 0.0) || !(Ruu < 1e300)) ok = false;
     const double Rinv = lm_rcp(Ruu);
     double RuxS[8];
@@ -681,7 +676,7 @@ LM_SWEEP void riccati_forward(const Params& P, const Mesh& M, const Options& O, 
     xi[2] = ds[2] - cw * (zn[2] - zm[2] - al * zn[3]);
     xi[3] = ds[3] - cw * (zn[3] - zm[3] - al * f.ax);
     xi[4] = ds[4] - cw * (zn[4] - zm[4] - al * zn[5]);
-    xi[5] = P.coup5 * ds[5] - cw * (zn[5] - P.coup5 * zm[5] - J.beta * u);
+    xi[5] = ds[5] - cw * (zn[5] - zm[5] - J.beta * u);
     xi[6] = ds[6] + dv;                       // u row: du_k = du_{k-1} + dv_k (its defect is identically 0)
     xi[7] = dtf;
     solveE8(J, xi);
