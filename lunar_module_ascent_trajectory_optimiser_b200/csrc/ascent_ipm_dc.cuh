@@ -172,6 +172,51 @@ LM_HD void ev_stage_copy(const Mesh& M, const Ws& W, int k, int so, bool read_pi
   tl_copy_rows<EV_PDS, 7>(tb, sm, F_DS);
   tl_commit();
 }
+// Inside the stage loops the same copies are issued in two halves, each its own commit group: (a) at the top of the
+// stage body, (b) in the middle of it.  As one burst the 24-38 LDGSTS of a stage filled the load/store unit's queue
+// (the source view showed 39 % "lg_throttle" and 16 % "mio_throttle" stall samples on the copy blocks); split, config 4
+// runs 85.2 -> 82.7 ms.  Three parts are slower again (85.4).  The wait is unchanged: before stage k is consumed
+// everything but the newest group -- part (a) of stage k-1, just issued -- has landed.
+LM_HD void ev_stage_copy_a(const Mesh& M, const Ws& W, int k, int so, bool read_pi) {
+  const TileRef tb = tl_buf(W, k);
+  tl_copy_mesh(tb, M, k);
+  const double* sp = W.stage(k);
+  tl_copy_rows<EV_CUR, N_CUR>(tb, ws_opaque(sp + so * LANES), F_LAM);
+  if (read_pi) tl_copy_rows<EV_PI, 7>(tb, sp, F_PI);
+  tl_commit();
+}
+LM_HD void ev_stage_copy_b(const Ws& W, int k, int so) {
+  const TileRef tb = tl_buf(W, k);
+  const double* sm = ws_opaque(W.stage(k) - W.SS);
+  tl_copy_rows<EV_PZ, 7>(tb, ws_opaque(sm + so * LANES), F_Z);
+  tl_copy_rows<EV_PDS, 7>(tb, sm, F_DS);
+  tl_commit();
+}
+LM_HD void bk_stage_copy_a(const Mesh& M, const Ws& W, int k, int so) {
+  const TileRef tb = tl_buf(W, k);
+  tl_copy_mesh(tb, M, k);
+  tl_copy_rows<BK_CUR, N_CUR>(tb, ws_opaque(W.stage(k) + so * LANES), F_LAM);
+  tl_commit();
+}
+LM_HD void bk_stage_copy_b(const Ws& W, int k, int so) {
+  const TileRef tb = tl_buf(W, k);
+  tl_copy_rows<BK_PZ, 7>(tb, ws_opaque(W.stage(k) + so * LANES - W.SS), F_Z);
+  tl_commit();
+}
+LM_HD void fw_stage_copy_a(const Mesh& M, const Ws& W, int k, int so) {
+  const TileRef tb = tl_buf(W, k);
+  tl_copy_mesh(tb, M, k);
+  const double* spo = ws_opaque(W.stage(k) + so * LANES);
+  tl_copy_rows<FW_Z, 7>(tb, spo, F_Z);
+  tl_copy_rows<FW_ZB, N_ITER - F_ZLA>(tb, spo, F_ZLA);
+  tl_commit();
+}
+LM_HD void fw_stage_copy_b(const Ws& W, int k) {
+  const TileRef tb = tl_buf(W, k);
+  tl_copy_rows<FW_K, N_FACT>(tb, W.stage(k), F_K);
+  tl_commit();
+}
+
 LM_HD void bk_stage_copy(const Mesh& M, const Ws& W, int k, int so) {
   const TileRef tb = tl_buf(W, k);
   tl_copy_mesh(tb, M, k);
@@ -244,7 +289,7 @@ LM_SWEEP void eval_pass(const Params& P, const Mesh& M, const Options& O, const 
   double pi_next[7] = {0, 0, 0, 0, 0, 0, 0};
   for (int k = N; k >= 1; --k) {
     double* sp = W.stage(k);
-    if (k > 1) ev_stage_copy(M, W, k - 1, so, mode == EV_READ_PI); else tl_commit();
+    if (k > 1) ev_stage_copy_a(M, W, k - 1, so, mode == EV_READ_PI); else tl_commit();
     tl_wait_prev();
     const TileRef tb = tl_buf(W, k);
     double z[7], zpo[7], dsp[7], zp[7], lam[7];
@@ -302,6 +347,7 @@ LM_SWEEP void eval_pass(const Params& P, const Mesh& M, const Options& O, const 
     }
 #pragma unroll
     for (int i = 0; i < 7; ++i) lam[i] = fma(alpha_lam, pi[i] - lam_old[i], lam_old[i]);
+    if (k > 1) ev_stage_copy_b(W, k - 1, so); else tl_commit();      // second half of the next stage's tile
     // ---- bound multipliers ----
     {
       double rLa, rUa, rLu, rUu;
@@ -469,7 +515,7 @@ LM_SWEEP bool riccati_backward(const Params& P, const Mesh& M, const Options& O,
   bool ok = true;
   for (int k = N; k >= 1; --k) {
     double* sp = W.stage(k);
-    if (k > 1) bk_stage_copy(M, W, k - 1, so); else tl_commit();
+    if (k > 1) bk_stage_copy_a(M, W, k - 1, so); else tl_commit();
     tl_wait_prev();
     const TileRef tb = tl_buf(W, k);
     const bool ls = W.ls_flag != 0;      // shadows the argument: a shared-memory load per stage
@@ -530,6 +576,7 @@ LM_SWEEP bool riccati_backward(const Params& P, const Mesh& M, const Options& O,
     for (int i = 0; i < 4; ++i) applyA11T(J, A[i][0], A[i][1], A[i][2], A[i][3]);
 #pragma unroll
     for (int j = 0; j < 4; ++j) applyA11T(J, Bm[0][j], Bm[1][j], Bm[2][j], Bm[3][j]);
+    if (k > 1) bk_stage_copy_b(W, k - 1, so); else tl_commit();      // second half of the next stage's tile
     // ---- T2: (angle, tf) couple into the velocity rows: C_T2 = [ga | 0 | 0 | e] ----
     {
       double ACa[4], ACt[4];
@@ -651,7 +698,7 @@ LM_SWEEP void riccati_forward(const Params& P, const Mesh& M, const Options& O, 
   const double cw = ls ? 0.0 : 1.0;
   for (int k = 1; k <= N; ++k) {
     double* sp = W.stage(k);
-    if (k < N) fw_stage_copy(M, W, k + 1, so); else tl_commit();
+    if (k < N) fw_stage_copy_a(M, W, k + 1, so); else tl_commit();
     tl_wait_prev();
     const TileRef tb = tl_buf(W, k);
     const bool ls = W.ls_flag != 0;      // shadows the argument: a shared-memory load per stage
@@ -680,6 +727,7 @@ LM_SWEEP void riccati_forward(const Params& P, const Mesh& M, const Options& O, 
     xi[6] = ds[6] + dv;                       // u row: du_k = du_{k-1} + dv_k (its defect is identically 0)
     xi[7] = dtf;
     solveE8(J, xi);
+    if (k < N) fw_stage_copy_b(W, k + 1); else tl_commit();          // second half of the next stage's tile
     {
       // slack pair: primal and dual steps, fraction to the boundary, merit slope
       const double pp = tl_ld(tb, FW_ZB + F_PP - F_ZLA), pn = tl_ld(tb, FW_ZB + F_PN - F_ZLA);
