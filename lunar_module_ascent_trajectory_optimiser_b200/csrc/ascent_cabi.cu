@@ -1023,11 +1023,15 @@ lmato_status_t lmato_solve_batch(lmato_handle* h, const double* params, int64_t 
   // barrier decrease exponent: IPOPT's 1.5 from the cold start, 2 from the batch warm start.  Measured on the
   // benchmark batch (warm): 1.3 / 1.5 / 1.7 / 2.0 / 2.5 / 3.0 -> 91 / 96 / 95 / 88 / 88 / 115 ms; from the cold
   // start 2.0 costs 0.7 iterations more than 1.5.  kappa_mu and tau_min do not matter.
-  a.O.kappa_eps = h->opt.kappa_eps; a.O.kappa_mu = 0.2; a.O.theta_mu = 1.5; a.O.theta_mu_warm = 2.0; a.O.tau_min = 0.99;
+  a.O.kappa_eps = h->opt.kappa_eps; a.O.kappa_mu = 0.2; a.O.theta_mu = 1.5; a.O.tau_min = 0.99;
   a.O.delta_c = h->opt.delta_c; a.O.tf_guess = h->opt.tf_guess;
   a.O.max_iter = h->opt.max_iter; a.O.max_ls = h->opt.max_ls;
   a.O.mu_min_factor = h->opt.mu_min_factor;
   a.O.n_polish = h->opt.n_polish >= 0 ? h->opt.n_polish : (use_dc ? 2 : 4);
+  // ... 2 from the warm start WITH the move term only.  Without it the control on the singular arc is a nearly flat
+  // direction, and the jump 1e-6 -> 1e-12 leaves a few problems in 10 000 on an error plateau until the stall guard
+  // gives the warm attempt up -- each holding its warp: 65 536 problems, dcost = 0: 260-560 ms with 2, 66 ms with 1.5.
+  a.O.theta_mu_warm = use_dc ? 2.0 : 1.5;
   {
     const int on = h->opt.objective_nodes > 0 ? h->opt.objective_nodes : h->nt - 1;
     a.O.w_dcost = use_dc ? h->opt.obj_scale * h->opt.dcost / (double)on : 0.0;

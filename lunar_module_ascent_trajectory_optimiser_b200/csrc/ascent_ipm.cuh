@@ -180,6 +180,9 @@ LM_HD double tl_ld(TileRef tb, int slot) {
 }
 
 constexpr int NFILT = 12;
+#ifndef LMATO_WARM_STALL_WINDOW
+#define LMATO_WARM_STALL_WINDOW 30
+#endif
 
 // Per-problem scalar state (registers / local memory).
 struct Scal {
@@ -669,6 +672,50 @@ LM_HD void fw7_stage_copy(const Mesh& M, const Ws& W, int k, int so) {
   tl_copy_rows<FW_K, N_FACT>(tb, sp, F_K);
   tl_commit();
 }
+// Inside the stage loops the same copies are issued in two halves, each its own commit group -- (a) at the top of the
+// stage body, (b) in the middle of it -- so that a stage's LDGSTS do not reach the load/store unit in one burst (see
+// ascent_ipm_dc.cuh for the measurement).  The wait is unchanged: before stage k is consumed everything but the newest
+// group, part (a) of the next stage, has landed.
+LM_HD void ev7_stage_copy_a(const Mesh& M, const Ws& W, int k, int so, bool read_pi) {
+  const TileRef tb = tl_buf(W, k);
+  tl_copy_mesh(tb, M, k);
+  const double* sp = W.stage(k);
+  tl_copy_rows<EV_CUR, N_CUR>(tb, ws_opaque(sp + so * LANES), F_U);
+  tl_copy(tb, EV_DU, sp + F_DU * LANES);
+  if (read_pi) tl_copy_rows<EV_PI, 6>(tb, sp, F_PI);
+  tl_commit();
+}
+LM_HD void ev7_stage_copy_b(const Ws& W, int k, int so) {
+  const TileRef tb = tl_buf(W, k);
+  const double* sm = ws_opaque(W.stage(k) - W.SS);
+  tl_copy_rows<EV_PZ, 6>(tb, ws_opaque(sm + so * LANES), F_Z);
+  tl_copy_rows<EV_PDS, 6>(tb, sm, F_DS);
+  tl_commit();
+}
+LM_HD void bk7_stage_copy_a(const Mesh& M, const Ws& W, int k, int so) {
+  const TileRef tb = tl_buf(W, k);
+  tl_copy_mesh(tb, M, k);
+  tl_copy_rows<BK_CUR, N_CUR>(tb, ws_opaque(W.stage(k) + so * LANES), F_U);
+  tl_commit();
+}
+LM_HD void bk7_stage_copy_b(const Ws& W, int k, int so) {
+  const TileRef tb = tl_buf(W, k);
+  tl_copy_rows<BK_PZ, 6>(tb, ws_opaque(W.stage(k) + so * LANES - W.SS), F_Z);
+  tl_commit();
+}
+LM_HD void fw7_stage_copy_a(const Mesh& M, const Ws& W, int k, int so) {
+  const TileRef tb = tl_buf(W, k);
+  tl_copy_mesh(tb, M, k);
+  const double* spo = ws_opaque(W.stage(k) + so * LANES);
+  tl_copy_rows<FW_Z, 7>(tb, spo, F_Z);
+  tl_copy_rows<FW_ZB, N_ITER - F_ZLA>(tb, spo, F_ZLA);
+  tl_commit();
+}
+LM_HD void fw7_stage_copy_b(const Ws& W, int k) {
+  const TileRef tb = tl_buf(W, k);
+  tl_copy_rows<FW_K, N_FACT>(tb, W.stage(k), F_K);
+  tl_commit();
+}
 
 enum : int { EV_READ_PI = 0, EV_NEWTON = 1, EV_LSQ = 2 };
 
@@ -723,7 +770,7 @@ LM_SWEEP void eval_pass(const Params& P, const Mesh& M, const Options& O, const 
   for (int k = N; k >= 1; --k) {
     double* sp = W.stage(k);
     // stage the rows of the next stage, then wait for this stage's tile
-    if (k > 1) ev7_stage_copy(M, W, k - 1, so, mode == EV_READ_PI); else tl_commit();
+    if (k > 1) ev7_stage_copy_a(M, W, k - 1, so, mode == EV_READ_PI); else tl_commit();
     tl_wait_prev();
     const TileRef tb = tl_buf(W, k);
     double z[6], zpo[6], dsp[6], zp[6], lam[6];
@@ -778,6 +825,7 @@ LM_SWEEP void eval_pass(const Params& P, const Mesh& M, const Options& O, const 
     }
 #pragma unroll
     for (int i = 0; i < 6; ++i) lam[i] = fma(alpha_lam, pi[i] - lam_old[i], lam_old[i]);
+    if (k > 1) ev7_stage_copy_b(W, k - 1, so); else tl_commit();     // second half of the next stage's tile
     // ---- bound multipliers: dz = (mu - z dx)/d - z  (old d, old z), then the kappa_Sigma clip ----
     {
       double rLa, rUa, rLu, rUu;
@@ -920,7 +968,7 @@ LM_SWEEP bool riccati_backward(const Params& P, const Mesh& M, const Options& O,
   bool ok = true;
   for (int k = N; k >= 1; --k) {
     double* sp = W.stage(k);
-    if (k > 1) bk7_stage_copy(M, W, k - 1, so); else tl_commit();
+    if (k > 1) bk7_stage_copy_a(M, W, k - 1, so); else tl_commit();
     tl_wait_prev();
     const TileRef tb = tl_buf(W, k);
     const bool ls = W.ls_flag != 0;      // shadows the argument: a shared-memory load per stage
@@ -972,6 +1020,7 @@ LM_SWEEP bool riccati_backward(const Params& P, const Mesh& M, const Options& O,
     for (int i = 0; i < 4; ++i) applyA11T(J, A[i][0], A[i][1], A[i][2], A[i][3]);
 #pragma unroll
     for (int j = 0; j < 3; ++j) applyA11T(J, Bm[0][j], Bm[1][j], Bm[2][j], Bm[3][j]);
+    if (k > 1) bk7_stage_copy_b(W, k - 1, so); else tl_commit();     // second half of the next stage's tile
     // ---- T2: couple (angle, tf) into the velocity rows ----
     {
       double AC0[4], AC2[4];
@@ -1098,7 +1147,7 @@ LM_SWEEP void riccati_forward(const Params& P, const Mesh& M, const Options& O, 
   const double cw = ls ? 0.0 : 1.0;   // defects are dropped in the least-squares mode
   for (int k = 1; k <= N; ++k) {
     double* sp = W.stage(k);
-    if (k < N) fw7_stage_copy(M, W, k + 1, so); else tl_commit();
+    if (k < N) fw7_stage_copy_a(M, W, k + 1, so); else tl_commit();
     tl_wait_prev();
     const TileRef tb = tl_buf(W, k);
     const bool ls = W.ls_flag != 0;      // shadows the argument: a shared-memory load per stage
@@ -1126,6 +1175,7 @@ LM_SWEEP void riccati_forward(const Params& P, const Mesh& M, const Options& O, 
     xi[5] = P.coup5 * ds[5] - cw * (zn[5] - P.coup5 * zm[5] - J.beta * u) + J.beta * du;
     xi[6] = dtf;
     solveE(J, xi);
+    if (k < N) fw7_stage_copy_b(W, k + 1); else tl_commit();         // second half of the next stage's tile
 #pragma unroll
     for (int i = 0; i < 6; ++i) { ds[i] = xi[i]; WS_AT(sp, F_DS + i) = xi[i]; zm[i] = zn[i]; dxmax = dmax(dxmax, fabs(xi[i])); }
     WS_AT(sp, F_DU) = du;
@@ -1322,7 +1372,10 @@ LM_HD bool ipm_iterate_t(const Params& P, const Mesh& M, const Options& O, const
     // filter keeps accepting; IPOPT would switch to its restoration phase and report infeasibility.  Here the
     // problem is stopped -- in a batch one such lane would otherwise hold its whole SM for MAX_ITER iterations.
     if (S.err0 < 0.9 * ctl.err_best) { ctl.err_best = S.err0; ctl.iter_best = ctl.iter; }
-    if (!S.polishing && (ctl.tiny_steps >= 10 || ctl.iter - ctl.iter_best >= 100)) { ctl.status = ST_STALLED; return true; }
+    // (a batch warm start or a caller's start point that makes no progress is given up much earlier: the lane then
+    //  restarts from the built-in roll-out, and every iteration it spends here holds its whole warp)
+    const int stall_window = (S.warm || S.from_guess) ? LMATO_WARM_STALL_WINDOW : 100;
+    if (!S.polishing && (ctl.tiny_steps >= 10 || ctl.iter - ctl.iter_best >= stall_window)) { ctl.status = ST_STALLED; return true; }
   }
   const bool polishing = S.polishing;
   // factorisation with inertia correction (IPOPT Algorithm IC)

@@ -48,6 +48,20 @@ def test_thread_and_coop_kernels_agree(lm, B, nt, dcost):
         assert float(got["kkt"].max()) <= 1e-9
 
 
+def test_warm_start_without_move_term_on_the_thread_kernel(lm):
+    """The batch warm start of the 7-state sweeps (dcost = 0) on the thread-per-problem kernel: every warm attempt must
+    converge on its own (no lane may fall back to the cold start after a long stalled attempt, which holds its warp:
+    a barrier exponent of 2 without the move term did exactly that, 260-560 ms instead of 66 ms per 65 536 problems)."""
+    B = 16384
+    rows = lm.dispersed_params(B, seed=11).rows(B)
+    warm = _solve(lm, rows, kernel="thread", dcost=0.0, warm_start=2)
+    cold = _solve(lm, rows, kernel="thread", dcost=0.0, warm_start=0)
+    assert int((warm["status"] != 0).sum()) == 0 and int((cold["status"] != 0).sum()) == 0
+    assert float(((warm["tf"] - cold["tf"]).abs() / cold["tf"]).max()) < 1e-10
+    assert int(warm["iterations"].max()) <= 32, int(warm["iterations"].max())         # a restarted lane would show ~26 more
+    assert float(warm["iterations"].double().mean()) < float(cold["iterations"].double().mean()) - 4
+
+
 def test_coop_kernel_matches_goldens(lm, golden_dir):
     """The cooperative kernel against the oracle directly (nominal without DCOST, four dispersions with DCOST,
     circular model), both lane counts."""
