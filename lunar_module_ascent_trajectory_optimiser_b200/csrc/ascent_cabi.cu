@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(kBlock, kBlocksPerSM) ascent_ipm_kernel(KArgs 
         // restarts the same problem from the built-in roll-out.  (IPOPT would enter its feasibility restoration
         // phase from such a point, e.g. from the reference's all-zero start values LO:39, 83-96; this solver's
         // substitute is a start point that is dynamically feasible by construction.)
-        ipm_begin(O, S);
+        { const int prior = S.iters_prior + S.ctl.iter; ipm_begin(O, S); S.iters_prior = prior; }
         SW::guess(P, M, O, W, S.cur);
         continue;
       }
@@ -478,7 +478,7 @@ __global__ void __launch_bounds__(kCoopBlock, BPS) ascent_coop_kernel(KArgs a) {
     if (active && ipm_iterate_t<SW>(P, M, O, W, S)) {
       if ((S.warm || S.from_guess) && S.ctl.status != ST_CONVERGED) {
         // a warm start or a caller's guess that did not work out: restart from the built-in roll-out
-        ipm_begin(O, S);
+        { const int prior = S.iters_prior + S.ctl.iter; ipm_begin(O, S); S.iters_prior = prior; }
         SW::guess(P, M, O, W, S.cur);
         continue;
       }

@@ -485,7 +485,8 @@ def test_pathological_inputs_fail_fast_and_alone(lm):
     raw = solver.solve_rows(rows.cuda())
     torch.cuda.synchronize()
     assert time.time() - t0 < 5.0
-    assert int(raw["status"][5]) == 5 and int(raw["iterations"][5]) < 400      # LMATO_ST_STALLED
+    # (status 5, stalled -- or 2, line search failed, when the bounded line search meets its third null step first)
+    assert int(raw["status"][5]) in (2, 5) and int(raw["iterations"][5]) < 400
     assert int((raw["status"].cpu()[torch.arange(64) != 5] != 0).sum()) == 0
 
 
