@@ -75,7 +75,9 @@ enum {
 enum {
   LMATO_ST_CONVERGED = 0,        /* scaled KKT error <= tol */
   LMATO_ST_MAX_ITER = 1,         /* MAX_ITER reached (LO:28) */
-  LMATO_ST_LINESEARCH_FAIL = 2,  /* filter line search could not make progress */
+  LMATO_ST_LINESEARCH_FAIL = 2,  /* filter line search could not make progress: no acceptable step within max_ls
+                                    halvings, or a third search of the solve that was still rejected after 12 (the
+                                    first two are taken as null steps); IPOPT would enter its restoration phase */
   LMATO_ST_INERTIA_FAIL = 3,     /* KKT inertia could not be corrected */
   LMATO_ST_NUMERICAL = 4,        /* NaN/Inf encountered */
   LMATO_ST_STALLED = 5           /* no progress: ten consecutive steps shorter than 1e-6, or no improvement of the KKT
@@ -151,6 +153,7 @@ lmato_status_t lmato_set_options(lmato_handle* h, const lmato_options* o);
  *   out_tf        [B]   scaled final time in (0,1)  (tf.value[0], LO:178)
  *   out_final_mass[B]   kg:  M0 - fuel_mass * mass(nt-1)
  *   out_status    [B]   LMATO_ST_*
+ *   out_iters     [B]   accepted iterations, including those of an abandoned warm start / caller's start point
  *   out_iters     [B]   IPM iterations used
  *   out_kkt       [B]   final scaled KKT error, or NULL
  * Replaces: m.solve() (LO:177) and the read-back LO:178-202. */
