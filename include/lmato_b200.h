@@ -153,8 +153,7 @@ lmato_status_t lmato_set_options(lmato_handle* h, const lmato_options* o);
  *   out_tf        [B]   scaled final time in (0,1)  (tf.value[0], LO:178)
  *   out_final_mass[B]   kg:  M0 - fuel_mass * mass(nt-1)
  *   out_status    [B]   LMATO_ST_*
- *   out_iters     [B]   accepted iterations, including those of an abandoned warm start / caller's start point
- *   out_iters     [B]   IPM iterations used
+ *   out_iters     [B]   IPM iterations used, including those of an abandoned warm start / caller's start point
  *   out_kkt       [B]   final scaled KKT error, or NULL
  * Replaces: m.solve() (LO:177) and the read-back LO:178-202. */
 lmato_status_t lmato_solve_batch(lmato_handle* h, const double* params, int64_t B,
