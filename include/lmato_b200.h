@@ -95,7 +95,7 @@ typedef struct {
   int32_t max_ls;    /* max backtracking steps per iteration; default 40 */
   int32_t n_polish;  /* Newton iterations taken after tol is first met; default -1 = automatic: 2 with the
                         DCOST term (it regularises the flat control directions), 4 without (DESIGN.md "Tolerance") */
-  int32_t warm_start; /* 1 (default): batches of >= 1024 problems (below that the serial reference solve costs more than it saves) first solve the batch-mean problem down to
+  int32_t warm_start; /* 1 (default): batches of >= 512 problems (below that the serial reference solve costs more than it saves) first solve the batch-mean problem down to
                          mu_ref and start every problem from that central-path point; a problem that fails
                          from there is restarted from the generic cold start.  0: always cold start.  2: warm start for
                          every batch size.  The handle keeps its last reference and the next reference solve

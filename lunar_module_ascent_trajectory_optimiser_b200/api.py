@@ -134,7 +134,7 @@ class SolverOptions:
     max_ls: int = 40
     mu_min_factor: float = 1e-3    # barrier floor = mu_min_factor * tol
     n_polish: int = -1             # Newton iterations after tol is first met; -1 = 2 with DCOST, 4 without
-    warm_start: int = 1            # 1: batches >= 1024 start from the batch-mean problem's central path; 0: never; 2: always
+    warm_start: int = 1            # 1: batches >= 512 start from the batch-mean problem's central path; 0: never; 2: always
     mu_ref: float = 1e-3           # barrier parameter at which that reference solve stops
     dcost: Optional[float] = None  # LO:99; None = take AscentParams.dcost (1e-5 in the reference)
     objective_nodes: int = 0       # APMonitor sums the objective over the horizon; 0 = nt-1
@@ -643,7 +643,7 @@ def optimise_batch(params: AscentParams, mesh: Optional[Mesh] = None,
         if len(devices) == 0:
             raise ValueError("`devices` is empty")
         nB = batch if batch is not None else (params.batch_size() or 1)
-        if options.warm_start == 1 and nB >= 1024:
+        if options.warm_start == 1 and nB >= 512:
             # the shards belong to one batch: they keep the batch warm start even if a shard alone is small
             options = dataclasses.replace(options, warm_start=2)
         if not on_dev and not sensitivities:

@@ -54,9 +54,10 @@ constexpr int kBlocksPerSM = 1;
 // dynamic shared memory: the staging tiles, then one workspace view per thread
 constexpr size_t kTileSmem = (size_t)(kBlock / 32) * 2 * TILE_ROWS * LANES * sizeof(double) + kBlock * sizeof(Ws);
 // Batch warm start: one reference solve of the batch-mean problem (cooperative kernel, one group) against ~6 saved
-// iterations per problem.  Measured break-even of the first call on a handle: 512-2048 problems (later calls
-// re-converge the reference from the previous one in 1-2 iterations and win at every size).
-constexpr long kWarmStartMinBatch = 1024;
+// iterations per problem.  Measured with the reference solve on the cooperative kernel (1.8 ms on the first call of a
+// handle, 0.2 ms afterwards): 512 problems 7.2 ms cold, 7.3 ms warm on the first call, 5.5 ms on later calls; from
+// 1 024 problems up the first call wins as well (tools/gpu_warm_threshold.py).
+constexpr long kWarmStartMinBatch = 512;
 
 struct KArgs {
   const double* params;  // [NPARAM][B]

@@ -99,7 +99,9 @@ def test_otol_rtol_rule(lm):
 def test_two_streams_share_one_handle(lm):
     """Solves issued back to back on DIFFERENT streams of one handle share its workspace and work queue: the
     library serialises them on the device (the second waits for the first), results equal the sequential ones."""
-    solver = lm.AscentSolver(lm.Mesh(), lm.SolverOptions(), device=0)
+    # (cold starts: with the batch warm start a result depends, to rounding, on the handle's previous reference,
+    #  and this test compares bit for bit)
+    solver = lm.AscentSolver(lm.Mesh(), lm.SolverOptions(warm_start=0), device=0)
     r1 = lm.dispersed_params(600, seed=1).rows(600).cuda()
     r2 = lm.dispersed_params(600, seed=2).rows(600).cuda()
     want1 = {k: v.clone() for k, v in solver.solve_rows(r1).items()}

@@ -286,7 +286,7 @@ def test_warm_start_is_reproducible_and_faster(lm):
     the answers: two solves of the same 4 096 problems from different start points agree on tf to
     rounding and on every state to well inside north_star's 1e-4, and the warm one needs fewer
     iterations."""
-    B = 4096           # the warm start engages from 1 024 problems
+    B = 4096           # the warm start engages from 512 problems
     rows = lm.dispersed_params(B, seed=11).rows(B).cuda()
     res = {}
     for warm in (False, True):
