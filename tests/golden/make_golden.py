@@ -69,7 +69,7 @@ def main():
              final_mass=np.array(fms), traj=np.stack(trajs), names=np.array(VAR_ROWS))
 
 
-if __name__ == "__main__" and not any(a in sys.argv for a in ("--dense", "--dcost", "--sens", "--nodes", "--config3", "--circular-dcost")):
+if __name__ == "__main__" and not any(a in sys.argv for a in ("--dense", "--dcost", "--sens", "--nodes", "--config3", "--circular-dcost", "--config4")):
     main()
 
 
@@ -225,3 +225,45 @@ def circular_dcost():
 
 if __name__ == "__main__" and "--circular-dcost" in sys.argv:
     circular_dcost()
+
+
+def _cfg4_one(args):
+    b, row = args
+    p = AscentParams(Ft=row[3], M0=row[4], M_dot=row[5], angle_doubledot_max=row[7], r_periapsis=row[8],
+                     r_apoapsis=row[9], dcost=1e-5)
+    nlp = AscentNLP(p, nt=200, obj_scale=10.0)
+    r = None
+    for tf0 in (0.9, 0.95, 0.85, 0.92):
+        r = solve_ipm(nlp, nlp.initial_guess(tf0), IPMOptions(tol=1e-12, max_iter=500))
+        if r.status == 0 or r.kkt_error < 1e-9:
+            break
+    nv = nlp.node_values(r.x)
+    traj = np.stack([nv[n] for n in VAR_ROWS])
+    return b, nv["tf"], p.M0 - p.fuel_mass * nv["mass"][-1], traj, r.iterations, r.kkt_error
+
+
+def config4_slice(B=512, stride=20):
+    """A slice of config 4 on the DEFAULT path: the first 512 of the seed-11 dispersions over all six parameters
+    (thrust, Isp, initial mass, angular-acceleration limit, target perilune and apolune), with the reference's move
+    suppression (DCOST = 1e-5, slack pairs in the oracle), every one solved by the oracle.  Kept per problem: tf, final
+    mass, the ten variables at every `stride`-th node and the final node."""
+    import multiprocessing as mp
+    import torch  # noqa: F401
+    from lunar_module_ascent_trajectory_optimiser_b200.dispersions import dispersed_params
+    rows = dispersed_params(B, seed=11).rows(B).numpy()
+    keep = np.unique(np.concatenate([np.arange(0, 200, stride), [199]]))
+    tf = np.zeros(B); fm = np.zeros(B); traj = np.zeros((B, 10, keep.size)); iters = np.zeros(B, np.int32)
+    kkt = np.zeros(B)
+    with mp.Pool(int(os.environ.get("GOLDEN_PROCS", os.cpu_count()))) as pool:
+        for n, (b, t, f, tr, it, kk) in enumerate(pool.imap_unordered(_cfg4_one, [(b, rows[:, b]) for b in range(B)], chunksize=2)):
+            tf[b] = t; fm[b] = f; traj[b] = tr[:, keep]; iters[b] = it; kkt[b] = kk
+            if n % 32 == 0:
+                print("config 4 slice:", n, "of", B, "solved", flush=True)
+    np.savez_compressed(os.path.join(HERE, f"elliptical_config4_dcost_disp{B}_seed11_nt200.npz"), rows=rows, tf=tf,
+                        final_mass=fm, traj=traj, nodes=keep, names=np.array(VAR_ROWS), iters=iters, kkt=kkt, dcost=1e-5,
+                        objective_nodes=199)
+    print("config 4 slice fixture: tf_s range", tf.min() * 470, tf.max() * 470, "max iters", iters.max(), "max kkt", kkt.max())
+
+
+if __name__ == "__main__" and "--config4" in sys.argv:
+    config4_slice()

@@ -114,6 +114,30 @@ def test_config3_matches_oracle_fixture(lm, golden_dir):
     assert np.max(np.abs(fm - g["final_mass"])[ok] / g["final_mass"][ok]) < 1e-7
 
 
+@pytest.mark.parametrize("kernel", ["auto", "thread"])
+def test_config4_slice_matches_oracle_fixture(lm, golden_dir, kernel):
+    """The DEFAULT path (the reference's objective with DCOST = 1e-5, six dispersed parameters -- config 4's draws) on
+    a 512-problem slice, every problem against the oracle's own solve of it with the move term as slack pairs
+    (tests/golden/make_golden.py --config4): once with the kernel the library picks for this size (cooperative, batch
+    warm start) and once on the thread-per-problem kernel that config 4 itself runs on."""
+    g = np.load(os.path.join(golden_dir, "elliptical_config4_dcost_disp512_seed11_nt200.npz"))
+    B = g["tf"].size
+    p = lm.dispersed_params(B, seed=11)
+    assert np.array_equal(p.rows(B).numpy(), g["rows"])
+    sol = lm.optimise_batch(p, options=lm.SolverOptions(kernel=kernel))
+    assert bool(sol.converged.all())
+    ok = g["kkt"] < 1e-9
+    assert ok.mean() > 0.99, ok.mean()
+    tf = sol.tf.cpu().numpy(); fm = sol.final_mass.cpu().numpy()
+    assert np.max(np.abs(tf - g["tf"])[ok] / g["tf"][ok]) < 1e-7
+    assert np.max(np.abs(fm - g["final_mass"])[ok] / g["final_mass"][ok]) < 1e-7
+    full = _traj(sol).transpose(1, 0, 2)
+    scale = np.abs(full).max(axis=2, keepdims=True) + 1e-300
+    err = (np.abs(full[:, :, g["nodes"]] - g["traj"]) / scale).max(axis=2)     # [B, 10]
+    assert err[ok][:, :9].max() < STATE_RTOL, err[ok][:, :9].max(axis=0)
+    assert np.quantile(err[ok][:, 9], 0.99) < 5e-3, np.quantile(err[ok][:, 9], 0.99)   # the MV, see CONTROL_RTOL
+
+
 def _defects(lm, p, sol, nt):
     """Recompute the backward-Euler defects and terminal rows from the returned arrays."""
     rows = p.rows(len(sol))
